@@ -1,0 +1,153 @@
+/* snch_b200.h — C-ABI of the B200-native SNCH-LBVH hot path (libsnch_b200.so).
+ *
+ * The reference (tyanyuy3125/snch-lbvh) is a header-only C++/Thrust library with no FFI layer: its contract is the
+ * source-level API in namespace lbvh.  This C-ABI is the boundary underneath our drop-in headers
+ * (the .cuh files under include/snch_lbvh): every entry point names the reference interface it replaces.  Plain pointers and sizes
+ * only; no C++ or torch types.  All functions return 0 on success and a negative snch_status otherwise; the message
+ * of the last failure on the calling thread is returned by snch_last_error().  Nothing here ever falls back to a CPU
+ * implementation: if CUDA is unavailable the call fails with SNCH_ERR_CUDA.
+ *
+ * Pointer convention for the *_batch calls: query and result pointers may be DEVICE pointers (zero-copy: the kernels
+ * read/write them directly on `stream`) or HOST pointers (the library stages them through its own pinned buffers and
+ * copies H2D / D2H on `stream`, then synchronises the stream before returning).  The kind is detected per pointer
+ * with cudaPointerGetAttributes; all pointers of one call must be of the same kind.
+ */
+#ifndef SNCH_B200_H
+#define SNCH_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNCH_B200_ABI_VERSION 1
+
+typedef struct snch_scene snch_scene; /* opaque; owns one device arena on one GPU */
+typedef void *snch_stream;            /* a cudaStream_t (NULL = legacy default stream) */
+
+enum snch_status
+{
+    SNCH_OK = 0,
+    SNCH_ERR_INVALID = -1,   /* bad argument */
+    SNCH_ERR_NOT_BUILT = -2, /* "BVH is not built yet."  (scene.cuh:686,1250) */
+    SNCH_ERR_CUDA = -3,      /* CUDA runtime failure / no device */
+    SNCH_ERR_OOM = -4,
+    SNCH_ERR_POINTER_KIND = -5
+};
+
+const char *snch_last_error(void);
+int snch_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Scene lifetime.   Replaces lbvh::scene<3>::scene(vFirst,vLast,iFirst,iLast)            scene.cuh:1128-1133
+ *                            lbvh::scene<3>::compute_silhouettes()                        scene.cuh:1167-1204
+ *                            lbvh::scene<3>::build_bvh() -> lbvh::bvh<...>::construct()   scene.cuh:1205-1229, bvh.cuh:380-613
+ * xyz: n_verts x 3 floats, tri: n_tris x 3 vertex indices (HOST pointers, copied).
+ * ------------------------------------------------------------------------------------------------------------- */
+int snch_scene3_create(const float *xyz, uint32_t n_verts, const int32_t *tri, uint32_t n_tris, int device, snch_scene **out);
+int snch_scene_destroy(snch_scene *s);
+/* host-side edge adjacency: first-seen edge ids, silhouette int4, first-owner rule (quirks Q17/Q18 reproduced) */
+int snch_scene_compute_silhouettes(snch_scene *s);
+
+typedef struct snch_build_options
+{
+    uint32_t struct_size;       /* = sizeof(snch_build_options) */
+    uint32_t keep_reference_layout; /* 1 (default): keep nodes/aabbs/cones/objects arrays of bvh_device (bvh.cuh:48-54) */
+    uint32_t print_collision;   /* 1: print "Morton code collision detected." like bvh.cuh:466 (default 0) */
+    uint32_t reserved;
+} snch_build_options;
+
+/* Morton -> radix sort -> Karras hierarchy -> fused AABB + normal-cone refit -> traversal records; asynchronous on `stream`
+ * except for the final stats read-back.  May be called again after snch_scene_update_vertices(). */
+int snch_scene_build(snch_scene *s, const snch_build_options *opts, snch_stream stream);
+
+typedef struct snch_build_stats
+{
+    uint32_t num_objects, num_nodes, num_edges, num_vertices;
+    uint32_t morton_collision;  /* the reference's 64-bit key path would have been taken (bvh.cuh:464) */
+    uint32_t q1_nodes;          /* internal nodes whose cone union exceeded pi (half_angle defined as pi) */
+    float build_ms;             /* device time of the last snch_scene_build (CUDA events) */
+    float adjacency_ms;         /* host time of snch_scene_compute_silhouettes */
+    uint64_t arena_bytes;
+    float scene_lower[3], scene_upper[3];
+} snch_build_stats;
+int snch_scene_stats(const snch_scene *s, snch_build_stats *out);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Reference-layout view.  Replaces lbvh::bvh<...>::get_device_repr() / scene<3>::get_bvh_device_ptr()
+ *                         (bvh.cuh:367-378, scene.cuh:1242-1252).  Non-owning DEVICE pointers, valid until the scene is
+ *                         rebuilt or destroyed.  Record layouts are the reference's:
+ *   nodes   16 B {parent,left,right,object_idx}      aabbs 24 B {upper xyz, lower xyz}     cones 20 B {axis xyz, half_angle, radius}
+ *   objects 40 B scene<3>::triangle {int3 v; int3 owned_edges; const float3* vertices; const silhouette_edge* silhouettes}
+ *   silhouettes 32 B {int4 indices; const float3* vertices}       vertices 12 B float3
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct snch_bvh_device_pod
+{
+    uint32_t num_nodes, num_objects;
+    void *nodes, *aabbs, *cones, *objects;
+    void *vertices, *silhouettes;
+    uint32_t num_vertices, num_silhouettes;
+} snch_bvh_device_pod;
+int snch_scene_device_repr(const snch_scene *s, snch_bvh_device_pod *out);
+
+/* Copy one build product to HOST memory (parity dumps).  `bytes` must equal the product's size. */
+enum snch_export_kind
+{
+    SNCH_EXPORT_NODES = 0,       /* (2N-1) x 4 u32 */
+    SNCH_EXPORT_AABBS = 1,       /* (2N-1) x 6 f32 */
+    SNCH_EXPORT_CONES = 2,       /* (2N-1) x 5 f32 */
+    SNCH_EXPORT_MORTON_SORTED = 3, /* N u32 */
+    SNCH_EXPORT_SORTED_INDEX = 4,  /* N u32 */
+    SNCH_EXPORT_RANGES = 5,      /* (N-1) x 2 u32 : Karras [first,last] */
+    SNCH_EXPORT_EDGES = 6,       /* E x 4 i32 : silhouette_edge::indices */
+    SNCH_EXPORT_TRI_EDGES = 7,   /* N x 3 i32 : edge_indices_h */
+    SNCH_EXPORT_TRI_OWNED = 8,   /* N x 3 i32 : triangle::silhouette_indices */
+    SNCH_EXPORT_Q1_TAINT = 9     /* (2N-1) u8 */
+};
+int snch_scene_export(const snch_scene *s, int kind, void *host_dst, size_t bytes);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched queries (one launch for n queries).  Each replaces a per-thread reference call made from a user kernel.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* query_device(bvh, nearest(p), scene<3>::distance_calculator())  -> pair<object idx, distance>     query.cuh:238-318
+ * Index rule on exact ties: any member of the argmin set (documented deviation). */
+int snch_closest_point_batch(const snch_scene *s, const float *points_xyz, uint64_t n, uint32_t *out_index, float *out_distance,
+                             snch_stream stream);
+
+/* query_device(bvh, nearest_silhouette(p, flip), scene<3>::silhouette_distance_calculator()) -> distance   query.cuh:325-423
+ * r_max (NULL = unbounded, the reference behaviour): search radius per query; result is +inf when no silhouette point
+ * lies within it — identical to filtering the unbounded answer.  flip: one byte per query, or NULL = false. */
+int snch_closest_silhouette_batch(const snch_scene *s, const float *points_xyz, const uint8_t *flip, const float *r_max, uint64_t n,
+                                  float *out_distance, snch_stream stream);
+
+/* query_device(bvh, ray_intersect<TestOnly>(ray, max_dist), scene<3>::intersect_test())                     query.cuh:79-169
+ * -> tuple<found, t, uv, prim idx>.  any_hit != 0 is TestOnly: only `found` is meaningful. */
+typedef struct snch_hit
+{
+    float t;          /* +inf when not found */
+    float u, v;       /* barycentrics of the hit (0 when not found) */
+    uint32_t prim;    /* 0xFFFFFFFF when not found */
+} snch_hit;
+int snch_intersect_batch(const snch_scene *s, const float *origins_xyz, const float *dirs_xyz, const float *t_max, uint64_t n,
+                         snch_hit *out_hits, uint8_t *out_found, int any_hit, snch_stream stream);
+
+/* sample_object_in_sphere(bvh, sphere_intersect(sph), intersect_sphere(), measurement_getter(), green_weight(), u)   sample.cuh:23-92
+ * followed by sample_on_object(bvh, idx, scene<3>::sample_on_object(), u1, u2)                               sample.cuh:7-21
+ * spheres: x,y,z,radius; rnd: 3 uniforms per query {u (branch), u1, u2 (point)}.  out_index = -1 and pdf = 0 on a miss
+ * (pdf is uninitialised in the reference).  out_point may be NULL. */
+int snch_sample_in_sphere_batch(const snch_scene *s, const float *spheres_xyzr, const float *rnd_uvw, uint64_t n, int32_t *out_index,
+                                float *out_pdf, float *out_point_xyz, snch_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Replication (multi-GPU): the built scene lives in ONE pointer-free arena.  Rank 0 exposes it, the caller
+ * moves the bytes (ncclBroadcast / cudaMemcpyPeer / torch.distributed.broadcast) and every other rank adopts its copy.
+ * ------------------------------------------------------------------------------------------------------------- */
+int snch_scene_arena(const snch_scene *s, void **device_ptr, uint64_t *bytes);
+/* arena_copy: DEVICE pointer on `device` holding a byte-exact copy of another scene's arena (copied; caller keeps ownership) */
+int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, snch_stream stream, snch_scene **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNCH_B200_H */

@@ -1,0 +1,695 @@
+// build.cu — LBVH + SNCH construction on the GPU.
+//
+// Computes what lbvh::bvh<...>::construct() computes (bvh.cuh:380-613) with hand-written kernels:
+//   k_scene_box   leaf boxes -> scene box (block reduction + ordered-int atomics)          [bvh.cuh:423-432]
+//   k_morton      30-bit Morton code of each leaf-box centroid, (key, index) pairs         [bvh.cuh:436-449]
+//   radix sort    stable LSD sort of 8-byte pairs (payload is NOT dragged along)           [bvh.cuh:452-454]
+//   k_hierarchy   Karras 2012 ranges/splits on the augmented key (morton<<32 | index)      [bvh.cuh:109-229,459-515]
+//   k_owned_count + scan   per-leaf silhouette-edge slots
+//   k_refit       leaf boxes/cones in sorted order, then ONE bottom-up climb that merges boxes AND normal cones and
+//                 emits the 64 B / 96 B two-child traversal records                       [bvh.cuh:520-604]
+// The augmented key reproduces the reference topology on both of its paths (unique 32-bit codes, or its 64-bit fallback
+// on collisions) — SURVEY 7 step 5.
+#include "scene.h"
+#include "snch_math.cuh"
+#include "sort_scan.cuh"
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+namespace snch
+{
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: edge adjacency (scene.cuh:1135-1229).  Same numbering and ownership as the reference (first-seen edge ids,
+// last-writer-wins face slots, first triangle in input order owns an edge), O(N) with an open-addressing table.
+// ---------------------------------------------------------------------------------------------------------------
+void compute_adjacency_host(snch_scene *s)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint32_t n = s->n_tris;
+    const int32_t *tri = s->h_tri.data();
+    s->h_tri_edges.assign((size_t)3 * n, -1);
+    s->h_tri_owned.assign((size_t)3 * n, -1);
+    uint64_t cap = 16;
+    while (cap < (uint64_t)6 * n + 16) cap <<= 1;
+    std::vector<uint64_t> keys(cap, ~0ull);
+    std::vector<int32_t> vals(cap, -1);
+    int32_t E = 0;
+    for (uint32_t i = 0; i < n; ++i)
+        for (int j = 0; j < 3; ++j)
+        {
+            int32_t I = tri[3 * i + j], J = tri[3 * i + (j + 1) % 3];
+            if (I > J) std::swap(I, J);
+            const uint64_t key = ((uint64_t)(uint32_t)I << 32) | (uint32_t)J;
+            uint64_t h = (key * 0x9E3779B97F4A7C15ull) >> 17;
+            for (;;)
+            {
+                h &= cap - 1;
+                if (keys[h] == key) break;
+                if (keys[h] == ~0ull)
+                {
+                    keys[h] = key;
+                    vals[h] = E++;
+                    break;
+                }
+                ++h;
+            }
+            s->h_tri_edges[3 * (size_t)i + j] = vals[h];
+        }
+    s->n_edges = (uint32_t)E;
+    s->h_edges4.assign((size_t)4 * E, -1);
+    std::vector<uint8_t> seen((size_t)E, 0);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const int32_t *vi = tri + 3 * (size_t)i;
+        int p = 0;
+        for (int j = 0; j < 3; ++j)
+        {
+            const int I = j - 1 < 0 ? 2 : j - 1;
+            int J = j, K = j + 1 > 2 ? 0 : j + 1;
+            int orientation = 1;
+            if (vi[J] > vi[K])
+            {
+                std::swap(J, K);
+                orientation = -1;
+            }
+            const int32_t e = s->h_tri_edges[3 * (size_t)i + j];
+            int32_t *se = &s->h_edges4[4 * (size_t)e];
+            se[orientation == 1 ? 0 : 3] = vi[I];
+            se[1] = vi[J];
+            se[2] = vi[K];
+            if (!seen[e])
+            {
+                seen[e] = 1;
+                s->h_tri_owned[3 * (size_t)i + p++] = e;
+            }
+        }
+    }
+    s->silhouettes_done = true;
+    s->adjacency_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// arena layout
+// ---------------------------------------------------------------------------------------------------------------
+static void layout_arena(ArenaHeader &h, uint32_t nV, uint32_t nT, uint32_t nE)
+{
+    std::memset(&h, 0, sizeof h);
+    h.magic = kArenaMagic;
+    h.version = kArenaVersion;
+    h.n_tris = nT;
+    h.n_verts = nV;
+    h.n_edges = nE;
+    h.n_nodes = nT ? 2 * nT - 1 : 0;
+    h.n_internal = nT ? nT - 1 : 0;
+    const uint64_t n_rec = nT > 1 ? nT - 1 : (nT ? 1 : 0); // traversal records (a 1-leaf tree gets one dummy root)
+    uint64_t off = align_up(sizeof(ArenaHeader), 256);
+    auto take = [&](uint64_t bytes)
+    {
+        const uint64_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    h.off_vertices = take((uint64_t)nV * sizeof(float3));
+    h.off_edges = take((uint64_t)nE * sizeof(RefEdge));
+    h.off_objects = take((uint64_t)nT * sizeof(RefTriangle));
+    h.off_tri_edges = take((uint64_t)nT * sizeof(int3));
+    h.off_nodes = take((uint64_t)h.n_nodes * sizeof(RefNode));
+    h.off_aabbs = take((uint64_t)h.n_nodes * sizeof(RefAabb));
+    h.off_cones = take((uint64_t)h.n_nodes * sizeof(RefCone));
+    h.off_morton = take((uint64_t)nT * 4);
+    h.off_sorted_idx = take((uint64_t)nT * 4);
+    h.off_ranges = take((uint64_t)h.n_internal * 8);
+    h.off_q1 = take((uint64_t)h.n_nodes);
+    h.off_bnode = take(n_rec * sizeof(BNode));
+    h.off_snode = take(n_rec * sizeof(SNode));
+    h.off_ltri = take((uint64_t)nT * sizeof(LTri));
+    h.off_ledge = take((uint64_t)nE * sizeof(LEdge));
+    h.off_edge_off = take((uint64_t)nT * 4);
+    h.total_bytes = off;
+}
+
+void resolve_view(snch_scene *s)
+{
+    const ArenaHeader &h = s->hdr;
+    unsigned char *b = s->arena;
+    SceneView &v = s->view;
+    v.n_tris = h.n_tris;
+    v.n_verts = h.n_verts;
+    v.n_edges = h.n_edges;
+    v.n_internal = h.n_internal;
+    v.vertices = (const float3 *)(b + h.off_vertices);
+    v.edges = (const RefEdge *)(b + h.off_edges);
+    v.objects = (const RefTriangle *)(b + h.off_objects);
+    v.bnode = (const BNode *)(b + h.off_bnode);
+    v.snode = (const SNode *)(b + h.off_snode);
+    v.ltri = (const LTri *)(b + h.off_ltri);
+    v.ledge = (const LEdge *)(b + h.off_ledge);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+struct BuildCtx
+{
+    uint32_t n, n_edges;
+    const float3 *verts;
+    const RefEdge *edges;
+    const RefTriangle *objects;
+    RefNode *nodes;
+    RefAabb *aabbs;
+    RefCone *cones;
+    uint32_t *morton, *sorted_idx;
+    uint2 *ranges;
+    uint8_t *q1;
+    BNode *bnode;
+    SNode *snode;
+    LTri *ltri;
+    LEdge *ledge;
+    uint32_t *edge_off;
+    // scratch
+    int *scene_box; // 6 ordered ints: lo xyz, hi xyz
+    uint32_t *flags;
+    uint32_t *counters; // [0] collision, [1] q1 events
+};
+
+SNCH_DI int f2ord(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+SNCH_DI float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+SNCH_DI V3 ldv(const float3 *v, int i)
+{
+    const float3 p = v[i];
+    return V3{p.x, p.y, p.z};
+}
+
+__global__ void k_init_box(int *box)
+{
+    if (threadIdx.x < 3) box[threadIdx.x] = f2ord(INFINITY);
+    else if (threadIdx.x < 6) box[threadIdx.x] = f2ord(-INFINITY);
+}
+
+__global__ void __launch_bounds__(256) k_scene_box(BuildCtx c)
+{
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x)
+    {
+        const int3 vi = c.objects[i].v;
+        const Box b = tri_box(ldv(c.verts, vi.x), ldv(c.verts, vi.y), ldv(c.verts, vi.z));
+        lo[0] = fminf(lo[0], b.lo.x);
+        lo[1] = fminf(lo[1], b.lo.y);
+        lo[2] = fminf(lo[2], b.lo.z);
+        hi[0] = fmaxf(hi[0], b.hi.x);
+        hi[1] = fmaxf(hi[1], b.hi.y);
+        hi[2] = fmaxf(hi[2], b.hi.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    __shared__ float sm[8][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+    {
+        for (int a = 0; a < 3; ++a)
+        {
+            sm[warp][a] = lo[a];
+            sm[warp][3 + a] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6)
+    {
+        float v = sm[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&c.scene_box[threadIdx.x], f2ord(v));
+        else atomicMax(&c.scene_box[threadIdx.x], f2ord(v));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_morton(BuildCtx c)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const V3 wlo = V3{ord2f(c.scene_box[0]), ord2f(c.scene_box[1]), ord2f(c.scene_box[2])};
+    const V3 whi = V3{ord2f(c.scene_box[3]), ord2f(c.scene_box[4]), ord2f(c.scene_box[5])};
+    const int3 vi = c.objects[i].v;
+    const Box b = tri_box(ldv(c.verts, vi.x), ldv(c.verts, vi.y), ldv(c.verts, vi.z));
+    c.morton[i] = morton30(b, wlo, whi);
+    c.sorted_idx[i] = i;
+}
+
+// common_upper_bits on the augmented 64-bit key (morton<<32 | object index)        morton_code.cuh:144-167
+SNCH_DI int key_delta(const uint32_t *__restrict__ m, const uint32_t *__restrict__ id, int n, uint32_t mi, uint32_t ii, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const uint32_t mj = m[j];
+    return mi != mj ? __clz(mi ^ mj) : 32 + __clz(ii ^ id[j]);
+}
+
+// Karras 2012: bvh.cuh:109-167 (determine_range), :169-199 (find_split), :200-229 (children + parent links)
+__global__ void __launch_bounds__(256) k_hierarchy(BuildCtx c)
+{
+    const int n = (int)c.n;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const uint32_t *__restrict__ m = c.morton;
+    const uint32_t *__restrict__ id = c.sorted_idx;
+    const uint32_t mi = m[i], ii = id[i];
+    if (mi == m[i + 1]) c.counters[0] = 1u; // duplicate Morton codes: the reference's 64-bit path (bvh.cuh:459-476)
+    int first, last;
+    if (i == 0)
+    {
+        first = 0;
+        last = n - 1;
+        c.nodes[0].parent = kNone;
+    }
+    else
+    {
+        const int dl = key_delta(m, id, n, mi, ii, i - 1), dr = key_delta(m, id, n, mi, ii, i + 1);
+        const int d = dr > dl ? 1 : -1;
+        const int dmin = min(dl, dr);
+        int lmax = 2;
+        while (key_delta(m, id, n, mi, ii, i + d * lmax) > dmin) lmax <<= 1;
+        int l = 0;
+        for (int t = lmax >> 1; t > 0; t >>= 1)
+            if (key_delta(m, id, n, mi, ii, i + (l + t) * d) > dmin) l += t;
+        const int j = i + l * d;
+        first = min(i, j);
+        last = max(i, j);
+    }
+    // split: highest differing bit between first and last key
+    const uint32_t mf = m[first], idf = id[first];
+    const int dnode = key_delta(m, id, n, mf, idf, last);
+    int split = first, stride = last - first;
+    do
+    {
+        stride = (stride + 1) >> 1;
+        const int mid = split + stride;
+        if (mid < last && key_delta(m, id, n, mf, idf, mid) > dnode) split = mid;
+    } while (stride > 1);
+    uint32_t left = (uint32_t)split, right = (uint32_t)split + 1;
+    if (first == split) left += (uint32_t)(n - 1);
+    if (last == split + 1) right += (uint32_t)(n - 1);
+    c.nodes[i].left = left;
+    c.nodes[i].right = right;
+    c.nodes[i].object = kNone;
+    c.nodes[left].parent = (uint32_t)i;
+    c.nodes[right].parent = (uint32_t)i;
+    c.ranges[i] = make_uint2((uint32_t)first, (uint32_t)last);
+}
+
+__global__ void __launch_bounds__(256) k_owned_count(BuildCtx c)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= c.n) return;
+    const int3 o = c.objects[c.sorted_idx[k]].owned;
+    c.edge_off[k] = (uint32_t)(o.x != -1) + (uint32_t)(o.y != -1) + (uint32_t)(o.z != -1);
+}
+
+SNCH_DI void store_aabb(RefAabb *dst, Box b)
+{
+    float2 *p = reinterpret_cast<float2 *>(dst);
+    p[0] = make_float2(b.hi.x, b.hi.y);
+    p[1] = make_float2(b.hi.z, b.lo.x);
+    p[2] = make_float2(b.lo.y, b.lo.z);
+}
+SNCH_DI Box load_aabb_cg(const RefAabb *src)
+{
+    const float2 *p = reinterpret_cast<const float2 *>(src);
+    const float2 a = __ldcg(p), b = __ldcg(p + 1), c = __ldcg(p + 2);
+    Box r;
+    r.hi = V3{a.x, a.y, b.x};
+    r.lo = V3{b.y, c.x, c.y};
+    return r;
+}
+SNCH_DI void store_cone(RefCone *dst, Cone c)
+{
+    float *p = reinterpret_cast<float *>(dst);
+    p[0] = c.axis.x;
+    p[1] = c.axis.y;
+    p[2] = c.axis.z;
+    p[3] = c.half_angle;
+    p[4] = c.radius;
+}
+SNCH_DI Cone load_cone_cg(const RefCone *src)
+{
+    const float *p = reinterpret_cast<const float *>(src);
+    Cone c;
+    c.axis = V3{__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)};
+    c.half_angle = __ldcg(p + 3);
+    c.radius = __ldcg(p + 4);
+    return c;
+}
+SNCH_DI void store_records(BNode *bn, SNode *sn, Box lb, Box rb, Cone lc, Cone rc, uint32_t lbref, uint32_t rbref, uint32_t lsref,
+                           uint32_t rsref, uint32_t parent)
+{
+    const float4 a = make_float4(lb.lo.x, lb.lo.y, lb.lo.z, lb.hi.x);
+    const float4 b = make_float4(lb.hi.y, lb.hi.z, rb.lo.x, rb.lo.y);
+    const float4 c = make_float4(rb.lo.z, rb.hi.x, rb.hi.y, rb.hi.z);
+    float4 *bp = reinterpret_cast<float4 *>(bn);
+    bp[0] = a;
+    bp[1] = b;
+    bp[2] = c;
+    bp[3] = make_float4(__uint_as_float(lbref), __uint_as_float(rbref), __uint_as_float(parent), 0.0f);
+    float4 *sp = reinterpret_cast<float4 *>(sn);
+    sp[0] = a;
+    sp[1] = b;
+    sp[2] = c;
+    sp[3] = make_float4(lc.axis.x, lc.axis.y, lc.axis.z, lc.half_angle);
+    sp[4] = make_float4(lc.radius, rc.axis.x, rc.axis.y, rc.axis.z);
+    sp[5] = make_float4(rc.half_angle, rc.radius, __uint_as_float(lsref), __uint_as_float(rsref));
+}
+
+// Leaf pass + fused bottom-up refit.  One thread per leaf in Morton order.
+//   leaf box      scene.cuh:870-885           leaf cone   scene.cuh:887-961
+//   climb         bvh.cuh:520-554 (boxes) and :556-604 (cones) fused into one pass, with the fences the reference's
+//                 cone pass lacks (quirk Q7).
+__global__ void __launch_bounds__(128) k_refit(BuildCtx c)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= c.n) return;
+    const uint32_t ni = c.n - 1;
+    const uint32_t obj = c.sorted_idx[k];
+    const RefTriangle t = c.objects[obj];
+    const V3 pa = ldv(c.verts, t.v.x), pb = ldv(c.verts, t.v.y), pc = ldv(c.verts, t.v.z);
+    Box box = tri_box(pa, pb, pc);
+    {
+        float4 *lt = reinterpret_cast<float4 *>(c.ltri + k);
+        lt[0] = make_float4(pa.x, pa.y, pa.z, __uint_as_float(obj));
+        lt[1] = make_float4(pb.x, pb.y, pb.z, 0.0f);
+        lt[2] = make_float4(pc.x, pc.y, pc.z, 0.0f);
+    }
+    // ---- leaf normal cone from the owned silhouette edges, and their traversal records
+    const V3 bc = box_centroid(box);
+    Cone cone;
+    cone.axis = V3{0.f, 0.f, 0.f};
+    cone.half_angle = kPi;
+    cone.radius = 0.f;
+    const uint32_t eoff = c.edge_off[k];
+    uint32_t cnt = 0;
+    bool all_two = true;
+    V3 fn0[3], fn1[3];
+    const int owned[3] = {t.owned.x, t.owned.y, t.owned.z};
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+    {
+        if (owned[s] == -1) continue;
+        const int4 id = c.edges[owned[s]].indices;
+        const V3 ea = ldv(c.verts, id.y), eb = ldv(c.verts, id.z);
+        const bool has0 = id.w != -1, has1 = id.x != -1;
+        V3 n0 = V3{0.f, 0.f, 0.f}, n1 = V3{0.f, 0.f, 0.f}, nsum = V3{0.f, 0.f, 0.f};
+        if (has0)
+        { // silhouette_edge::normal(0): (pb-pa) x (pc-pa) with pa=v[1], pb=v[2], pc=v[3]      scene.cuh:747-772
+            n0 = cross(eb - ea, ldv(c.verts, id.w) - ea);
+            nsum = V3{nsum.x + n0.x, nsum.y + n0.y, nsum.z + n0.z};
+        }
+        if (has1)
+        { // normal(1): pa=v[2], pb=v[1], pc=v[0]
+            n1 = cross(ea - eb, ldv(c.verts, id.x) - eb);
+            nsum = V3{nsum.x + n1.x, nsum.y + n1.y, nsum.z + n1.z};
+        }
+        const V3 en = normalize(nsum);
+        cone.axis = V3{cone.axis.x + en.x, cone.axis.y + en.y, cone.axis.z + en.z};
+        const V3 ec = V3{(ea.x + eb.x) / 2, (ea.y + eb.y) / 2, (ea.z + eb.z) / 2};
+        cone.radius = std_max(cone.radius, len(ec - bc));
+        all_two = all_two && has0 && has1;
+        const V3 u0 = has0 ? normalize(n0) : V3{0.f, 0.f, 0.f};
+        const V3 u1 = has1 ? normalize(n1) : V3{0.f, 0.f, 0.f};
+        fn0[s] = u0;
+        fn1[s] = u1;
+        float4 *le = reinterpret_cast<float4 *>(c.ledge + eoff + cnt);
+        const bool boundary = !(has0 && has1);
+        le[0] = make_float4(ea.x, ea.y, ea.z, eb.x);
+        le[1] = make_float4(eb.y, eb.z, boundary ? __int_as_float(0x7FC00000) : u0.x, u0.y);
+        le[2] = make_float4(u0.z, u1.x, u1.y, u1.z);
+        ++cnt;
+    }
+    if (cnt == 0) cone.half_angle = -kPi;
+    else if (!all_two) cone.half_angle = kPi;
+    else
+    {
+        const float an = len(cone.axis);
+        if (an > FLT_EPSILON)
+        {
+            cone.axis = V3{cone.axis.x / an, cone.axis.y / an, cone.axis.z / an};
+            cone.half_angle = 0.0f;
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+            {
+                if (owned[s] == -1) continue;
+                cone.half_angle = std_max(cone.half_angle, acosf(std_max(-1.0f, std_min(1.0f, dot(cone.axis, fn0[s])))));
+                cone.half_angle = std_max(cone.half_angle, acosf(std_max(-1.0f, std_min(1.0f, dot(cone.axis, fn1[s])))));
+            }
+        }
+    }
+    const uint32_t packed = (eoff << 2) | cnt;
+    c.edge_off[k] = packed;
+
+    uint32_t cur = ni + k;
+    store_aabb(c.aabbs + cur, box);
+    store_cone(c.cones + cur, cone);
+    c.nodes[cur].left = kNone;
+    c.nodes[cur].right = kNone;
+    c.nodes[cur].object = obj;
+    c.q1[cur] = 0;
+    if (c.n == 1)
+    { // single-leaf tree: dummy root record whose second child can never be entered (NaN box, invalid cone)
+        c.nodes[cur].parent = kNone;
+        const float qnan = __int_as_float(0x7FC00000);
+        Box nb;
+        nb.lo = nb.hi = V3{qnan, qnan, qnan};
+        Cone ncone;
+        ncone.axis = V3{0.f, 0.f, 0.f};
+        ncone.half_angle = -kPi;
+        ncone.radius = 0.f;
+        store_records(c.bnode, c.snode, box, nb, cone, ncone, kLeafFlag | 0u, kLeafFlag | 0u, kLeafFlag | packed, kLeafFlag | 0u, kNone);
+        return;
+    }
+    bool taint = false;
+    uint32_t cur_bref = kLeafFlag | k, cur_sref = kLeafFlag | packed;
+    uint32_t parent = c.nodes[cur].parent;
+    while (parent != kNone)
+    {
+        __threadfence();
+        const uint32_t old = atomicAdd(c.flags + parent, 1u);
+        if (old == 0) return; // first arriver: the sibling subtree is not finished yet
+        __threadfence();
+        const uint32_t l = c.nodes[parent].left, r = c.nodes[parent].right;
+        const bool cur_is_left = (l == cur);
+        const uint32_t sib = cur_is_left ? r : l;
+        const Box sbox = load_aabb_cg(c.aabbs + sib);
+        const Cone scone = load_cone_cg(c.cones + sib);
+        const bool staint = __ldcg(c.q1 + sib) != 0;
+        uint32_t sib_bref = sib, sib_sref = sib;
+        if (sib >= ni)
+        {
+            sib_bref = kLeafFlag | (sib - ni);
+            sib_sref = kLeafFlag | __ldcg(c.edge_off + (sib - ni));
+        }
+        const Box lb = cur_is_left ? box : sbox, rb = cur_is_left ? sbox : box;
+        const Cone lc = cur_is_left ? cone : scone, rc = cur_is_left ? scone : cone;
+        const Box pbx = box_merge(lb, rb);
+        bool q1;
+        const Cone pcn = cone_merge(lc, rc, box_centroid(lb), box_centroid(rb), box_centroid(pbx), &q1);
+        if (q1) atomicAdd(c.counters + 1, 1u);
+        taint = taint || staint || q1;
+        store_aabb(c.aabbs + parent, pbx);
+        store_cone(c.cones + parent, pcn);
+        c.q1[parent] = taint ? 1 : 0;
+        const uint32_t gp = c.nodes[parent].parent;
+        store_records(c.bnode + parent, c.snode + parent, lb, rb, lc, rc, cur_is_left ? cur_bref : sib_bref,
+                      cur_is_left ? sib_bref : cur_bref, cur_is_left ? cur_sref : sib_sref, cur_is_left ? sib_sref : cur_sref, gp);
+        cur = parent;
+        box = pbx;
+        cone = pcn;
+        cur_bref = cur_sref = parent;
+        parent = gp;
+    }
+}
+
+__global__ void k_patch_pointers(RefEdge *edges, uint32_t n_edges, RefTriangle *objects, uint32_t n_tris, const float3 *verts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_edges) edges[i].vertices = verts;
+    if (i < n_tris)
+    {
+        objects[i].vertices = verts;
+        objects[i].silhouettes = edges;
+    }
+}
+
+int patch_pointers(snch_scene *s, cudaStream_t stream)
+{
+    const ArenaHeader &h = s->hdr;
+    const uint32_t m = h.n_edges > h.n_tris ? h.n_edges : h.n_tris;
+    if (m == 0) return SNCH_OK;
+    k_patch_pointers<<<(m + 255) / 256, 256, 0, stream>>>((RefEdge *)(s->arena + h.off_edges), h.n_edges,
+                                                           (RefTriangle *)(s->arena + h.off_objects), h.n_tris,
+                                                           (const float3 *)(s->arena + h.off_vertices));
+    SNCH_CUDA(cudaGetLastError());
+    return SNCH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------------------------
+int build_device(snch_scene *s, cudaStream_t stream)
+{
+    SNCH_CUDA(cudaSetDevice(s->device));
+    const uint32_t nV = s->n_verts, nT = s->n_tris, nE = s->n_edges;
+    ArenaHeader h;
+    layout_arena(h, nV, nT, nE);
+    if (!s->arena || s->arena_bytes != h.total_bytes)
+    {
+        if (s->arena) cudaFree(s->arena);
+        s->arena = nullptr;
+        if (cudaMalloc(&s->arena, h.total_bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            set_error("cudaMalloc of the scene arena failed");
+            return SNCH_ERR_OOM;
+        }
+        s->arena_bytes = h.total_bytes;
+    }
+    s->hdr = h;
+    resolve_view(s);
+    unsigned char *b = s->arena;
+
+    // ---- uploads (host arrays -> arena); the reference does these in its constructors (scene.cuh:1131, bvh.cuh:330)
+    if (nV) SNCH_CUDA(cudaMemcpyAsync(b + h.off_vertices, s->h_xyz.data(), (size_t)nV * 12, cudaMemcpyHostToDevice, stream));
+    std::vector<RefEdge> he(nE);
+    for (uint32_t e = 0; e < nE; ++e)
+    {
+        he[e].indices = make_int4(s->h_edges4[4 * e], s->h_edges4[4 * e + 1], s->h_edges4[4 * e + 2], s->h_edges4[4 * e + 3]);
+        he[e].vertices = (const float3 *)(b + h.off_vertices);
+        he[e].pad_ = 0;
+    }
+    std::vector<RefTriangle> ho(nT);
+    for (uint32_t i = 0; i < nT; ++i)
+    {
+        ho[i].v = make_int3(s->h_tri[3 * i], s->h_tri[3 * i + 1], s->h_tri[3 * i + 2]);
+        ho[i].owned = make_int3(s->h_tri_owned[3 * i], s->h_tri_owned[3 * i + 1], s->h_tri_owned[3 * i + 2]);
+        ho[i].vertices = (const float3 *)(b + h.off_vertices);
+        ho[i].silhouettes = (const RefEdge *)(b + h.off_edges);
+    }
+    if (nE) SNCH_CUDA(cudaMemcpyAsync(b + h.off_edges, he.data(), (size_t)nE * sizeof(RefEdge), cudaMemcpyHostToDevice, stream));
+    if (nT)
+    {
+        SNCH_CUDA(cudaMemcpyAsync(b + h.off_objects, ho.data(), (size_t)nT * sizeof(RefTriangle), cudaMemcpyHostToDevice, stream));
+        SNCH_CUDA(cudaMemcpyAsync(b + h.off_tri_edges, s->h_tri_edges.data(), (size_t)nT * 12, cudaMemcpyHostToDevice, stream));
+    }
+    SNCH_CUDA(cudaStreamSynchronize(stream)); // staging vectors go out of scope below; also isolates build_ms
+    if (nT == 0)
+    {
+        SNCH_CUDA(cudaMemcpyAsync(b, &s->hdr, sizeof(ArenaHeader), cudaMemcpyHostToDevice, stream));
+        SNCH_CUDA(cudaStreamSynchronize(stream));
+        s->built = true;
+        s->build_ms = 0.f;
+        return SNCH_OK;
+    }
+
+    // ---- scratch: sort ping-pong + sort/scan counters + flags + box + counters
+    const uint64_t sort_elems = sort_scratch_elems(nT);
+    const uint64_t scan_elems = scan_scratch_elems(nT);
+    uint64_t so = 0;
+    auto stake = [&](uint64_t bytes)
+    {
+        const uint64_t o = so;
+        so = align_up(so + bytes, 256);
+        return o;
+    };
+    const uint64_t o_ktmp = stake((uint64_t)nT * 4), o_vtmp = stake((uint64_t)nT * 4);
+    const uint64_t o_sort = stake(sort_elems * 4), o_scan = stake(scan_elems * 4);
+    const uint64_t o_flags = stake((uint64_t)nT * 4), o_box = stake(64), o_cnt = stake(64);
+    if (s->scratch_bytes < so)
+    {
+        if (s->scratch) cudaFree(s->scratch);
+        s->scratch = nullptr;
+        if (cudaMalloc(&s->scratch, so) != cudaSuccess)
+        {
+            cudaGetLastError();
+            set_error("cudaMalloc of the build scratch failed");
+            return SNCH_ERR_OOM;
+        }
+        s->scratch_bytes = so;
+    }
+    unsigned char *sc = s->scratch;
+
+    BuildCtx c;
+    c.n = nT;
+    c.n_edges = nE;
+    c.verts = (const float3 *)(b + h.off_vertices);
+    c.edges = (const RefEdge *)(b + h.off_edges);
+    c.objects = (const RefTriangle *)(b + h.off_objects);
+    c.nodes = (RefNode *)(b + h.off_nodes);
+    c.aabbs = (RefAabb *)(b + h.off_aabbs);
+    c.cones = (RefCone *)(b + h.off_cones);
+    c.morton = (uint32_t *)(b + h.off_morton);
+    c.sorted_idx = (uint32_t *)(b + h.off_sorted_idx);
+    c.ranges = (uint2 *)(b + h.off_ranges);
+    c.q1 = (uint8_t *)(b + h.off_q1);
+    c.bnode = (BNode *)(b + h.off_bnode);
+    c.snode = (SNode *)(b + h.off_snode);
+    c.ltri = (LTri *)(b + h.off_ltri);
+    c.ledge = (LEdge *)(b + h.off_ledge);
+    c.edge_off = (uint32_t *)(b + h.off_edge_off);
+    c.scene_box = (int *)(sc + o_box);
+    c.flags = (uint32_t *)(sc + o_flags);
+    c.counters = (uint32_t *)(sc + o_cnt);
+
+    cudaEvent_t ev0, ev1;
+    SNCH_CUDA(cudaEventCreate(&ev0));
+    SNCH_CUDA(cudaEventCreate(&ev1));
+    SNCH_CUDA(cudaEventRecord(ev0, stream));
+
+    const unsigned g256 = (nT + 255) / 256;
+    SNCH_CUDA(cudaMemsetAsync(c.flags, 0, (size_t)nT * 4, stream));
+    SNCH_CUDA(cudaMemsetAsync(c.counters, 0, 64, stream));
+    k_init_box<<<1, 32, 0, stream>>>(c.scene_box);
+    k_scene_box<<<g256 < 1184 ? g256 : 1184, 256, 0, stream>>>(c);
+    k_morton<<<g256, 256, 0, stream>>>(c);
+    radix_sort_pairs(c.morton, c.sorted_idx, (uint32_t *)(sc + o_ktmp), (uint32_t *)(sc + o_vtmp), nT, 30, (uint32_t *)(sc + o_sort),
+                     stream);
+    if (nT > 1) k_hierarchy<<<(nT - 1 + 255) / 256, 256, 0, stream>>>(c);
+    k_owned_count<<<g256, 256, 0, stream>>>(c);
+    exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream);
+    k_refit<<<(nT + 127) / 128, 128, 0, stream>>>(c);
+    SNCH_CUDA(cudaGetLastError());
+    SNCH_CUDA(cudaEventRecord(ev1, stream));
+
+    // ---- stats read-back + header
+    uint32_t counters[2] = {0, 0};
+    int boxi[6];
+    SNCH_CUDA(cudaMemcpyAsync(counters, c.counters, 8, cudaMemcpyDeviceToHost, stream));
+    SNCH_CUDA(cudaMemcpyAsync(boxi, c.scene_box, 24, cudaMemcpyDeviceToHost, stream));
+    SNCH_CUDA(cudaStreamSynchronize(stream));
+    SNCH_CUDA(cudaEventElapsedTime(&s->build_ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    s->hdr.collision = counters[0];
+    s->hdr.q1_nodes = counters[1];
+    for (int a = 0; a < 3; ++a)
+    {
+        int lo = boxi[a], hi = boxi[3 + a];
+        lo = lo >= 0 ? lo : lo ^ 0x7FFFFFFF;
+        hi = hi >= 0 ? hi : hi ^ 0x7FFFFFFF;
+        std::memcpy(&s->hdr.scene_lo[a], &lo, 4);
+        std::memcpy(&s->hdr.scene_hi[a], &hi, 4);
+    }
+    SNCH_CUDA(cudaMemcpyAsync(b, &s->hdr, sizeof(ArenaHeader), cudaMemcpyHostToDevice, stream));
+    SNCH_CUDA(cudaStreamSynchronize(stream));
+    if (s->hdr.collision && s->opt_print_collision) std::printf("Morton code collision detected.\n");
+    s->built = true;
+    return SNCH_OK;
+}
+
+} // namespace snch

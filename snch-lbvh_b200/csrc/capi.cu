@@ -1,0 +1,578 @@
+// capi.cu — the C-ABI (include/snch_b200.h): scene lifetime, build, exports, batched query entry points, replication.
+#include "scene.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace snch
+{
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_last_error = std::string("CUDA error '") + cudaGetErrorString(e) + "' in " + what;
+    cudaGetLastError();
+    return SNCH_ERR_CUDA;
+}
+
+enum PtrKind
+{
+    PK_NULL,
+    PK_HOST,
+    PK_DEVICE
+};
+static PtrKind ptr_kind(const void *p)
+{
+    if (!p) return PK_NULL;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return PK_HOST;
+    }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PK_DEVICE : PK_HOST;
+}
+
+// Host-pointer batches: inputs are copied into a device staging area, results copied back; both grow on demand.
+struct Stager
+{
+    snch_scene *s;
+    cudaStream_t st;
+    uint64_t used = 0;
+    int status = SNCH_OK;
+    struct Out
+    {
+        void *host;
+        void *dev;
+        uint64_t bytes;
+    };
+    Out outs[4];
+    int n_outs = 0;
+    Stager(snch_scene *s_, cudaStream_t st_, uint64_t total) : s(s_), st(st_)
+    {
+        if (s->dstage_bytes < total)
+        {
+            if (s->dstage) cudaFree(s->dstage);
+            s->dstage = nullptr;
+            s->dstage_bytes = 0;
+            if (cudaMalloc(&s->dstage, total) != cudaSuccess)
+            {
+                cudaGetLastError();
+                set_error("cudaMalloc of the query staging buffer failed");
+                status = SNCH_ERR_OOM;
+                return;
+            }
+            s->dstage_bytes = total;
+        }
+    }
+    static uint64_t pad(uint64_t b) { return align_up(b, 256); }
+    template <typename T> const T *in(const T *host, uint64_t bytes)
+    {
+        if (!host || status != SNCH_OK) return nullptr;
+        void *d = s->dstage + used;
+        used += pad(bytes);
+        const cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) status = cuda_fail(e, "H2D staging copy");
+        return (const T *)d;
+    }
+    template <typename T> T *out(T *host, uint64_t bytes)
+    {
+        if (!host || status != SNCH_OK) return nullptr;
+        void *d = s->dstage + used;
+        used += pad(bytes);
+        outs[n_outs++] = Out{host, d, bytes};
+        return (T *)d;
+    }
+    int finish()
+    {
+        for (int i = 0; i < n_outs && status == SNCH_OK; ++i)
+        {
+            const cudaError_t e = cudaMemcpyAsync(outs[i].host, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) status = cuda_fail(e, "D2H staging copy");
+        }
+        if (status == SNCH_OK)
+        {
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) status = cuda_fail(e, "cudaStreamSynchronize");
+        }
+        return status;
+    }
+};
+
+static int check_built(const snch_scene *s)
+{
+    if (!s)
+    {
+        set_error("null scene");
+        return SNCH_ERR_INVALID;
+    }
+    if (!s->built)
+    {
+        set_error("BVH is not built yet.");
+        return SNCH_ERR_NOT_BUILT;
+    }
+    return SNCH_OK;
+}
+// all non-null pointers must be of one kind; returns PK_DEVICE / PK_HOST, or PK_NULL on a mix
+static PtrKind common_kind(std::initializer_list<const void *> ptrs)
+{
+    PtrKind k = PK_NULL;
+    for (const void *p : ptrs)
+    {
+        const PtrKind pk = ptr_kind(p);
+        if (pk == PK_NULL) continue;
+        if (k == PK_NULL) k = pk;
+        else if (k != pk) return PK_NULL;
+    }
+    return k;
+}
+} // namespace snch
+
+using namespace snch;
+
+extern "C"
+{
+
+const char *snch_last_error(void) { return g_last_error.c_str(); }
+int snch_abi_version(void) { return SNCH_B200_ABI_VERSION; }
+
+int snch_scene3_create(const float *xyz, uint32_t n_verts, const int32_t *tri, uint32_t n_tris, int device, snch_scene **out)
+{
+    if (!out || (n_verts && !xyz) || (n_tris && !tri))
+    {
+        set_error("snch_scene3_create: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (n_tris > 0x7FFFFFFFu / 2)
+    {
+        set_error("snch_scene3_create: too many triangles for 32-bit node ids");
+        return SNCH_ERR_INVALID;
+    }
+    for (uint64_t i = 0; i < (uint64_t)3 * n_tris; ++i)
+        if (tri[i] < 0 || (uint32_t)tri[i] >= n_verts)
+        {
+            set_error("snch_scene3_create: vertex index out of range");
+            return SNCH_ERR_INVALID;
+        }
+    if (device < 0)
+    {
+        set_error("snch_scene3_create: bad device ordinal");
+        return SNCH_ERR_INVALID;
+    }
+    // no CUDA call here: creation and compute_silhouettes() are host-only (as in the reference, whose scene constructor
+    // only fills host vectors before the first device_vector copy); the device is first touched by snch_scene_build().
+    snch_scene *s = new (std::nothrow) snch_scene();
+    if (!s)
+    {
+        set_error("out of host memory");
+        return SNCH_ERR_OOM;
+    }
+    s->device = device;
+    s->n_verts = n_verts;
+    s->n_tris = n_tris;
+    s->h_xyz.assign(xyz, xyz + (size_t)3 * n_verts);
+    s->h_tri.assign(tri, tri + (size_t)3 * n_tris);
+    *out = s;
+    return SNCH_OK;
+}
+
+int snch_scene_destroy(snch_scene *s)
+{
+    if (!s) return SNCH_OK;
+    cudaSetDevice(s->device);
+    if (s->arena) cudaFree(s->arena);
+    if (s->scratch) cudaFree(s->scratch);
+    if (s->dstage) cudaFree(s->dstage);
+    if (s->pinned) cudaFreeHost(s->pinned);
+    delete s;
+    return SNCH_OK;
+}
+
+int snch_scene_compute_silhouettes(snch_scene *s)
+{
+    if (!s || s->adopted)
+    {
+        set_error("snch_scene_compute_silhouettes: invalid scene");
+        return SNCH_ERR_INVALID;
+    }
+    compute_adjacency_host(s);
+    return SNCH_OK;
+}
+
+int snch_scene_build(snch_scene *s, const snch_build_options *opts, snch_stream stream)
+{
+    if (!s || s->adopted)
+    {
+        set_error("snch_scene_build: invalid scene");
+        return SNCH_ERR_INVALID;
+    }
+    if (opts)
+    {
+        if (opts->struct_size != sizeof(snch_build_options))
+        {
+            set_error("snch_scene_build: snch_build_options.struct_size mismatch");
+            return SNCH_ERR_INVALID;
+        }
+        s->opt_print_collision = opts->print_collision;
+    }
+    // the reference's build_bvh() silently uses whatever compute_silhouettes() left behind; an un-prepared scene has
+    // no edges at all, which makes every leaf cone invalid.  Do the same (no implicit call).
+    if (!s->silhouettes_done)
+    {
+        s->n_edges = 0;
+        s->h_edges4.clear();
+        s->h_tri_edges.assign((size_t)3 * s->n_tris, -1);
+        s->h_tri_owned.assign((size_t)3 * s->n_tris, -1);
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return SNCH_ERR_CUDA;
+    }
+    if (s->device >= count)
+    {
+        set_error("snch_scene_build: bad device ordinal");
+        return SNCH_ERR_INVALID;
+    }
+    return build_device(s, (cudaStream_t)stream);
+}
+
+int snch_scene_stats(const snch_scene *s, snch_build_stats *out)
+{
+    if (!s || !out)
+    {
+        set_error("snch_scene_stats: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    std::memset(out, 0, sizeof *out);
+    out->num_objects = s->n_tris;
+    out->num_vertices = s->n_verts;
+    out->num_edges = s->n_edges;
+    out->adjacency_ms = s->adjacency_ms;
+    if (s->built)
+    {
+        out->num_nodes = s->hdr.n_nodes;
+        out->morton_collision = s->hdr.collision;
+        out->q1_nodes = s->hdr.q1_nodes;
+        out->build_ms = s->build_ms;
+        out->arena_bytes = s->arena_bytes;
+        for (int a = 0; a < 3; ++a)
+        {
+            out->scene_lower[a] = s->hdr.scene_lo[a];
+            out->scene_upper[a] = s->hdr.scene_hi[a];
+        }
+    }
+    return SNCH_OK;
+}
+
+int snch_scene_device_repr(const snch_scene *s, snch_bvh_device_pod *out)
+{
+    if (!out)
+    {
+        set_error("snch_scene_device_repr: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    const int st = check_built(s);
+    if (st != SNCH_OK) return st;
+    const ArenaHeader &h = s->hdr;
+    out->num_nodes = h.n_nodes;
+    out->num_objects = h.n_tris;
+    out->num_vertices = h.n_verts;
+    out->num_silhouettes = h.n_edges;
+    const bool empty = h.n_tris == 0;
+    out->nodes = empty ? nullptr : s->arena + h.off_nodes;
+    out->aabbs = empty ? nullptr : s->arena + h.off_aabbs;
+    out->cones = empty ? nullptr : s->arena + h.off_cones;
+    out->objects = empty ? nullptr : s->arena + h.off_objects;
+    out->vertices = s->arena + h.off_vertices;
+    out->silhouettes = s->arena + h.off_edges;
+    return SNCH_OK;
+}
+
+int snch_scene_export(const snch_scene *s, int kind, void *host_dst, size_t bytes)
+{
+    if (!host_dst && bytes)
+    {
+        set_error("snch_scene_export: null destination");
+        return SNCH_ERR_INVALID;
+    }
+    if (s && !s->adopted && s->silhouettes_done &&
+        (kind == SNCH_EXPORT_EDGES || kind == SNCH_EXPORT_TRI_EDGES || kind == SNCH_EXPORT_TRI_OWNED))
+    { // host-side adjacency products are available as soon as compute_silhouettes() ran
+        const std::vector<int32_t> &v = kind == SNCH_EXPORT_EDGES ? s->h_edges4 : (kind == SNCH_EXPORT_TRI_EDGES ? s->h_tri_edges : s->h_tri_owned);
+        if (bytes != v.size() * 4)
+        {
+            set_error("snch_scene_export: size mismatch");
+            return SNCH_ERR_INVALID;
+        }
+        if (bytes) std::memcpy(host_dst, v.data(), bytes);
+        return SNCH_OK;
+    }
+    const int st = check_built(s);
+    if (st != SNCH_OK) return st;
+    const ArenaHeader &h = s->hdr;
+    uint64_t off = 0, want = 0;
+    const void *host_src = nullptr;
+    std::vector<int32_t> tmp;
+    switch (kind)
+    {
+    case SNCH_EXPORT_NODES: off = h.off_nodes; want = (uint64_t)h.n_nodes * 16; break;
+    case SNCH_EXPORT_AABBS: off = h.off_aabbs; want = (uint64_t)h.n_nodes * 24; break;
+    case SNCH_EXPORT_CONES: off = h.off_cones; want = (uint64_t)h.n_nodes * 20; break;
+    case SNCH_EXPORT_MORTON_SORTED: off = h.off_morton; want = (uint64_t)h.n_tris * 4; break;
+    case SNCH_EXPORT_SORTED_INDEX: off = h.off_sorted_idx; want = (uint64_t)h.n_tris * 4; break;
+    case SNCH_EXPORT_RANGES: off = h.off_ranges; want = (uint64_t)h.n_internal * 8; break;
+    case SNCH_EXPORT_Q1_TAINT: off = h.off_q1; want = (uint64_t)h.n_nodes; break;
+    case SNCH_EXPORT_TRI_EDGES: off = h.off_tri_edges; want = (uint64_t)h.n_tris * 12; break;
+    case SNCH_EXPORT_EDGES:
+    case SNCH_EXPORT_TRI_OWNED:
+    {
+        // unpack from the reference-layout structs living in the arena (works for adopted replicas too)
+        const bool edges = kind == SNCH_EXPORT_EDGES;
+        const uint64_t cnt = edges ? h.n_edges : h.n_tris;
+        want = cnt * (edges ? 16 : 12);
+        if (bytes != want) break;
+        const uint64_t rec = edges ? sizeof(RefEdge) : sizeof(RefTriangle);
+        std::vector<unsigned char> raw(cnt * rec);
+        SNCH_CUDA(cudaSetDevice(s->device));
+        if (cnt) SNCH_CUDA(cudaMemcpy(raw.data(), s->arena + (edges ? h.off_edges : h.off_objects), cnt * rec, cudaMemcpyDeviceToHost));
+        int32_t *dst = (int32_t *)host_dst;
+        for (uint64_t i = 0; i < cnt; ++i)
+        {
+            if (edges) std::memcpy(dst + 4 * i, raw.data() + i * rec, 16);
+            else std::memcpy(dst + 3 * i, raw.data() + i * rec + 12, 12);
+        }
+        return SNCH_OK;
+    }
+    default:
+        set_error("snch_scene_export: unknown kind");
+        return SNCH_ERR_INVALID;
+    }
+    if (bytes != want)
+    {
+        char buf[128];
+        std::snprintf(buf, sizeof buf, "snch_scene_export: kind %d needs %llu bytes, got %llu", kind, (unsigned long long)want,
+                      (unsigned long long)bytes);
+        set_error(buf);
+        return SNCH_ERR_INVALID;
+    }
+    if (host_src)
+    {
+        std::memcpy(host_dst, host_src, bytes);
+        return SNCH_OK;
+    }
+    SNCH_CUDA(cudaSetDevice(s->device));
+    if (bytes) SNCH_CUDA(cudaMemcpy(host_dst, s->arena + off, bytes, cudaMemcpyDeviceToHost));
+    return SNCH_OK;
+}
+
+// ---- batched queries ----------------------------------------------------------------------------------------------
+int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n, uint32_t *out_index, float *out_distance, snch_stream stream)
+{
+    int st = check_built(cs);
+    if (st != SNCH_OK) return st;
+    if (n == 0) return SNCH_OK;
+    if (!pts || !out_index || !out_distance)
+    {
+        set_error("snch_closest_point_batch: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    snch_scene *s = const_cast<snch_scene *>(cs);
+    SNCH_CUDA(cudaSetDevice(s->device));
+    const PtrKind k = common_kind({pts, out_index, out_distance});
+    if (k == PK_NULL)
+    {
+        set_error("snch_closest_point_batch: mixed host/device pointers");
+        return SNCH_ERR_POINTER_KIND;
+    }
+    cudaStream_t cst = (cudaStream_t)stream;
+    if (k == PK_DEVICE) return launch_closest(s->view, pts, n, out_index, out_distance, cst);
+    Stager sg(s, cst, Stager::pad(n * 12) + 2 * Stager::pad(n * 4));
+    const float *dq = sg.in(pts, n * 12);
+    uint32_t *di = sg.out(out_index, n * 4);
+    float *dd = sg.out(out_distance, n * 4);
+    if (sg.status != SNCH_OK) return sg.status;
+    st = launch_closest(s->view, dq, n, di, dd, cst);
+    if (st != SNCH_OK) return st;
+    return sg.finish();
+}
+
+int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const uint8_t *flip, const float *r_max, uint64_t n,
+                                  float *out_distance, snch_stream stream)
+{
+    int st = check_built(cs);
+    if (st != SNCH_OK) return st;
+    if (n == 0) return SNCH_OK;
+    if (!pts || !out_distance)
+    {
+        set_error("snch_closest_silhouette_batch: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    snch_scene *s = const_cast<snch_scene *>(cs);
+    SNCH_CUDA(cudaSetDevice(s->device));
+    const PtrKind k = common_kind({pts, flip, r_max, out_distance});
+    if (k == PK_NULL)
+    {
+        set_error("snch_closest_silhouette_batch: mixed host/device pointers");
+        return SNCH_ERR_POINTER_KIND;
+    }
+    cudaStream_t cst = (cudaStream_t)stream;
+    if (k == PK_DEVICE) return launch_silhouette(s->view, pts, flip, r_max, n, out_distance, cst);
+    Stager sg(s, cst, Stager::pad(n * 12) + Stager::pad(n) + 2 * Stager::pad(n * 4));
+    const float *dq = sg.in(pts, n * 12);
+    const uint8_t *df = sg.in(flip, n);
+    const float *dr = sg.in(r_max, n * 4);
+    float *dd = sg.out(out_distance, n * 4);
+    if (sg.status != SNCH_OK) return sg.status;
+    st = launch_silhouette(s->view, dq, df, dr, n, dd, cst);
+    if (st != SNCH_OK) return st;
+    return sg.finish();
+}
+
+int snch_intersect_batch(const snch_scene *cs, const float *org, const float *dir, const float *t_max, uint64_t n, snch_hit *out_hits,
+                         uint8_t *out_found, int any_hit, snch_stream stream)
+{
+    int st = check_built(cs);
+    if (st != SNCH_OK) return st;
+    if (n == 0) return SNCH_OK;
+    if (!org || !dir || (any_hit && !out_found) || (!any_hit && !out_hits && !out_found))
+    {
+        set_error("snch_intersect_batch: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    snch_scene *s = const_cast<snch_scene *>(cs);
+    SNCH_CUDA(cudaSetDevice(s->device));
+    const PtrKind k = common_kind({org, dir, t_max, out_hits, out_found});
+    if (k == PK_NULL)
+    {
+        set_error("snch_intersect_batch: mixed host/device pointers");
+        return SNCH_ERR_POINTER_KIND;
+    }
+    cudaStream_t cst = (cudaStream_t)stream;
+    if (k == PK_DEVICE) return launch_intersect(s->view, org, dir, t_max, n, out_hits, out_found, any_hit, cst);
+    Stager sg(s, cst, 2 * Stager::pad(n * 12) + Stager::pad(n * 4) + Stager::pad(n * 16) + Stager::pad(n));
+    const float *dor = sg.in(org, n * 12);
+    const float *ddi = sg.in(dir, n * 12);
+    const float *dtm = sg.in(t_max, n * 4);
+    snch_hit *dh = sg.out(out_hits, n * sizeof(snch_hit));
+    uint8_t *df = sg.out(out_found, n);
+    if (sg.status != SNCH_OK) return sg.status;
+    st = launch_intersect(s->view, dor, ddi, dtm, n, dh, df, any_hit, cst);
+    if (st != SNCH_OK) return st;
+    return sg.finish();
+}
+
+int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, const float *rnd, uint64_t n, int32_t *out_index, float *out_pdf,
+                                float *out_point, snch_stream stream)
+{
+    int st = check_built(cs);
+    if (st != SNCH_OK) return st;
+    if (n == 0) return SNCH_OK;
+    if (!spheres || !rnd || !out_index || !out_pdf)
+    {
+        set_error("snch_sample_in_sphere_batch: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    snch_scene *s = const_cast<snch_scene *>(cs);
+    SNCH_CUDA(cudaSetDevice(s->device));
+    const PtrKind k = common_kind({spheres, rnd, out_index, out_pdf, out_point});
+    if (k == PK_NULL)
+    {
+        set_error("snch_sample_in_sphere_batch: mixed host/device pointers");
+        return SNCH_ERR_POINTER_KIND;
+    }
+    cudaStream_t cst = (cudaStream_t)stream;
+    if (k == PK_DEVICE) return launch_sample(s->view, spheres, rnd, n, out_index, out_pdf, out_point, cst);
+    Stager sg(s, cst, Stager::pad(n * 16) + 2 * Stager::pad(n * 12) + 2 * Stager::pad(n * 4));
+    const float *ds = sg.in(spheres, n * 16);
+    const float *dr = sg.in(rnd, n * 12);
+    int32_t *di = sg.out(out_index, n * 4);
+    float *dp = sg.out(out_pdf, n * 4);
+    float *dpt = sg.out(out_point, n * 12);
+    if (sg.status != SNCH_OK) return sg.status;
+    st = launch_sample(s->view, ds, dr, n, di, dp, dpt, cst);
+    if (st != SNCH_OK) return st;
+    return sg.finish();
+}
+
+// ---- replication ------------------------------------------------------------------------------------------------------
+int snch_scene_arena(const snch_scene *s, void **device_ptr, uint64_t *bytes)
+{
+    const int st = check_built(s);
+    if (st != SNCH_OK) return st;
+    if (!device_ptr || !bytes)
+    {
+        set_error("snch_scene_arena: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    *device_ptr = s->arena;
+    *bytes = s->arena_bytes;
+    return SNCH_OK;
+}
+
+int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, snch_stream stream, snch_scene **out)
+{
+    if (!arena_copy || !out || bytes < sizeof(ArenaHeader))
+    {
+        set_error("snch_scene_adopt_arena: bad argument");
+        return SNCH_ERR_INVALID;
+    }
+    *out = nullptr;
+    SNCH_CUDA(cudaSetDevice(device));
+    cudaStream_t cst = (cudaStream_t)stream;
+    ArenaHeader h;
+    SNCH_CUDA(cudaMemcpyAsync(&h, arena_copy, sizeof h, cudaMemcpyDeviceToHost, cst));
+    SNCH_CUDA(cudaStreamSynchronize(cst));
+    if (h.magic != kArenaMagic || h.version != kArenaVersion || h.total_bytes != bytes)
+    {
+        set_error("snch_scene_adopt_arena: not a scene arena (magic/version/size mismatch)");
+        return SNCH_ERR_INVALID;
+    }
+    snch_scene *s = new (std::nothrow) snch_scene();
+    if (!s)
+    {
+        set_error("out of host memory");
+        return SNCH_ERR_OOM;
+    }
+    s->device = device;
+    s->adopted = true;
+    s->n_verts = h.n_verts;
+    s->n_tris = h.n_tris;
+    s->n_edges = h.n_edges;
+    if (cudaMalloc(&s->arena, bytes) != cudaSuccess)
+    {
+        cudaGetLastError();
+        delete s;
+        set_error("cudaMalloc of the adopted arena failed");
+        return SNCH_ERR_OOM;
+    }
+    s->arena_bytes = bytes;
+    s->hdr = h;
+    cudaError_t e = cudaMemcpyAsync(s->arena, arena_copy, bytes, cudaMemcpyDeviceToDevice, cst);
+    if (e != cudaSuccess)
+    {
+        snch_scene_destroy(s);
+        return cuda_fail(e, "arena copy");
+    }
+    resolve_view(s);
+    int st = patch_pointers(s, cst); // reference-layout structs embed raw pointers (scene.cuh:831-839)
+    if (st == SNCH_OK)
+    {
+        e = cudaStreamSynchronize(cst);
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    if (st != SNCH_OK)
+    {
+        snch_scene_destroy(s);
+        return st;
+    }
+    s->built = true;
+    *out = s;
+    return SNCH_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,75 @@
+"""The C-ABI library loads on a CPU-only box, exports exactly what include/snch_b200.h declares, keeps its host-side
+logic (creation, adjacency, argument checks) working without a GPU and fails loudly — never falls back — for compute."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "snch_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(snch_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(pkg):
+    declared = _declared_symbols()
+    assert sorted(pkg.ABI_SYMBOLS) == declared
+    out = subprocess.check_output(["nm", "-D", "--defined-only", pkg.lib_path()], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in snch_b200.h but not exported: {missing}"
+    L = pkg.lib()
+    assert L.snch_abi_version() == 1
+    for s in declared:
+        assert hasattr(L, s)
+
+
+def test_library_is_sm100a_cuda(pkg):
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+
+
+def test_argument_errors(pkg):
+    v = np.zeros((3, 3), np.float32)
+    with pytest.raises(pkg.SnchError) as e:
+        pkg.Scene3(v, np.array([[0, 1, 3]], np.int32))
+    assert e.value.status == -1 and "out of range" in str(e.value)
+    sc = pkg.Scene3(v, np.array([[0, 1, 2]], np.int32))
+    with pytest.raises(pkg.SnchError) as e:
+        sc.get_bvh_device_ptr()
+    assert e.value.status == -2 and str(e.value) == "BVH is not built yet."  # scene.cuh:1250
+    with pytest.raises(pkg.SnchError) as e:
+        sc.closest_point(np.zeros((1, 3), np.float32))
+    assert e.value.status == -2
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    v, f = pkg.meshes.tetrahedron()
+    sc = pkg.Scene3(v, f).compute_silhouettes()
+    with pytest.raises(pkg.SnchError) as e:
+        sc.build_bvh()
+    assert e.value.status == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_touches_oracle():
+    """The product path must not import, link or execute anything under oracle/."""
+    pk = os.path.join(ROOT, "snch-lbvh_b200")
+    bad = re.compile(r"(^\s*(import|from)\s+oracle\b)|liboracle|snch_oracle|oracle/|oracle\.loader|_ref/", re.M)
+    for dirpath, _, files in os.walk(pk):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or fn == "Makefile":
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert not bad.search(txt), f"{fn} references the oracle"
+    out = subprocess.check_output(["ldd", os.path.join(pk, "libsnch_b200.so")], text=True)
+    assert "oracle" not in out and "snch_ref" not in out

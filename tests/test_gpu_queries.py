@@ -1,0 +1,177 @@
+"""Query parity on the GPU, through the C-ABI, against the CPU oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import small_cases
+from oracle import OracleScene
+from parity import bits, check_closest, check_rays, check_silhouette, rel_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _mesh(meshes, name):
+    cases = small_cases(meshes)
+    if name in cases:
+        return cases[name]
+    return {"ico5": lambda: meshes.icosphere(5), "grid40": lambda: meshes.open_grid(40),
+            "torus200": lambda: meshes.bumpy_torus(200, 200)}[name]()
+
+
+@pytest.fixture(scope="module", params=["tet", "ico2", "grid6", "torus24x16", "ico5", "grid40", "torus200"])
+def scene(request, pkg, meshes):
+    v, f = _mesh(meshes, request.param)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    orc = OracleScene(v, f)
+    lo, hi = meshes.mesh_bounds(v)
+    n = 20000 if len(f) > 1000 else 4000
+    q = meshes.points_in_box(n, lo, hi, 1.5, seed=41)
+    d = meshes.unit_directions(n, seed=42)
+    return request.param, sc, orc, q, d
+
+
+def test_closest_point(scene):
+    _, sc, orc, q, _ = scene
+    idx, dist = sc.closest_point(q)
+    check_closest(q, idx, dist, orc)
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_closest_silhouette_unbounded(scene, flip):
+    _, sc, orc, q, _ = scene
+    dist = sc.closest_silhouette(q, flip=flip)
+    check_silhouette(dist, orc.silhouette(q, flip, nthreads=8))
+
+
+def test_closest_silhouette_star_radius(scene, meshes):
+    """config C3 semantics: r_max = s * closest-point distance; equals the filtered unbounded answer (Q5)."""
+    _, sc, orc, q, _ = scene
+    _, dcp = orc.closest(q, nthreads=8)
+    rmax = (dcp * meshes.star_radius_scale(len(q))).astype(np.float32)
+    dist = sc.closest_silhouette(q, r_max=rmax)
+    check_silhouette(dist, orc.silhouette(q, False, r_max=rmax, nthreads=8))
+    unb = sc.closest_silhouette(q)
+    assert np.array_equal(bits(dist), bits(np.where(unb <= rmax, unb, np.inf).astype(np.float32)))
+
+
+def test_rays_closest_hit(scene):
+    _, sc, orc, q, d = scene
+    found, hits = sc.intersect(q, d)
+    both = check_rays(found, hits["t"], hits["prim"], q, d, None, orc)
+    # the reported primitive really is hit at the reported t (ties between triangles sharing an edge are legal, Q4)
+    f_b, t_b, _, _ = orc.ray(q[both], d[both], brute=True)
+    assert rel_close(hits["t"][both], t_b).all()
+    assert np.all(hits["prim"][~found.astype(bool)] == 0xFFFFFFFF)
+    u, v = hits["u"][both], hits["v"][both]
+    assert np.all(u >= 0) and np.all(v >= 0) and np.all(u + v <= 1 + 1e-6)
+
+
+def test_rays_tmax_and_any_hit(scene):
+    _, sc, orc, q, d = scene
+    tm = np.full(len(q), 0.7, np.float32)
+    found, hits = sc.intersect(q, d, t_max=tm)
+    check_rays(found, hits["t"], hits["prim"], q, d, tm, orc)
+    assert np.all(hits["t"][found.astype(bool)] < 0.7)
+    any_found, _ = sc.intersect(q, d, t_max=tm, any_hit=True)
+    assert np.mean(any_found.astype(bool) == found.astype(bool)) > 0.9998
+
+
+def test_sample_in_sphere(scene, meshes):
+    _, sc, orc, q, _ = scene
+    _, dcp = orc.closest(q, nthreads=8)
+    sph = np.concatenate([q, (dcp * 1.5 + 0.05)[:, None]], axis=1).astype(np.float32)
+    rnd = meshes.uniforms(len(q), 3, seed=43)
+    idx, pdf, pt = sc.sample_in_sphere(sph, rnd)
+    idx_o, pdf_o = orc.sample(sph, rnd[:, 0].copy())
+    same = idx == idx_o
+    assert same.mean() > 0.999, f"sampled primitive differs on {np.count_nonzero(~same)} of {len(same)}"
+    hit = same & (idx >= 0)
+    assert rel_close(pdf[hit], pdf_o[hit], 2e-5).all()
+    assert np.all(pdf[idx < 0] == 0)
+    pt_o = orc.sample_on_object(idx, rnd[:, 1].copy(), rnd[:, 2].copy())
+    assert np.allclose(pt[idx >= 0], pt_o[idx >= 0], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["tet", "ico2", "grid6", "torus24x16"])
+def test_queries_match_golden(pkg, name):
+    """Against vectors produced by the reference itself (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    sc = pkg.Scene3(g["verts"], g["tris"]).compute_silhouettes().build_bvh()
+    q, d = g["q"], g["d"]
+    _, dist = sc.closest_point(q)
+    assert rel_close(dist, g["closest_dist"]).all()
+    check_silhouette(sc.closest_silhouette(q, flip=False), g["sil_noflip"], 5e-3)
+    check_silhouette(sc.closest_silhouette(q, flip=True), g["sil_flip"], 5e-3)
+    found, hits = sc.intersect(q, d)
+    assert np.mean(found.astype(bool) == g["ray_found"].astype(bool)) >= 0.995
+    both = found.astype(bool) & g["ray_found"].astype(bool)
+    assert rel_close(hits["t"][both], g["ray_t"][both]).all()
+    idx, pdf, _ = sc.sample_in_sphere(g["sph"], np.stack([g["u"], g["u"], g["u"]], 1))
+    assert np.mean(idx == g["sample_idx"]) >= 0.995
+
+
+def test_edge_cases(pkg, meshes):
+    # empty scene: sentinels
+    sc = pkg.Scene3(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.int32)).compute_silhouettes().build_bvh()
+    q = np.zeros((5, 3), np.float32)
+    idx, dist = sc.closest_point(q)
+    assert np.all(idx == 0xFFFFFFFF) and np.all(np.isinf(dist))
+    assert np.all(np.isinf(sc.closest_silhouette(q)))
+    found, hits = sc.intersect(q, np.ones((5, 3), np.float32))
+    assert not found.any() and np.all(np.isinf(hits["t"]))
+    sidx, pdf, _ = sc.sample_in_sphere(np.ones((5, 4), np.float32), np.zeros((5, 3), np.float32))
+    assert np.all(sidx == -1) and np.all(pdf == 0)
+    # zero queries
+    v, f = meshes.icosphere(1)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    idx, dist = sc.closest_point(np.zeros((0, 3), np.float32))
+    assert len(idx) == 0
+    # single triangle (the reference reads out of bounds here, Q6; defined behaviour: test the only leaf)
+    v1 = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    sc = pkg.Scene3(v1, np.array([[0, 1, 2]], np.int32)).compute_silhouettes().build_bvh()
+    orc = OracleScene(v1, np.array([[0, 1, 2]], np.int32))
+    q = meshes.points_in_box(500, [-1, -1, -1], [2, 2, 1], 1.0, seed=44)
+    idx, dist = sc.closest_point(q)
+    assert np.all(idx == 0) and rel_close(dist, orc.closest(q)[1]).all()
+    assert rel_close(sc.closest_silhouette(q), orc.silhouette(q)).all()
+    d = meshes.unit_directions(500, seed=45)
+    found, hits = sc.intersect(q, d)
+    f_o, t_o, _, _ = orc.ray(q, d)
+    assert np.array_equal(found.astype(bool), f_o.astype(bool)) and rel_close(hits["t"], t_o).all()
+    # query points ON the surface and far away
+    v, f = meshes.icosphere(3)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    orc = OracleScene(v, f)
+    q = np.concatenate([v[:200], v[:200] * 1000.0, np.zeros((1, 3), np.float32)]).astype(np.float32)
+    check_closest(q, *sc.closest_point(q), orc)
+    check_silhouette(sc.closest_silhouette(q), orc.silhouette(q), 2e-2)
+    # axis-aligned rays (zero direction components -> infinite inverse directions)
+    o = np.tile(np.array([[0.1, 0.2, -3.0]], np.float32), (4, 1))
+    dd = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0]], np.float32)
+    found, hits = sc.intersect(o, dd)
+    f_o, t_o, _, _ = orc.ray(o, dd)
+    assert np.array_equal(found.astype(bool), f_o.astype(bool)) and rel_close(hits["t"], t_o).all()
+
+
+def test_host_and_device_pointer_paths_agree(pkg, meshes):
+    import torch
+    v, f = meshes.bumpy_torus(64, 48)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    lo, hi = meshes.mesh_bounds(v)
+    q = meshes.points_in_box(10000, lo, hi, 1.3, seed=46)
+    d = meshes.unit_directions(10000, seed=47)
+    qd, dd = torch.from_numpy(q).cuda(), torch.from_numpy(d).cuda()
+    ih, dh = sc.closest_point(q)
+    it, dt = sc.closest_point(qd)
+    torch.cuda.synchronize()
+    assert np.array_equal(ih, it.cpu().numpy().view(np.uint32)) and np.array_equal(bits(dh), bits(dt.cpu().numpy()))
+    assert np.array_equal(bits(sc.closest_silhouette(q)), bits(sc.closest_silhouette(qd).cpu().numpy()))
+    fh, hh = sc.intersect(q, d)
+    ft, ht = sc.intersect(qd, dd)
+    torch.cuda.synchronize()
+    assert np.array_equal(fh, ft.cpu().numpy()) and np.array_equal(bits(hh["t"]), bits(ht.cpu().numpy()[:, 0]))
+    # mixed pointer kinds are rejected, not guessed
+    st = pkg.lib().snch_closest_point_batch(sc._h, qd.data_ptr(), 10, ih.ctypes.data, dh.ctypes.data, None)
+    assert st == -5 and b"mixed" in pkg.lib().snch_last_error()

@@ -1,0 +1,41 @@
+"""Against the reference's own CUDA path compiled for sm_100a (oracle/_ref/libsnch_ref_cuda.so, "Oracle A").
+Skipped where that prebuilt library did not travel."""
+import numpy as np
+import pytest
+
+from oracle import RefScene, ref_available
+from parity import bits, check_silhouette, rel_close
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_available("cuda"), reason="oracle/_ref/libsnch_ref_cuda.so not built")]
+
+
+@pytest.mark.parametrize("name", ["ico5", "torus300", "grid40"])
+def test_against_reference_cuda(pkg, meshes, name):
+    m = meshes
+    v, f = {"ico5": lambda: m.icosphere(5), "torus300": lambda: m.bumpy_torus(300, 300), "grid40": lambda: m.open_grid(40)}[name]()
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    ref = RefScene(v, f, "cuda")
+    K = pkg.ExportKind
+    rn, ra, rc = ref.tree()
+    assert np.array_equal(sc.export(K.NODES), rn), "topology differs from the reference CUDA build"
+    assert np.array_equal(bits(sc.export(K.AABBS)), bits(ra))
+    rm, rsi = ref.morton()
+    assert np.array_equal(sc.export(K.MORTON_SORTED), rm) and np.array_equal(sc.export(K.SORTED_INDEX), rsi)
+    taint = sc.export(K.Q1_TAINT).astype(bool)
+    cones = sc.export(K.CONES)
+    ok = ~taint & (cones[:, 3] >= 0)
+    assert np.array_equal(cones[:, 3] >= 0, rc[:, 3] >= 0) or np.array_equal((cones[:, 3] >= 0)[~taint], (rc[:, 3] >= 0)[~taint])
+    assert rel_close(cones[ok, 3], rc[ok, 3], 1e-5, 2e-6).all() and rel_close(cones[ok, 4], rc[ok, 4], 1e-5, 2e-6).all()
+    lo, hi = m.mesh_bounds(v)
+    n = 200000
+    q = m.points_in_box(n, lo, hi, 1.5, seed=61)
+    d = m.unit_directions(n, seed=62)
+    _, dist = sc.closest_point(q)
+    _, rdist = ref.closest(q)
+    assert rel_close(dist, rdist).all()
+    check_silhouette(sc.closest_silhouette(q), ref.silhouette(q), 1e-3)
+    found, hits = sc.intersect(q, d)
+    rf, rt, _, _ = ref.ray(q, d)
+    assert np.mean(found.astype(bool) == rf.astype(bool)) > 0.9998
+    both = found.astype(bool) & rf.astype(bool)
+    assert np.mean(rel_close(hits["t"][both], rt[both])) > 0.9998
