@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import RefScene, ref_available
-from parity import bits, check_silhouette, rel_close
+from parity import angle_close, bits, check_silhouette, rel_close
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_available("cuda"), reason="oracle/_ref/libsnch_ref_cuda.so not built")]
 
@@ -25,7 +25,7 @@ def test_against_reference_cuda(pkg, meshes, name):
     cones = sc.export(K.CONES)
     ok = ~taint & (cones[:, 3] >= 0)
     assert np.array_equal(cones[:, 3] >= 0, rc[:, 3] >= 0) or np.array_equal((cones[:, 3] >= 0)[~taint], (rc[:, 3] >= 0)[~taint])
-    assert rel_close(cones[ok, 3], rc[ok, 3], 1e-5, 2e-6).all() and rel_close(cones[ok, 4], rc[ok, 4], 1e-5, 2e-6).all()
+    assert angle_close(cones[ok, 3], rc[ok, 3]).all() and rel_close(cones[ok, 4], rc[ok, 4], 1e-5, 2e-6).all()
     lo, hi = m.mesh_bounds(v)
     n = 200000
     q = m.points_in_box(n, lo, hi, 1.5, seed=61)
