@@ -139,6 +139,16 @@ int snch_intersect_batch(const snch_scene *s, const float *origins_xyz, const fl
 int snch_sample_in_sphere_batch(const snch_scene *s, const float *spheres_xyzr, const float *rnd_uvw, uint64_t n, int32_t *out_index,
                                 float *out_pdf, float *out_point_xyz, snch_stream stream);
 
+/* Scheduling knobs of the batched kernels; results never depend on them (tests/test_gpu_queries.py sweeps them).
+ *   "query.sort_min_n"  batches at least this large are visited in Morton order of the query points (default 16384; 0 = never)
+ *   "query.sort_bits"   key bits of that ordering (8..30, default 24)
+ *   "query.sort_rays"   also order ray batches by origin (default 0)
+ *   "query.cone_filter" silhouette: guard-banded sine-space evaluation of the normal-cone test (default 1; 0 = always cone.cuh:168-212 verbatim)
+ *   "query.seed"        closest point: bound each query by the triangle that answered the lane's previous query (default 1)
+ *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
+ * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel). */
+int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Replication (multi-GPU): the built scene lives in ONE pointer-free arena.  Rank 0 exposes it, the caller
  * moves the bytes (ncclBroadcast / cudaMemcpyPeer / torch.distributed.broadcast) and every other rank adopts its copy.

@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "snch_last_error", "snch_abi_version", "snch_scene3_create", "snch_scene_destroy", "snch_scene_compute_silhouettes",
     "snch_scene_build", "snch_scene_stats", "snch_scene_device_repr", "snch_scene_export", "snch_closest_point_batch",
     "snch_closest_silhouette_batch", "snch_intersect_batch", "snch_sample_in_sphere_batch", "snch_scene_arena",
-    "snch_scene_adopt_arena",
+    "snch_scene_adopt_arena", "snch_scene_set_option",
 ]
 
 
@@ -96,6 +96,7 @@ def lib():
     L.snch_sample_in_sphere_batch.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     L.snch_scene_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.snch_scene_adopt_arena.argtypes = [vp, u64, C.c_int, vp, C.POINTER(vp)]
+    L.snch_scene_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     for name in ABI_SYMBOLS:
         if name not in ("snch_last_error",):
             getattr(L, name).restype = C.c_int
@@ -186,6 +187,11 @@ class Scene3:
     def build_bvh(self, stream=None, print_collision=False):
         opts = BuildOptions(C.sizeof(BuildOptions), 1, int(print_collision), 0)
         _check(self._L.snch_scene_build(self._h, C.byref(opts), _stream_ptr(stream)))
+        return self
+
+    def set_option(self, name: str, value: int):
+        """Scheduling knobs of the batched kernels (include/snch_b200.h: snch_scene_set_option); results never depend on them."""
+        _check(self._L.snch_scene_set_option(self._h, name.encode(), int(value)))
         return self
 
     def stats(self) -> dict:

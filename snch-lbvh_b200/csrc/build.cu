@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
         lt[0] = make_float4(pa.x, pa.y, pa.z, __uint_as_float(obj));
         lt[1] = make_float4(pb.x, pb.y, pb.z, 0.0f);
         lt[2] = make_float4(pc.x, pc.y, pc.z, 0.0f);
+        lt[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     // ---- leaf normal cone from the owned silhouette edges, and their traversal records
     const V3 bc = box_centroid(box);
@@ -431,6 +432,7 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
         le[0] = make_float4(ea.x, ea.y, ea.z, eb.x);
         le[1] = make_float4(eb.y, eb.z, boundary ? __int_as_float(0x7FC00000) : u0.x, u0.y);
         le[2] = make_float4(u0.z, u1.x, u1.y, u1.z);
+        le[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         ++cnt;
     }
     if (cnt == 0) cone.half_angle = -kPi;

@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 
 namespace snch
@@ -34,11 +35,54 @@ static PtrKind ptr_kind(const void *p)
     return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? PK_DEVICE : PK_HOST;
 }
 
-// Host-pointer batches: inputs are copied into a device staging area, results copied back; both grow on demand.
-struct Stager
+// Per-call device scratch from the scene's stream-ordered pool: allocation and release are ordered on the caller's
+// stream, so concurrent batches on different streams (or host threads) never share a buffer.
+static int ensure_pool(snch_scene *s)
+{
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (s->pool) return SNCH_OK;
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = s->device;
+    SNCH_CUDA(cudaMemPoolCreate(&s->pool, &props));
+    uint64_t keep = ~0ull; // keep freed blocks cached in the pool: steady-state calls never reach the driver allocator
+    SNCH_CUDA(cudaMemPoolSetAttribute(s->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return SNCH_OK;
+}
+struct PoolBuffer
 {
     snch_scene *s;
     cudaStream_t st;
+    unsigned char *p = nullptr;
+    int status = SNCH_OK;
+    PoolBuffer(snch_scene *s_, cudaStream_t st_, uint64_t bytes) : s(s_), st(st_)
+    {
+        status = ensure_pool(s);
+        if (status != SNCH_OK) return;
+        if (cudaMallocFromPoolAsync((void **)&p, bytes ? bytes : 256, s->pool, st) != cudaSuccess)
+        {
+            cudaGetLastError();
+            p = nullptr;
+            set_error("out of device memory for the per-call query scratch");
+            status = SNCH_ERR_OOM;
+        }
+    }
+    ~PoolBuffer()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    PoolBuffer(const PoolBuffer &) = delete;
+    PoolBuffer &operator=(const PoolBuffer &) = delete;
+};
+
+// Host-pointer batches: inputs are copied into a device staging area, results copied back.
+struct Stager
+{
+    cudaStream_t st;
+    unsigned char *base;
     uint64_t used = 0;
     int status = SNCH_OK;
     struct Out
@@ -49,28 +93,12 @@ struct Stager
     };
     Out outs[4];
     int n_outs = 0;
-    Stager(snch_scene *s_, cudaStream_t st_, uint64_t total) : s(s_), st(st_)
-    {
-        if (s->dstage_bytes < total)
-        {
-            if (s->dstage) cudaFree(s->dstage);
-            s->dstage = nullptr;
-            s->dstage_bytes = 0;
-            if (cudaMalloc(&s->dstage, total) != cudaSuccess)
-            {
-                cudaGetLastError();
-                set_error("cudaMalloc of the query staging buffer failed");
-                status = SNCH_ERR_OOM;
-                return;
-            }
-            s->dstage_bytes = total;
-        }
-    }
+    Stager(unsigned char *base_, cudaStream_t st_) : st(st_), base(base_) {}
     static uint64_t pad(uint64_t b) { return align_up(b, 256); }
     template <typename T> const T *in(const T *host, uint64_t bytes)
     {
         if (!host || status != SNCH_OK) return nullptr;
-        void *d = s->dstage + used;
+        void *d = base + used;
         used += pad(bytes);
         const cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) status = cuda_fail(e, "H2D staging copy");
@@ -79,7 +107,7 @@ struct Stager
     template <typename T> T *out(T *host, uint64_t bytes)
     {
         if (!host || status != SNCH_OK) return nullptr;
-        void *d = s->dstage + used;
+        void *d = base + used;
         used += pad(bytes);
         outs[n_outs++] = Out{host, d, bytes};
         return (T *)d;
@@ -99,6 +127,9 @@ struct Stager
         return status;
     }
 };
+
+// one launch handles at most this many queries (32-bit slots in the kernels); larger batches are split
+constexpr uint64_t kMaxLaunch = 1ull << 30;
 
 static int check_built(const snch_scene *s)
 {
@@ -184,8 +215,7 @@ int snch_scene_destroy(snch_scene *s)
     cudaSetDevice(s->device);
     if (s->arena) cudaFree(s->arena);
     if (s->scratch) cudaFree(s->scratch);
-    if (s->dstage) cudaFree(s->dstage);
-    if (s->pinned) cudaFreeHost(s->pinned);
+    if (s->pool) cudaMemPoolDestroy(s->pool);
     delete s;
     return SNCH_OK;
 }
@@ -371,6 +401,8 @@ int snch_scene_export(const snch_scene *s, int kind, void *host_dst, size_t byte
 }
 
 // ---- batched queries ----------------------------------------------------------------------------------------------
+// Every entry point: validate, classify the pointers, then per slice of <= kMaxLaunch queries either launch directly on
+// the caller's device buffers or stage host buffers through pool memory (H2D, launch, D2H, synchronise).
 int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n, uint32_t *out_index, float *out_distance, snch_stream stream)
 {
     int st = check_built(cs);
@@ -390,15 +422,30 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
         return SNCH_ERR_POINTER_KIND;
     }
     cudaStream_t cst = (cudaStream_t)stream;
-    if (k == PK_DEVICE) return launch_closest(s->view, pts, n, out_index, out_distance, cst);
-    Stager sg(s, cst, Stager::pad(n * 12) + 2 * Stager::pad(n * 4));
-    const float *dq = sg.in(pts, n * 12);
-    uint32_t *di = sg.out(out_index, n * 4);
-    float *dd = sg.out(out_distance, n * 4);
-    if (sg.status != SNCH_OK) return sg.status;
-    st = launch_closest(s->view, dq, n, di, dd, cst);
-    if (st != SNCH_OK) return st;
-    return sg.finish();
+    for (uint64_t off = 0; off < n; off += kMaxLaunch)
+    {
+        const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
+        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + 2 * Stager::pad(m * 4);
+        PoolBuffer buf(s, cst, qs + stage);
+        if (buf.status != SNCH_OK) return buf.status;
+        if (k == PK_DEVICE)
+        {
+            st = launch_closest(s->view, s->tuning, pts + 3 * off, m, out_index + off, out_distance + off, buf.p, cst);
+            if (st != SNCH_OK) return st;
+            continue;
+        }
+        Stager sg(buf.p + qs, cst);
+        const float *dq = sg.in(pts + 3 * off, m * 12);
+        uint32_t *di = sg.out(out_index + off, m * 4);
+        float *dd = sg.out(out_distance + off, m * 4);
+        if (sg.status != SNCH_OK) return sg.status;
+        st = launch_closest(s->view, s->tuning, dq, m, di, dd, buf.p, cst);
+        if (st != SNCH_OK) return st;
+        st = sg.finish();
+        if (st != SNCH_OK) return st;
+    }
+    return SNCH_OK;
 }
 
 int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const uint8_t *flip, const float *r_max, uint64_t n,
@@ -421,16 +468,33 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
         return SNCH_ERR_POINTER_KIND;
     }
     cudaStream_t cst = (cudaStream_t)stream;
-    if (k == PK_DEVICE) return launch_silhouette(s->view, pts, flip, r_max, n, out_distance, cst);
-    Stager sg(s, cst, Stager::pad(n * 12) + Stager::pad(n) + 2 * Stager::pad(n * 4));
-    const float *dq = sg.in(pts, n * 12);
-    const uint8_t *df = sg.in(flip, n);
-    const float *dr = sg.in(r_max, n * 4);
-    float *dd = sg.out(out_distance, n * 4);
-    if (sg.status != SNCH_OK) return sg.status;
-    st = launch_silhouette(s->view, dq, df, dr, n, dd, cst);
-    if (st != SNCH_OK) return st;
-    return sg.finish();
+    for (uint64_t off = 0; off < n; off += kMaxLaunch)
+    {
+        const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
+        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + Stager::pad(m) + 2 * Stager::pad(m * 4);
+        PoolBuffer buf(s, cst, qs + stage);
+        if (buf.status != SNCH_OK) return buf.status;
+        const uint8_t *fo = flip ? flip + off : nullptr;
+        const float *ro = r_max ? r_max + off : nullptr;
+        if (k == PK_DEVICE)
+        {
+            st = launch_silhouette(s->view, s->tuning, pts + 3 * off, fo, ro, m, out_distance + off, buf.p, cst);
+            if (st != SNCH_OK) return st;
+            continue;
+        }
+        Stager sg(buf.p + qs, cst);
+        const float *dq = sg.in(pts + 3 * off, m * 12);
+        const uint8_t *df = sg.in(fo, m);
+        const float *dr = sg.in(ro, m * 4);
+        float *dd = sg.out(out_distance + off, m * 4);
+        if (sg.status != SNCH_OK) return sg.status;
+        st = launch_silhouette(s->view, s->tuning, dq, df, dr, m, dd, buf.p, cst);
+        if (st != SNCH_OK) return st;
+        st = sg.finish();
+        if (st != SNCH_OK) return st;
+    }
+    return SNCH_OK;
 }
 
 int snch_intersect_batch(const snch_scene *cs, const float *org, const float *dir, const float *t_max, uint64_t n, snch_hit *out_hits,
@@ -453,17 +517,35 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
         return SNCH_ERR_POINTER_KIND;
     }
     cudaStream_t cst = (cudaStream_t)stream;
-    if (k == PK_DEVICE) return launch_intersect(s->view, org, dir, t_max, n, out_hits, out_found, any_hit, cst);
-    Stager sg(s, cst, 2 * Stager::pad(n * 12) + Stager::pad(n * 4) + Stager::pad(n * 16) + Stager::pad(n));
-    const float *dor = sg.in(org, n * 12);
-    const float *ddi = sg.in(dir, n * 12);
-    const float *dtm = sg.in(t_max, n * 4);
-    snch_hit *dh = sg.out(out_hits, n * sizeof(snch_hit));
-    uint8_t *df = sg.out(out_found, n);
-    if (sg.status != SNCH_OK) return sg.status;
-    st = launch_intersect(s->view, dor, ddi, dtm, n, dh, df, any_hit, cst);
-    if (st != SNCH_OK) return st;
-    return sg.finish();
+    for (uint64_t off = 0; off < n; off += kMaxLaunch)
+    {
+        const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
+        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t stage = k == PK_DEVICE ? 0 : 2 * Stager::pad(m * 12) + Stager::pad(m * 4) + Stager::pad(m * 16) + Stager::pad(m);
+        PoolBuffer buf(s, cst, qs + stage);
+        if (buf.status != SNCH_OK) return buf.status;
+        const float *to = t_max ? t_max + off : nullptr;
+        snch_hit *ho = out_hits ? out_hits + off : nullptr;
+        uint8_t *fo = out_found ? out_found + off : nullptr;
+        if (k == PK_DEVICE)
+        {
+            st = launch_intersect(s->view, s->tuning, org + 3 * off, dir + 3 * off, to, m, ho, fo, any_hit, buf.p, cst);
+            if (st != SNCH_OK) return st;
+            continue;
+        }
+        Stager sg(buf.p + qs, cst);
+        const float *dor = sg.in(org + 3 * off, m * 12);
+        const float *ddi = sg.in(dir + 3 * off, m * 12);
+        const float *dtm = sg.in(to, m * 4);
+        snch_hit *dh = sg.out(ho, m * sizeof(snch_hit));
+        uint8_t *df = sg.out(fo, m);
+        if (sg.status != SNCH_OK) return sg.status;
+        st = launch_intersect(s->view, s->tuning, dor, ddi, dtm, m, dh, df, any_hit, buf.p, cst);
+        if (st != SNCH_OK) return st;
+        st = sg.finish();
+        if (st != SNCH_OK) return st;
+    }
+    return SNCH_OK;
 }
 
 int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, const float *rnd, uint64_t n, int32_t *out_index, float *out_pdf,
@@ -486,17 +568,56 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
         return SNCH_ERR_POINTER_KIND;
     }
     cudaStream_t cst = (cudaStream_t)stream;
-    if (k == PK_DEVICE) return launch_sample(s->view, spheres, rnd, n, out_index, out_pdf, out_point, cst);
-    Stager sg(s, cst, Stager::pad(n * 16) + 2 * Stager::pad(n * 12) + 2 * Stager::pad(n * 4));
-    const float *ds = sg.in(spheres, n * 16);
-    const float *dr = sg.in(rnd, n * 12);
-    int32_t *di = sg.out(out_index, n * 4);
-    float *dp = sg.out(out_pdf, n * 4);
-    float *dpt = sg.out(out_point, n * 12);
-    if (sg.status != SNCH_OK) return sg.status;
-    st = launch_sample(s->view, ds, dr, n, di, dp, dpt, cst);
-    if (st != SNCH_OK) return st;
-    return sg.finish();
+    for (uint64_t off = 0; off < n; off += kMaxLaunch)
+    {
+        const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
+        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 16) + 2 * Stager::pad(m * 12) + 2 * Stager::pad(m * 4);
+        PoolBuffer buf(s, cst, qs + stage);
+        if (buf.status != SNCH_OK) return buf.status;
+        float *po = out_point ? out_point + 3 * off : nullptr;
+        if (k == PK_DEVICE)
+        {
+            st = launch_sample(s->view, s->tuning, spheres + 4 * off, rnd + 3 * off, m, out_index + off, out_pdf + off, po, buf.p, cst);
+            if (st != SNCH_OK) return st;
+            continue;
+        }
+        Stager sg(buf.p + qs, cst);
+        const float *ds = sg.in(spheres + 4 * off, m * 16);
+        const float *dr = sg.in(rnd + 3 * off, m * 12);
+        int32_t *di = sg.out(out_index + off, m * 4);
+        float *dp = sg.out(out_pdf + off, m * 4);
+        float *dpt = sg.out(po, m * 12);
+        if (sg.status != SNCH_OK) return sg.status;
+        st = launch_sample(s->view, s->tuning, ds, dr, m, di, dp, dpt, buf.p, cst);
+        if (st != SNCH_OK) return st;
+        st = sg.finish();
+        if (st != SNCH_OK) return st;
+    }
+    return SNCH_OK;
+}
+
+int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
+{
+    if (!s || !name)
+    {
+        set_error("snch_scene_set_option: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    const std::string k(name);
+    QueryTuning &t = s->tuning;
+    if (k == "query.sort_min_n") t.sort_min_n = (int)value;
+    else if (k == "query.sort_bits") t.sort_bits = (int)value;
+    else if (k == "query.sort_rays") t.sort_rays = (int)value;
+    else if (k == "query.cone_filter") t.cone_filter = (int)value;
+    else if (k == "query.seed") t.seed = (int)value;
+    else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
+    else
+    {
+        set_error("snch_scene_set_option: unknown option '" + k + "'");
+        return SNCH_ERR_INVALID;
+    }
+    return SNCH_OK;
 }
 
 // ---- replication ------------------------------------------------------------------------------------------------------

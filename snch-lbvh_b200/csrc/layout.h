@@ -14,7 +14,7 @@ namespace snch
 {
 
 constexpr uint64_t kArenaMagic = 0x534e43484c425648ull; // "SNCHLBVH"
-constexpr uint32_t kArenaVersion = 1;
+constexpr uint32_t kArenaVersion = 2;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -52,7 +52,7 @@ static_assert(sizeof(RefEdge) == 32 && sizeof(RefTriangle) == 40, "reference lay
 // ref: internal child -> node index; leaf child -> kLeafFlag | payload
 //   BNode payload  = sorted leaf position k   (LTri[k])
 //   SNode payload  = (first_edge << 2) | edge_count   (LEdge[first_edge .. first_edge+count))
-struct __align__(16) BNode // 64 B: closest-point, ray, sphere sampling
+struct __align__(32) BNode // 64 B: closest-point, ray, sphere sampling (two 256-bit loads)
 {
     float4 a; // lo0.x lo0.y lo0.z hi0.x
     float4 b; // hi0.y hi0.z lo1.x lo1.y
@@ -66,19 +66,21 @@ struct __align__(32) SNode // 96 B: silhouette traversal = boxes + both normal c
     float4 e;       // radius0 axis1.xyz
     float4 f;       // half1 radius1 ref0(bits) ref1(bits)
 };
-struct __align__(16) LTri // 48 B, Morton (leaf) order
+struct __align__(32) LTri // 64 B (two sectors, two 256-bit loads), Morton (leaf) order
 {
     float4 v0; // xyz, w = object index bits
     float4 v1;
     float4 v2;
+    float4 pad;
 };
-struct __align__(16) LEdge // 48 B, grouped by owning leaf in Morton order
+struct __align__(32) LEdge // 64 B, grouped by owning leaf in Morton order
 {
     float4 a; // pa.xyz pb.x
     float4 b; // pb.y pb.z n0.x n0.y       n0.x = NaN  <=> boundary edge (fewer than two faces: always a silhouette)
     float4 c; // n0.z n1.xyz
+    float4 pad;
 };
-static_assert(sizeof(BNode) == 64 && sizeof(SNode) == 96 && sizeof(LTri) == 48 && sizeof(LEdge) == 48, "record sizes");
+static_assert(sizeof(BNode) == 64 && sizeof(SNode) == 96 && sizeof(LTri) == 64 && sizeof(LEdge) == 64, "record sizes");
 
 struct ArenaHeader
 {

@@ -1,23 +1,38 @@
 // query.cu — batched traversal kernels (one launch per query batch).
 //
 // Each kernel returns what the reference's per-thread query_device()/sample_object_in_sphere() returns for the same
-// query (query.cuh:79-169, 238-318, 325-423; sample.cuh:23-92), but walks the two-child traversal records
-// (layout.h) near-child-first with the running best distance applied when a child is *pushed*, not only when it is
-// popped — the reference pops 4-6x more nodes than any exact traversal must open.
+// query (query.cuh:79-169, 238-318, 325-423; sample.cuh:23-92).  What differs is how the batch is scheduled:
 //
-// Result equivalence (see DESIGN.md "Parity rules"):
+//   1. ORDER.   Large batches are visited in Morton order of the query points (k_query_bounds -> k_query_keys -> the
+//      build's own radix sort): the 32 lanes of a warp then walk nearly the same root-to-leaf paths, so a node record
+//      fetched by one lane is an L1 hit for its neighbours.  Results are written back to the caller's slots.
+//   2. PERSISTENT LANES.  The grid is sized to the machine (SMs x resident CTAs), not to the batch.  A warp draws chunks
+//      of consecutive queries from one global counter and every lane that finishes its query immediately takes the next
+//      one of the chunk (ballot + popc rank, no per-lane atomics).  Query cost varies by >100x (a star radius below the
+//      closest distance prunes at the root; a point in the hole of the torus opens thousands of nodes): with one query
+//      per thread a warp ran at 3.2 of 32 lanes (profiles/r01a_*); refilling keeps the lanes occupied.
+//   3. TRAVERSAL.  Two-child records (layout.h), nearer child first, the running best applied when a child is pushed
+//      and again when it is popped.  The closest-point kernel seeds its bound with the triangle that answered the lane's
+//      previous (neighbouring) query.  The silhouette kernel decides the reference's normal-cone test (cone.cuh:168-212)
+//      in sine space with a guard band and only evaluates the acosf/asinf/atan2f chain inside the band, so prune
+//      decisions are the reference's while ~99.9% of tests cost a fifth of it.
+//
+// Result equivalence (DESIGN.md "Parity rules"):
 //   closest   : min over all triangles of the reference's own point-triangle distance; index = any argmin (ties, Q3)
-//   silhouette: min over the leaves that pass the reference's cone test chain (same predicate, same libm calls)
+//   silhouette: min over the leaves that pass the reference's cone test chain (same predicate)
 //   ray       : smallest t with t < max_dist; prim = any triangle attaining it (Q4)
 //   sample    : identical single-path descent (deterministic given u)
 #include "scene.h"
 #include "snch_math.cuh"
+#include "sort_scan.cuh"
 
 namespace snch
 {
 
 constexpr int kQueryThreads = 128;
 constexpr int kStackDepth = 64; // >= 62 levels possible with the 62-bit augmented key
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kChunk = 64; // consecutive queries a warp draws per atomic
 
 struct NodeBoxes
 {
@@ -32,170 +47,407 @@ SNCH_DI NodeBoxes unpack_boxes(float4 a, float4 b, float4 c)
     n.hi1 = V3{c.y, c.z, c.w};
     return n;
 }
-SNCH_DI V3 load_point(const float *__restrict__ q, uint64_t i) { return V3{q[3 * i], q[3 * i + 1], q[3 * i + 2]}; }
+// One 32-byte sector per instruction (LDG.E.256, sm_100): a divergent warp pays one L1 tag lookup per lane per
+// instruction, so a 64 B / 96 B record costs 2 / 3 lookups instead of 4 / 6 with 128-bit loads.  p must be 32 B aligned.
+SNCH_DI void ld256(const void *p, float4 &lo, float4 &hi)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+// traversal stack entry: node reference + the key it was pushed with, moved with one 64-bit local access
+struct __align__(8) StackEntry
+{
+    uint32_t node;
+    float key;
+};
+SNCH_DI V3 load_point(const float *__restrict__ q, uint64_t i) { return V3{__ldg(q + 3 * i), __ldg(q + 3 * i + 1), __ldg(q + 3 * i + 2)}; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp-level work distribution
+// ---------------------------------------------------------------------------------------------------------------
+struct Feeder
+{
+    uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
+    bool exhausted;     // the global counter ran past n
+};
+// Gives every idle lane (bit set in `idle`) the next query slot of the warp's chunk; draws a new chunk when needed.
+// Returns the slot for this lane or kNone.  Warp-convergent call.
+SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter)
+{
+    if (f.next == f.end && !f.exhausted)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)kChunk);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) f.exhausted = true;
+        else
+        {
+            f.next = (uint32_t)base;
+            f.end = (uint32_t)min((unsigned long long)n, base + kChunk);
+        }
+    }
+    const uint32_t avail = f.end - f.next;
+    const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+    const uint32_t want = __popc(idle);
+    const uint32_t take = min(avail, want);
+    uint32_t slot = kNone;
+    if (lane_idle && rank < take) slot = f.next + rank;
+    f.next += take;
+    return slot;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// query ordering
+// ---------------------------------------------------------------------------------------------------------------
+SNCH_DI int f2ord_q(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+SNCH_DI float ord2f_q(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void k_query_box_init(int *box)
+{
+    if (threadIdx.x < 3) box[threadIdx.x] = f2ord_q(INFINITY);
+    else if (threadIdx.x < 6) box[threadIdx.x] = f2ord_q(-INFINITY);
+}
+// bounding box of the finite query points (stride = floats per query: 3 for points/origins, 4 for spheres)
+__global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ q, int stride, uint32_t n, int *box)
+{
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            const float x = __ldg(q + (uint64_t)stride * i + a);
+            if (fabsf(x) <= FLT_MAX)
+            {
+                lo[a] = fminf(lo[a], x);
+                hi[a] = fmaxf(hi[a], x);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(kFull, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFull, hi[a], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+    {
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            atomicMin(box + a, f2ord_q(lo[a]));
+            atomicMax(box + 3 + a, f2ord_q(hi[a]));
+        }
+    }
+}
+// 30-bit Morton key of each query point inside the batch's own bounding box (a scheduling hint only: any key is correct)
+__global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q, int stride, uint32_t n, const int *__restrict__ box,
+                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ perm)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t code = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+        const float lo = ord2f_q(box[a]), hi = ord2f_q(box[3 + a]);
+        const float x = __ldg(q + (uint64_t)stride * i + a);
+        float t = (x - lo) / fmaxf(hi - lo, FLT_MIN) * 1024.0f;
+        t = fminf(fmaxf(t, 0.0f), 1023.0f); // NaN -> 0
+        code |= expand_bits10((uint32_t)t) << (2 - a);
+    }
+    keys[i] = code;
+    perm[i] = i;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // nearest primitive                                                                      query.cuh:238-318
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kQueryThreads)
-    k_closest(SceneView sv, const float *__restrict__ q, uint64_t n, uint32_t *__restrict__ out_idx, float *__restrict__ out_dist)
+    k_closest(SceneView sv, const float *__restrict__ q, const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ out_idx,
+              float *__restrict__ out_dist, unsigned long long *counter, int use_seed)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 p = load_point(q, i);
-    uint32_t stk_n[kStackDepth];
-    float stk_k[kStackDepth];
+    const int lane = threadIdx.x & 31;
+    Feeder fd{0u, 0u, false};
+    StackEntry stk[kStackDepth];
     int sp = 0;
+    V3 p = V3{0.f, 0.f, 0.f};
     float best2 = INFINITY;
-    uint32_t best = kNone;
-    uint32_t node = 0;
+    uint32_t best = kNone, best_leaf = kNone, slot = kNone, node = kNone;
     for (;;)
     {
-        const float4 *np = reinterpret_cast<const float4 *>(sv.bnode + node);
-        const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), d = __ldg(np + 3);
-        const NodeBoxes nb = unpack_boxes(a, b, c);
-        float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
-        uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
-        if (m1 < m0)
+        const unsigned idle = __ballot_sync(kFull, node == kNone);
+        if (idle)
         {
-            const float tm = m0;
-            m0 = m1;
-            m1 = tm;
-            const uint32_t tr = r0;
-            r0 = r1;
-            r1 = tr;
-        }
-        uint32_t next = kNone;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-        {
-            const float m = ch ? m1 : m0;
-            const uint32_t r = ch ? r1 : r0;
-            if (!(m < best2)) continue;
-            if (r & kLeafFlag)
+            const uint32_t s = feeder_take(fd, idle, node == kNone, lane, n, counter);
+            if (s != kNone)
             {
-                const float4 *tp = reinterpret_cast<const float4 *>(sv.ltri + (r & ~kLeafFlag));
-                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
-                dist *= dist; // the reference squares the distance it got back (query.cuh:284-285)
-                if (dist < best2)
-                {
-                    best2 = dist;
-                    best = __float_as_uint(t0.w);
+                slot = perm ? __ldg(perm + s) : s;
+                p = load_point(q, slot);
+                best2 = INFINITY;
+                best = kNone;
+                sp = 0;
+                node = 0;
+                if (use_seed && best_leaf != kNone)
+                { // the triangle that answered this lane's previous (neighbouring) query bounds this one
+                    const LTri *tp = sv.ltri + best_leaf;
+                    float4 t0, t1, t2, t3;
+                    ld256(tp, t0, t1);
+                    ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                    float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+                    dist *= dist;
+                    if (dist < INFINITY)
+                    { // if nothing closer turns up, this triangle IS the answer (best_leaf keeps pointing at it)
+                        best2 = dist;
+                        best = __float_as_uint(t0.w);
+                    }
+                    else best_leaf = kNone;
                 }
             }
-            else if (next == kNone) next = r;
-            else
-            {
-                stk_n[sp] = r;
-                stk_k[sp] = m;
-                ++sp;
-            }
+            if (fd.exhausted && __all_sync(kFull, node == kNone)) break;
         }
-        if (next == kNone)
+        if (node != kNone)
         {
-            while (sp > 0)
+
+            float4 a, b, c, d;
+            ld256(sv.bnode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
+            if (m1 < m0)
             {
-                --sp;
-                if (stk_k[sp] < best2)
+                const float tm = m0;
+                m0 = m1;
+                m1 = tm;
+                const uint32_t tr = r0;
+                r0 = r1;
+                r1 = tr;
+            }
+            uint32_t next = kNone;
+    #pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const float m = ch ? m1 : m0;
+                const uint32_t r = ch ? r1 : r0;
+                if (!(m < best2)) continue;
+                if (r & kLeafFlag)
                 {
-                    next = stk_n[sp];
-                    break;
+                    const uint32_t k = r & ~kLeafFlag;
+                    const LTri *tp = sv.ltri + k;
+                    float4 t0, t1, t2, t3;
+                    ld256(tp, t0, t1);
+                    ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                    float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+                    dist *= dist; // the reference squares the distance it got back (query.cuh:284-285)
+                    if (dist < best2)
+                    {
+                        best2 = dist;
+                        best = __float_as_uint(t0.w);
+                        best_leaf = k;
+                    }
+                }
+                else if (next == kNone) next = r;
+                else
+                {
+                    stk[sp] = StackEntry{r, m};
+                    ++sp;
                 }
             }
-            if (next == kNone) break;
+            if (next == kNone)
+            {
+                while (sp > 0)
+                {
+                    --sp;
+                    const StackEntry se = stk[sp];
+                    if (se.key < best2)
+                    {
+                        next = se.node;
+                        break;
+                    }
+                }
+                if (next == kNone)
+                {
+                    out_idx[slot] = best;
+                    out_dist[slot] = sqrtf(best2);
+                }
+            }
+            node = next;
         }
-        node = next;
     }
-    out_idx[i] = best;
-    out_dist[i] = sqrtf(best2);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // nearest silhouette                                                                     query.cuh:325-423
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kQueryThreads)
-    k_silhouette(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax, uint64_t n,
-                 float *__restrict__ out_dist)
+// The reference's view-cone test (cone.cuh:168-212) is, in real arithmetic,  |acos(t) - pi/2| <= alpha + beta  (or
+// alpha + beta >= pi/2), with t = axis . dir(o -> box centre), alpha the cone half-angle and beta the half-angle the box
+// subtends (asin(radius/l) outside the cone's sphere, atan2(projected extent, l - d) inside).  Equivalently
+// |t| <= sin(alpha + beta).  The filter evaluates that in sine space with fast intrinsics and answers only when the
+// inequality holds or fails by more than kConeBand (>= 10x the rounding of either evaluation); inside the band — and for
+// every branch decision the reference takes on exact float values — it defers to cone_overlap(), the reference's own
+// operation sequence.  Decisions are therefore the reference's; only their cost changes.
+constexpr float kConeBand = 2e-5f;
+template <bool kFilter> SNCH_DI bool cone_test(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 p = load_point(q, i);
-    const bool flip = flipv ? (flipv[i] != 0) : false;
-    float best = rmax ? rmax[i] : INFINITY;
-    float best2 = best * best;
-    bool found = false;
-    uint32_t stk_n[kStackDepth];
-    float stk_k[kStackDepth];
+    if (!kFilter) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+    if (half_angle >= kHalfPi || md2 < FLT_EPSILON) return true;
+    const V3 c = V3{(hi.x + lo.x) * 0.5f, (hi.y + lo.y) * 0.5f, (hi.z + lo.z) * 0.5f};
+    const V3 w = c - o;
+    const float l = len(w); // exact: the reference branches on l > radius
+    const float rl = __frcp_rn(l);
+    const float t = fabsf(__fmaf_rn(axis.x, w.x, __fmaf_rn(axis.y, w.y, axis.z * w.z))) * rl;
+    float sa, ca;
+    __sincosf(half_angle, &sa, &ca);
+    float sb, cb;
+    if (l > radius)
+    {
+        sb = radius * rl;
+        cb = sqrtf(fmaxf(__fmaf_rn(-sb, sb, 1.0f), 0.0f));
+    }
+    else
+    {
+        const V3 v = V3{w.x * rl, w.y * rl, w.z * rl};
+        const V3 e = hi - c;
+        const float d = __fmaf_rn(e.x, fabsf(v.x), __fmaf_rn(e.y, fabsf(v.y), e.z * fabsf(v.z)));
+        const float s = l - d;
+        const float sband = kConeBand * l;
+        if (s < -sband) return true; // the reference returns true for s <= 0
+        if (!(s > sband)) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+        // project_to_plane(v, e)                                                        cone.cuh:34-42, 58-66
+        const float sign = copysignf(1.0f, v.z);
+        const float ia = -__frcp_rn(sign + v.z);
+        const float bb = v.x * v.y * ia;
+        const float b1x = __fmaf_rn(sign * v.x * v.x, ia, 1.0f), b1y = sign * bb, b1z = -sign * v.x;
+        const float b2x = bb, b2y = __fmaf_rn(v.y * v.y, ia, sign), b2z = -v.y;
+        const float r1 = __fmaf_rn(e.x, fabsf(b1x), __fmaf_rn(e.y, fabsf(b1y), e.z * fabsf(b1z)));
+        const float r2 = __fmaf_rn(e.x, fabsf(b2x), __fmaf_rn(e.y, fabsf(b2y), e.z * fabsf(b2z)));
+        const float pr2 = __fmaf_rn(r1, r1, r2 * r2);
+        const float rh = rsqrtf(__fmaf_rn(s, s, pr2));
+        sb = sqrtf(pr2) * rh;
+        cb = s * rh;
+    }
+    const float cg = __fmaf_rn(ca, cb, -sa * sb); // cos(alpha + beta)
+    const float sg = __fmaf_rn(sa, cb, ca * sb);  // sin(alpha + beta)
+    if (cg <= -kConeBand) return true;            // alpha + beta > pi/2
+    if (cg >= kConeBand)
+    {
+        if (t <= sg - kConeBand) return true;
+        if (t >= sg + kConeBand) return false;
+    }
+    return cone_overlap(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
+}
+
+template <bool kFilter>
+__global__ void __launch_bounds__(kQueryThreads)
+    k_silhouette(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
+                 const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+{
+    const int lane = threadIdx.x & 31;
+    Feeder fd{0u, 0u, false};
+    StackEntry stk[kStackDepth];
     int sp = 0;
-    uint32_t node = 0;
+    V3 p = V3{0.f, 0.f, 0.f};
+    bool flip = false, found = false;
+    float best = INFINITY, best2 = INFINITY;
+    uint32_t slot = kNone, node = kNone;
     for (;;)
     {
-        const float4 *np = reinterpret_cast<const float4 *>(sv.snode + node);
-        const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), d = __ldg(np + 3), e = __ldg(np + 4), f = __ldg(np + 5);
-        const NodeBoxes nb = unpack_boxes(a, b, c);
-        const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
-        const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
-        // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367),
-        // evaluated only for children that can still beat the current best
-        bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_overlap(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-        bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_overlap(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
-        const bool swap = m1 < m0;
-        uint32_t next = kNone;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
+        const unsigned idle = __ballot_sync(kFull, node == kNone);
+        if (idle)
         {
-            const bool second = (ch == 1) != swap; // visit the nearer child first
-            const bool h = second ? h1 : h0;
-            const float m = second ? m1 : m0;
-            const uint32_t r = second ? r1 : r0;
-            if (!h || !(m <= best2)) continue;
-            if (r & kLeafFlag)
+            const uint32_t s = feeder_take(fd, idle, node == kNone, lane, n, counter);
+            if (s != kNone)
             {
-                const uint32_t payload = r & ~kLeafFlag;
-                const uint32_t first = payload >> 2, cnt = payload & 3u;
-                for (uint32_t k = 0; k < cnt; ++k)
-                { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
-                    const float4 *ep = reinterpret_cast<const float4 *>(sv.ledge + first + k);
-                    const float4 e0 = __ldg(ep), e1 = __ldg(ep + 1), e2 = __ldg(ep + 2);
-                    const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
-                    V3 cp;
-                    const float dist = point_segment_distance(pa, pb, p, &cp);
-                    if (dist * dist > best2) continue;
-                    bool is_sil = isnan(e1.z); // boundary edge
-                    if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
-                    if (is_sil && dist <= best)
-                    {
-                        best = dist;
-                        best2 = dist * dist;
-                        found = true;
+                slot = perm ? __ldg(perm + s) : s;
+                p = load_point(q, slot);
+                flip = flipv ? (__ldg(flipv + slot) != 0) : false;
+                best = rmax ? __ldg(rmax + slot) : INFINITY;
+                best2 = best * best;
+                found = false;
+                sp = 0;
+                node = 0;
+            }
+            if (fd.exhausted && __all_sync(kFull, node == kNone)) break;
+        }
+        if (node != kNone)
+        {
+
+            float4 a, b, c, d, e, f;
+            ld256(sv.snode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
+            ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
+            // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367),
+            // evaluated only for children that can still beat the current best
+            const bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+            const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+            const bool swap = m1 < m0;
+            uint32_t next = kNone;
+    #pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const bool second = (ch == 1) != swap; // visit the nearer child first
+                const bool h = second ? h1 : h0;
+                const float m = second ? m1 : m0;
+                const uint32_t r = second ? r1 : r0;
+                if (!h || !(m <= best2)) continue;
+                if (r & kLeafFlag)
+                {
+                    const uint32_t payload = r & ~kLeafFlag;
+                    const uint32_t first = payload >> 2, cnt = payload & 3u;
+                    for (uint32_t k = 0; k < cnt; ++k)
+                    { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
+                        float4 e0, e1, e2, e3;
+                        ld256(sv.ledge + first + k, e0, e1);
+                        ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
+                        const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
+                        V3 cp;
+                        const float dist = point_segment_distance(pa, pb, p, &cp);
+                        if (dist * dist > best2) continue;
+                        bool is_sil = isnan(e1.z); // boundary edge
+                        if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
+                        if (is_sil && dist <= best)
+                        {
+                            best = dist;
+                            best2 = dist * dist;
+                            found = true;
+                        }
                     }
                 }
-            }
-            else if (next == kNone) next = r;
-            else
-            {
-                stk_n[sp] = r;
-                stk_k[sp] = m;
-                ++sp;
-            }
-        }
-        if (next == kNone)
-        {
-            while (sp > 0)
-            {
-                --sp;
-                if (stk_k[sp] <= best2)
+                else if (next == kNone) next = r;
+                else
                 {
-                    next = stk_n[sp];
-                    break;
+                    stk[sp] = StackEntry{r, m};
+                    ++sp;
                 }
             }
-            if (next == kNone) break;
+            if (next == kNone)
+            {
+                while (sp > 0)
+                {
+                    --sp;
+                    const StackEntry se = stk[sp];
+                    if (se.key <= best2)
+                    {
+                        next = se.node;
+                        break;
+                    }
+                }
+                if (next == kNone) out_dist[slot] = found ? best : INFINITY;
+            }
+            node = next;
         }
-        node = next;
     }
-    out_dist[i] = found ? best : INFINITY;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -203,107 +455,133 @@ __global__ void __launch_bounds__(kQueryThreads)
 // ---------------------------------------------------------------------------------------------------------------
 template <bool kAnyHit>
 __global__ void __launch_bounds__(kQueryThreads)
-    k_intersect(SceneView sv, const float *__restrict__ org, const float *__restrict__ dir, const float *__restrict__ tmaxv, uint64_t n,
-                snch_hit *__restrict__ hits, uint8_t *__restrict__ found_out)
+    k_intersect(SceneView sv, const float *__restrict__ org, const float *__restrict__ dir, const float *__restrict__ tmaxv,
+                const uint32_t *__restrict__ perm, uint32_t n, snch_hit *__restrict__ hits, uint8_t *__restrict__ found_out,
+                unsigned long long *counter)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 o = load_point(org, i), dv = load_point(dir, i);
-    const V3 dinv = V3{1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z}; // aabb.cuh:305-312
-    const float max_dist = tmaxv ? tmaxv[i] : INFINITY;
-    float best_t = INFINITY, best_u = 0.f, best_v = 0.f;
-    uint32_t best_prim = kNone;
-    bool found = false;
-    uint32_t stk_n[kStackDepth];
-    float stk_k[kStackDepth];
+    const int lane = threadIdx.x & 31;
+    Feeder fd{0u, 0u, false};
+    StackEntry stk[kStackDepth];
     int sp = 0;
-    uint32_t node = 0;
+    V3 o = V3{0.f, 0.f, 0.f}, dv = o, dinv = o;
+    float max_dist = INFINITY, best_t = INFINITY, best_u = 0.f, best_v = 0.f;
+    uint32_t best_prim = kNone, slot = kNone, node = kNone;
+    bool found = false;
     for (;;)
     {
-        const float4 *np = reinterpret_cast<const float4 *>(sv.bnode + node);
-        const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), d = __ldg(np + 3);
-        const NodeBoxes nb = unpack_boxes(a, b, c);
-        float e0, e1;
-        bool h0 = box_ray(nb.lo0, nb.hi0, o, dinv, max_dist, &e0);
-        bool h1 = box_ray(nb.lo1, nb.hi1, o, dinv, max_dist, &e1);
-        const uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
-        const bool swap = h0 && h1 && (e1 < e0); // the reference visits L first on ties (query.cuh:141)
-        uint32_t next = kNone;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
+        const unsigned idle = __ballot_sync(kFull, node == kNone);
+        if (idle)
         {
-            const bool second = (ch == 1) != swap;
-            const bool h = second ? h1 : h0;
-            const float en = second ? e1 : e0;
-            const uint32_t r = second ? r1 : r0;
-            if (!h || en > best_t) continue; // same rejection the reference applies at pop time (query.cuh:106)
-            if (r & kLeafFlag)
+            const uint32_t s = feeder_take(fd, idle, node == kNone, lane, n, counter);
+            if (s != kNone)
             {
-                const float4 *tp = reinterpret_cast<const float4 *>(sv.ltri + (r & ~kLeafFlag));
-                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                float t, u, v;
-                if (ray_triangle(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, o, dv, &t, &u, &v) && t < max_dist &&
-                    t < best_t)
+                slot = perm ? __ldg(perm + s) : s;
+                o = load_point(org, slot);
+                dv = load_point(dir, slot);
+                dinv = V3{1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z}; // aabb.cuh:305-312
+                max_dist = tmaxv ? __ldg(tmaxv + slot) : INFINITY;
+                best_t = INFINITY;
+                best_u = best_v = 0.f;
+                best_prim = kNone;
+                found = false;
+                sp = 0;
+                node = 0;
+            }
+            if (fd.exhausted && __all_sync(kFull, node == kNone)) break;
+        }
+        if (node != kNone)
+        {
+
+            float4 a, b, c, d;
+            ld256(sv.bnode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            float e0, e1;
+            const bool h0 = box_ray(nb.lo0, nb.hi0, o, dinv, max_dist, &e0);
+            const bool h1 = box_ray(nb.lo1, nb.hi1, o, dinv, max_dist, &e1);
+            const uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
+            const bool swap = h0 && h1 && (e1 < e0); // the reference visits L first on ties (query.cuh:141)
+            uint32_t next = kNone;
+            bool done = false;
+    #pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const bool second = (ch == 1) != swap;
+                const bool h = second ? h1 : h0;
+                const float en = second ? e1 : e0;
+                const uint32_t r = second ? r1 : r0;
+                if (done || !h || en > best_t) continue; // same rejection the reference applies at pop time (query.cuh:106)
+                if (r & kLeafFlag)
                 {
-                    best_t = t;
-                    best_u = u;
-                    best_v = v;
-                    best_prim = __float_as_uint(t0.w);
-                    found = true;
-                    if (kAnyHit)
+                    const LTri *tp = sv.ltri + (r & ~kLeafFlag);
+                    float4 t0, t1, t2, t3;
+                    ld256(tp, t0, t1);
+                    ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                    float t, u, v;
+                    if (ray_triangle(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, o, dv, &t, &u, &v) && t < max_dist &&
+                        t < best_t)
                     {
-                        found_out[i] = 1;
-                        return;
+                        best_t = t;
+                        best_u = u;
+                        best_v = v;
+                        best_prim = __float_as_uint(t0.w);
+                        found = true;
+                        if (kAnyHit) done = true;
+                    }
+                }
+                else if (next == kNone) next = r;
+                else
+                {
+                    stk[sp] = StackEntry{r, en};
+                    ++sp;
+                }
+            }
+            if (done) next = kNone;
+            else if (next == kNone)
+            {
+                while (sp > 0)
+                {
+                    --sp;
+                    const StackEntry se = stk[sp];
+                    if (!(se.key > best_t))
+                    {
+                        next = se.node;
+                        break;
                     }
                 }
             }
-            else if (next == kNone) next = r;
-            else
+            if (next == kNone)
             {
-                stk_n[sp] = r;
-                stk_k[sp] = en;
-                ++sp;
-            }
-        }
-        if (next == kNone)
-        {
-            while (sp > 0)
-            {
-                --sp;
-                if (!(stk_k[sp] > best_t))
+                if (found_out) found_out[slot] = found ? 1 : 0;
+                if (!kAnyHit && hits)
                 {
-                    next = stk_n[sp];
-                    break;
+                    snch_hit h;
+                    h.t = best_t;
+                    h.u = best_u;
+                    h.v = best_v;
+                    h.prim = best_prim;
+                    hits[slot] = h;
                 }
             }
-            if (next == kNone) break;
+            node = next;
         }
-        node = next;
-    }
-    if (found_out) found_out[i] = found ? 1 : 0;
-    if (!kAnyHit && hits)
-    {
-        snch_hit h;
-        h.t = best_t;
-        h.u = best_u;
-        h.v = best_v;
-        h.prim = best_prim;
-        hits[i] = h;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // SampleTriangleInSphere                                              sample.cuh:23-92 + 7-21, scene.cuh:14-27
+// One root-to-leaf path per query: no stack, no variance in length beyond the tree depth -> one query per thread.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kQueryThreads)
-    k_sample(SceneView sv, const float *__restrict__ sph, const float *__restrict__ rnd, uint64_t n, int32_t *__restrict__ out_idx,
-             float *__restrict__ out_pdf, float *__restrict__ out_pt)
+    k_sample(SceneView sv, const float *__restrict__ sph, const float *__restrict__ rnd, const uint32_t *__restrict__ perm, uint32_t n,
+             int32_t *__restrict__ out_idx, float *__restrict__ out_pdf, float *__restrict__ out_pt)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V3 ctr = V3{sph[4 * i], sph[4 * i + 1], sph[4 * i + 2]};
-    const float radius = sph[4 * i + 3];
-    float u = rnd[3 * i];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint64_t i = perm ? __ldg(perm + s) : s;
+    const V3 ctr = V3{__ldg(sph + 4 * i), __ldg(sph + 4 * i + 1), __ldg(sph + 4 * i + 2)};
+    const float radius = __ldg(sph + 4 * i + 3);
+    float u = __ldg(rnd + 3 * i);
     float path = 1.0f;
     int32_t idx = -1;
     float pdf = 0.0f;
@@ -311,8 +589,9 @@ __global__ void __launch_bounds__(kQueryThreads)
     uint32_t node = 0;
     for (;;)
     {
-        const float4 *np = reinterpret_cast<const float4 *>(sv.bnode + node);
-        const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2), d = __ldg(np + 3);
+        float4 a, b, c, d;
+        ld256(sv.bnode + node, a, b);
+        ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
         const NodeBoxes nb = unpack_boxes(a, b, c);
         const V3 c0 = V3{(nb.hi0.x + nb.lo0.x) * 0.5f, (nb.hi0.y + nb.lo0.y) * 0.5f, (nb.hi0.z + nb.lo0.z) * 0.5f};
         const V3 c1 = V3{(nb.hi1.x + nb.lo1.x) * 0.5f, (nb.hi1.y + nb.lo1.y) * 0.5f, (nb.hi1.z + nb.lo1.z) * 0.5f};
@@ -337,14 +616,16 @@ __global__ void __launch_bounds__(kQueryThreads)
         }
         if (r & kLeafFlag)
         {
-            const float4 *tp = reinterpret_cast<const float4 *>(sv.ltri + (r & ~kLeafFlag));
-            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            const LTri *tp = sv.ltri + (r & ~kLeafFlag);
+            float4 t0, t1, t2, t3;
+            ld256(tp, t0, t1);
+            ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
             const V3 pa = V3{t0.x, t0.y, t0.z}, pb = V3{t1.x, t1.y, t1.z}, pc = V3{t2.x, t2.y, t2.z};
             if (sphere_triangle(pa, pb, pc, ctr, radius))
             {
                 idx = (int32_t)__float_as_uint(t0.w);
                 pdf = path / triangle_area(pa, pb, pc);
-                float su = rnd[3 * i + 1], sv2 = rnd[3 * i + 2];
+                float su = __ldg(rnd + 3 * i + 1), sv2 = __ldg(rnd + 3 * i + 2);
                 if (su + sv2 > 1.0f)
                 {
                     su = 1.0f - su;
@@ -389,39 +670,141 @@ __global__ void k_fill_empty(uint64_t n, uint32_t *idx, float *dist, snch_hit *h
     if (pt) pt[3 * i] = pt[3 * i + 1] = pt[3 * i + 2] = 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
 static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kQueryThreads - 1) / kQueryThreads); }
 
-int launch_closest(const SceneView &v, const float *q, uint64_t n, uint32_t *idx, float *dist, cudaStream_t st)
+// bytes of device scratch one batch of n queries needs (ordering buffers + sort counters + the work counter)
+uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
+{
+    uint64_t b = 256; // work counter + query box
+    if (t.sort_min_n > 0 && n >= (uint64_t)t.sort_min_n) b += 4 * align_up(n * 4, 256) + align_up(sort_scratch_elems(n) * 4, 256);
+    return b;
+}
+
+// Lays the scratch out and, for batches worth ordering, produces the Morton permutation.  *perm_out = nullptr otherwise.
+static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, uint32_t n, unsigned char *scratch, cudaStream_t st,
+                         unsigned long long **counter_out, const uint32_t **perm_out)
+{
+    SNCH_CUDA(cudaMemsetAsync(scratch, 0, 64, st));
+    *counter_out = reinterpret_cast<unsigned long long *>(scratch);
+    *perm_out = nullptr;
+    if (!(order && t.sort_min_n > 0 && n >= (uint32_t)t.sort_min_n)) return SNCH_OK;
+    int *box = reinterpret_cast<int *>(scratch + 64);
+    const uint64_t a = align_up((uint64_t)n * 4, 256);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(scratch + 256);
+    uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + 256 + a);
+    uint32_t *ktmp = reinterpret_cast<uint32_t *>(scratch + 256 + 2 * a);
+    uint32_t *vtmp = reinterpret_cast<uint32_t *>(scratch + 256 + 3 * a);
+    uint32_t *sscr = reinterpret_cast<uint32_t *>(scratch + 256 + 4 * a);
+    const unsigned g = (n + 255) / 256;
+    k_query_box_init<<<1, 32, 0, st>>>(box);
+    k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, n, box);
+    k_query_keys<<<g, 256, 0, st>>>(pts, stride, n, box, keys, perm);
+    int bits = t.sort_bits < 8 ? 8 : (t.sort_bits > 30 ? 30 : t.sort_bits);
+    radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
+    SNCH_CUDA(cudaGetLastError());
+    *perm_out = perm;
+    return SNCH_OK;
+}
+
+template <typename K> static unsigned persistent_grid(K kernel, const QueryTuning &t, uint32_t n)
+{
+    static thread_local int cached_dev = -1, sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev)
+    {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kQueryThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    if (t.blocks_per_sm > 0 && t.blocks_per_sm < per_sm) per_sm = t.blocks_per_sm;
+    const uint64_t full = (uint64_t)sms * per_sm;
+    const uint64_t need = ((uint64_t)n + kChunk * (kQueryThreads / 32) - 1) / (kChunk * (kQueryThreads / 32));
+    return (unsigned)(need < full ? (need ? need : 1) : full);
+}
+
+int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
+                   cudaStream_t st)
 {
     if (n == 0) return SNCH_OK;
-    if (v.n_tris == 0) k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, idx, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
-    else k_closest<<<grid_for(n), kQueryThreads, 0, st>>>(v, q, n, idx, dist);
+    if (v.n_tris == 0)
+    {
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, idx, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
+        SNCH_CUDA(cudaGetLastError());
+        return SNCH_OK;
+    }
+    unsigned long long *counter;
+    const uint32_t *perm;
+    const int rc = prepare_batch(t, true, q, 3, (uint32_t)n, scratch, st, &counter, &perm);
+    if (rc != SNCH_OK) return rc;
+    k_closest<<<persistent_grid(k_closest, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist, counter, t.seed);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
-int launch_silhouette(const SceneView &v, const float *q, const uint8_t *flip, const float *rmax, uint64_t n, float *dist, cudaStream_t st)
+int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax, uint64_t n,
+                      float *dist, unsigned char *scratch, cudaStream_t st)
 {
     if (n == 0) return SNCH_OK;
-    if (v.n_tris == 0) k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
-    else k_silhouette<<<grid_for(n), kQueryThreads, 0, st>>>(v, q, flip, rmax, n, dist);
+    if (v.n_tris == 0)
+    {
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
+        SNCH_CUDA(cudaGetLastError());
+        return SNCH_OK;
+    }
+    unsigned long long *counter;
+    const uint32_t *perm;
+    const int rc = prepare_batch(t, true, q, 3, (uint32_t)n, scratch, st, &counter, &perm);
+    if (rc != SNCH_OK) return rc;
+    if (t.cone_filter)
+        k_silhouette<true><<<persistent_grid(k_silhouette<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, (uint32_t)n,
+                                                                                                        dist, counter);
+    else
+        k_silhouette<false><<<persistent_grid(k_silhouette<false>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm,
+                                                                                                          (uint32_t)n, dist, counter);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
-int launch_intersect(const SceneView &v, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits, uint8_t *found,
-                     int any_hit, cudaStream_t st)
+int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
+                     uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st)
 {
     if (n == 0) return SNCH_OK;
-    if (v.n_tris == 0) k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, nullptr, hits, found, nullptr, nullptr, nullptr);
-    else if (any_hit) k_intersect<true><<<grid_for(n), kQueryThreads, 0, st>>>(v, o, d, tmax, n, hits, found);
-    else k_intersect<false><<<grid_for(n), kQueryThreads, 0, st>>>(v, o, d, tmax, n, hits, found);
+    if (v.n_tris == 0)
+    {
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, nullptr, any_hit ? nullptr : hits, found, nullptr, nullptr, nullptr);
+        SNCH_CUDA(cudaGetLastError());
+        return SNCH_OK;
+    }
+    unsigned long long *counter;
+    const uint32_t *perm;
+    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, (uint32_t)n, scratch, st, &counter, &perm);
+    if (rc != SNCH_OK) return rc;
+    if (any_hit)
+        k_intersect<true><<<persistent_grid(k_intersect<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, (uint32_t)n, hits,
+                                                                                                      found, counter);
+    else
+        k_intersect<false><<<persistent_grid(k_intersect<false>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, (uint32_t)n,
+                                                                                                        hits, found, counter);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
-int launch_sample(const SceneView &v, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf, float *pt, cudaStream_t st)
+int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf,
+                  float *pt, unsigned char *scratch, cudaStream_t st)
 {
     if (n == 0) return SNCH_OK;
-    if (v.n_tris == 0) k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, nullptr, nullptr, nullptr, idx, pdf, pt);
-    else k_sample<<<grid_for(n), kQueryThreads, 0, st>>>(v, sph, rnd, n, idx, pdf, pt);
+    if (v.n_tris == 0)
+    {
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, nullptr, nullptr, nullptr, idx, pdf, pt);
+        SNCH_CUDA(cudaGetLastError());
+        return SNCH_OK;
+    }
+    (void)t;
+    (void)scratch; // one short root-to-leaf path per query: neither ordering nor work stealing pays for itself here
+    k_sample<<<grid_for(n), kQueryThreads, 0, st>>>(v, sph, rnd, nullptr, (uint32_t)n, idx, pdf, pt);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }

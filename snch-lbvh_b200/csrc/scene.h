@@ -3,8 +3,23 @@
 #include "../../include/snch_b200.h"
 #include "layout.h"
 
+#include <mutex>
 #include <string>
 #include <vector>
+
+namespace snch
+{
+// Scheduling knobs of the batched query kernels (snch_scene_set_option).  Results never depend on them.
+struct QueryTuning
+{
+    int sort_min_n = 16384; // batches at least this large are visited in Morton order of the query points (0 = never)
+    int sort_bits = 24;     // Morton key bits the ordering sorts on (top bits of the 30-bit code)
+    int sort_rays = 0;      // also order ray batches by origin (off: random directions decorrelate the paths anyway)
+    int cone_filter = 1;    // silhouette: guard-banded sine-space normal-cone test (0 = always the reference's libm chain)
+    int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
+    int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
+};
+} // namespace snch
 
 struct snch_scene
 {
@@ -23,11 +38,10 @@ struct snch_scene
     // build scratch (kept between builds)
     unsigned char *scratch = nullptr;
     uint64_t scratch_bytes = 0;
-    // staging for host-pointer batches
-    unsigned char *pinned = nullptr;
-    uint64_t pinned_bytes = 0;
-    unsigned char *dstage = nullptr;
-    uint64_t dstage_bytes = 0;
+    // stream-ordered pool for per-call scratch (query ordering, work counters, staging of host-pointer batches)
+    cudaMemPool_t pool = nullptr;
+    std::mutex mu;
+    snch::QueryTuning tuning;
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0;
@@ -50,10 +64,14 @@ int build_device(snch_scene *s, cudaStream_t stream);
 void resolve_view(snch_scene *s);
 int patch_pointers(snch_scene *s, cudaStream_t stream);
 
-// query.cu
-int launch_closest(const SceneView &v, const float *q, uint64_t n, uint32_t *idx, float *dist, cudaStream_t st);
-int launch_silhouette(const SceneView &v, const float *q, const uint8_t *flip, const float *rmax, uint64_t n, float *dist, cudaStream_t st);
-int launch_intersect(const SceneView &v, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits, uint8_t *found,
-                     int any_hit, cudaStream_t st);
-int launch_sample(const SceneView &v, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf, float *pt, cudaStream_t st);
+// query.cu — n <= 2^32 - 2^20 per launch (the C-ABI splits larger batches); `scratch` has query_scratch_bytes(n) bytes
+uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t);
+int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
+                   cudaStream_t st);
+int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax, uint64_t n,
+                      float *dist, unsigned char *scratch, cudaStream_t st);
+int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
+                     uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st);
+int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf,
+                  float *pt, unsigned char *scratch, cudaStream_t st);
 } // namespace snch

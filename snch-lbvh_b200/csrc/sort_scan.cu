@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kSortThreads)
 }
 
 void radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
-                      uint32_t *scratch, cudaStream_t stream)
+                      uint32_t *scratch, cudaStream_t stream, int first_bit)
 {
     if (n == 0) return;
     const uint32_t tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
@@ -183,7 +183,7 @@ void radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32
     uint32_t *sk = keys, *sv = vals, *dk = keys_tmp, *dv = vals_tmp;
     for (int p = 0; p < passes; ++p)
     {
-        const int shift = 8 * p;
+        const int shift = first_bit + 8 * p;
         k_radix_hist<<<tiles, kSortThreads, 0, stream>>>(sk, n, shift, counts, tiles);
         exclusive_scan_u32(counts, counts, (uint64_t)tiles * kSortBins, scan_scratch, stream);
         k_radix_scatter<<<tiles, kSortThreads, 0, stream>>>(sk, sv, dk, dv, n, shift, counts, tiles);

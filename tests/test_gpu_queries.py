@@ -175,3 +175,42 @@ def test_host_and_device_pointer_paths_agree(pkg, meshes):
     # mixed pointer kinds are rejected, not guessed
     st = pkg.lib().snch_closest_point_batch(sc._h, qd.data_ptr(), 10, ih.ctypes.data, dh.ctypes.data, None)
     assert st == -5 and b"mixed" in pkg.lib().snch_last_error()
+
+
+def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
+    """Query ordering, the guard-banded cone test, seeding and grid size only change scheduling: bit-identical results."""
+    v, f = meshes.bumpy_torus(120, 90)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    orc = OracleScene(v, f)
+    lo, hi = meshes.mesh_bounds(v)
+    n = 60000
+    q = meshes.points_in_box(n, lo, hi, 1.3, seed=48)
+    d = meshes.unit_directions(n, seed=49)
+    flip = (np.arange(n) % 3 == 0).astype(np.uint8)
+    rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(n)).astype(np.float32)
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0}
+
+    def run():
+        idx, dist = sc.closest_point(q)
+        found, hits = sc.intersect(q, d)
+        sidx, pdf, _ = sc.sample_in_sphere(np.concatenate([q, rmax[:, None] + 0.05], 1).astype(np.float32), meshes.uniforms(n, 3, seed=50))
+        return dict(dist=dist, sil=sc.closest_silhouette(q, flip=flip), silr=sc.closest_silhouette(q, r_max=rmax), found=found,
+                    t=hits["t"].copy(), sidx=sidx, pdf=pdf), idx
+
+    base, idx0 = run()
+    check_closest(q[:5000], idx0[:5000], base["dist"][:5000], orc)
+    for fl in (0, 1):  # per-query flip bytes: each subset must match the oracle run with that scalar flag
+        sel = np.nonzero(flip[:6000] == fl)[0]
+        check_silhouette(base["sil"][sel], orc.silhouette(q[sel], bool(fl), nthreads=8), 2e-3)
+    for kv in ({"query.sort_min_n": 0}, {"query.cone_filter": 0}, {"query.seed": 0}, {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
+               {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0}):
+        for k, val in {**defaults, **kv}.items():
+            sc.set_option(k, val)
+        other, idx1 = run()
+        for k in base:
+            a, b = base[k], other[k]
+            assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b), (kv, k)
+        # indices may differ only between triangles at the same distance (documented tie rule, Q3)
+        assert rel_close(orc.point_triangle_distance(q, idx1), base["dist"]).all(), kv
+    with pytest.raises(pkg.SnchError):
+        sc.set_option("query.no_such_knob", 1)

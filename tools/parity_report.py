@@ -70,6 +70,12 @@ def report(name, v, f, n, out):
         row["refcuda_closest_frac_rel_gt_1e-5"] = float(np.mean(rel(dist, rd) > 1e-5))
         rs = ref.silhouette(q)
         row["refcuda_sil_frac_rel_gt_1e-5"] = float(np.mean(rel(sc.closest_silhouette(q), rs) > 1e-5))
+        if ref_available("cpu") and len(f) <= 200000:
+            # the reference against ITSELF: same headers on Thrust's CPP backend (no FMA contraction) vs its CUDA build
+            rcpu = RefScene(v, f, "cpu")
+            ns = min(n, 20000)
+            row["refcpu_vs_refcuda_sil_frac"] = float(np.mean(rel(rcpu.silhouette(q[:ns]), rs[:ns]) > 1e-5))
+            row["refcpu_vs_refcuda_closest_frac"] = float(np.mean(rel(rcpu.closest(q[:ns])[1], rd[:ns]) > 1e-5))
         rf, rt, _, _ = ref.ray(q, d)
         row["refcuda_ray_found_eq"] = float(np.mean(found.astype(bool) == rf.astype(bool)))
         both = found.astype(bool) & rf.astype(bool)

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""A/B table of the scheduling knobs on the bench workload (GPU box only; diagnostic, not a bench value).
+
+    python tools/variants.py [--queries N] [--torus 708] > gpurun_out/<tag>/variants.json
+
+For every knob setting: device time (CUDA events, best of 3 after one warm-up) of the closest-point, bounded and
+unbounded silhouette and ray kernels on the C3 query set, and whether the results are bit-identical to the default
+setting's (they must be: knobs only change scheduling).
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import snch_lbvh_b200 as pkg
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--queries", type=int, default=1 << 24)
+    ap.add_argument("--torus", type=int, default=708)
+    ap.add_argument("--sets", default="all")
+    args = ap.parse_args()
+    m = pkg.meshes
+    n = args.queries
+    v, f = m.bumpy_torus(args.torus, args.torus)
+    lo, hi = m.mesh_bounds(v)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    q = torch.from_numpy(m.points_in_box(n, lo, hi, 1.1, seed=2025)).cuda()
+    d = torch.from_numpy(m.unit_directions(n, seed=77)).cuda()
+    s = torch.from_numpy(m.star_radius_scale(n, seed=4242)).cuda()
+    _, dcp = sc.closest_point(q)
+    rmax = (dcp * s).contiguous()
+    stream = torch.cuda.current_stream()
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        out = None
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            out = fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best, out
+
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0}
+    settings = [("default", {}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
+                ("no_seed", {"query.seed": 0}), ("sort_bits_30", {"query.sort_bits": 30}), ("sort_rays", {"query.sort_rays": 1}), ("sort_bits_18", {"query.sort_bits": 18}),
+                ("blocks_per_sm_4", {"query.blocks_per_sm": 4}), ("blocks_per_sm_6", {"query.blocks_per_sm": 6}),
+                ("no_sort_no_filter_no_seed", {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0})]
+    if args.sets != "all":
+        settings = [x for x in settings if x[0] in args.sets.split(",")]
+    ref = {}
+    table = {}
+    for name, kv in settings:
+        for k, val in {**defaults, **kv}.items():
+            sc.set_option(k, val)
+        row = {}
+        t, (idx, dist) = timed(lambda: sc.closest_point(q))
+        row["closest_ms"], row["closest_mqps"] = t, n / t / 1e3
+        t, sb = timed(lambda: sc.closest_silhouette(q, r_max=rmax))
+        row["sil_bounded_ms"], row["sil_bounded_mqps"] = t, n / t / 1e3
+        t, su = timed(lambda: sc.closest_silhouette(q))
+        row["sil_unbounded_ms"], row["sil_unbounded_mqps"] = t, n / t / 1e3
+        t, (fd, hits) = timed(lambda: sc.intersect(q, d))
+        row["ray_ms"], row["ray_mqps"] = t, n / t / 1e3
+        t, (fa, _) = timed(lambda: sc.intersect(q, d, any_hit=True))
+        row["ray_any_ms"] = t
+        res = {"dist": dist, "sb": sb, "su": su, "t": hits[:, 0].contiguous(), "found": fd}
+        if not ref:
+            ref = {k: x.clone() for k, x in res.items()}
+        row["identical_to_default"] = {k: bool(torch.equal(ref[k].view(torch.int32) if ref[k].dtype == torch.float32 else ref[k],
+                                                           x.view(torch.int32) if x.dtype == torch.float32 else x)) for k, x in res.items()}
+        table[name] = row
+        print(name, json.dumps(row), file=sys.stderr, flush=True)
+    print(json.dumps({"queries": n, "triangles": len(f), "table": table}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
