@@ -143,6 +143,8 @@ int snch_sample_in_sphere_batch(const snch_scene *s, const float *spheres_xyzr, 
  *   "query.sort_min_n"  batches at least this large are visited in Morton order of the query points (default 16384; 0 = never)
  *   "query.sort_bits"   key bits of that ordering (8..30, default 24)
  *   "query.sort_rays"   also order ray batches by origin (default 0)
+ *   "query.packet"      bit mask: ordered batches walked by whole warps (one node fetch per warp, ballots pick the children)
+ *                       instead of one traversal per lane.  bit 0 closest point, bit 1 silhouette (default 1)
  *   "query.cone_filter" silhouette: guard-banded sine-space evaluation of the normal-cone test (default 1; 0 = always cone.cuh:168-212 verbatim)
  *   "query.seed"        closest point: bound each query by the triangle that answered the lane's previous query (default 1)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)

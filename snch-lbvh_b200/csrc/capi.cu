@@ -609,6 +609,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     if (k == "query.sort_min_n") t.sort_min_n = (int)value;
     else if (k == "query.sort_bits") t.sort_bits = (int)value;
     else if (k == "query.sort_rays") t.sort_rays = (int)value;
+    else if (k == "query.packet") t.packet = (int)value;
     else if (k == "query.cone_filter") t.cone_filter = (int)value;
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;

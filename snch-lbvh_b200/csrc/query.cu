@@ -148,8 +148,11 @@ __global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ 
     }
 }
 // 30-bit Morton key of each query point inside the batch's own bounding box (a scheduling hint only: any key is correct)
+// With `radius` (silhouette star radii) the top 4 key bits are the radius octave relative to the batch extent, so the 32
+// queries a warp walks together also have similar search radii (a scheduling hint only: any key is correct).
 __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q, int stride, uint32_t n, const int *__restrict__ box,
-                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ perm)
+                                                    const float *__restrict__ radius, uint32_t *__restrict__ keys,
+                                                    uint32_t *__restrict__ perm)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -162,6 +165,15 @@ __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q,
         float t = (x - lo) / fmaxf(hi - lo, FLT_MIN) * 1024.0f;
         t = fminf(fmaxf(t, 0.0f), 1023.0f); // NaN -> 0
         code |= expand_bits10((uint32_t)t) << (2 - a);
+    }
+    if (radius)
+    {
+        const float ext = fmaxf(fmaxf(ord2f_q(box[3]) - ord2f_q(box[0]), ord2f_q(box[4]) - ord2f_q(box[1])),
+                                fmaxf(ord2f_q(box[5]) - ord2f_q(box[2]), FLT_MIN));
+        const float r = __ldg(radius + i);
+        const int oct = (int)((__float_as_uint(fmaxf(r, 0.0f)) >> 23) & 0xFFu) - (int)((__float_as_uint(ext) >> 23) & 0xFFu); // floor(log2(r/ext))
+        const uint32_t cls = (uint32_t)min(max(oct + 13, 0), 15); // >= 4 x extent (incl. +inf) -> 15; NaN -> 0
+        code = (cls << 26) | (code >> 4);
     }
     keys[i] = code;
     perm[i] = i;
@@ -285,6 +297,121 @@ __global__ void __launch_bounds__(kQueryThreads)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// warp-cooperative ("packet") traversal for Morton-ordered batches
+// ---------------------------------------------------------------------------------------------------------------
+// The 32 lanes of a warp hold 32 consecutive queries of the ordered batch and walk the tree TOGETHER: one node record is
+// fetched per warp (a single broadcast sector per load instead of 32 divergent ones), every lane tests its own query
+// against it, and __ballot_sync decides which children any lane still needs.  The traversal stack is per warp (node +
+// lane mask, in shared memory); per-lane state is just the running best.  Lanes only ever skip work they could not use
+// (mindist >= their best / their cone test failed), so each lane's result is exactly what its own traversal returns.
+struct PacketStack
+{
+    uint2 e[kStackDepth];
+};
+
+__global__ void __launch_bounds__(kQueryThreads)
+    k_closest_packet(SceneView sv, const float *__restrict__ q, const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ out_idx,
+                     float *__restrict__ out_dist, unsigned long long *counter, int use_seed)
+{
+    __shared__ PacketStack s_stack[kQueryThreads / 32];
+    const int lane = threadIdx.x & 31;
+    uint2 *stk = s_stack[threadIdx.x >> 5].e;
+    uint32_t best_leaf = kNone;
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        const uint32_t s = (uint32_t)base + lane;
+        const bool valid = s < n;
+        const uint32_t slot = valid ? __ldg(perm + s) : 0u;
+        const V3 p = valid ? load_point(q, slot) : V3{0.f, 0.f, 0.f};
+        float best2 = INFINITY;
+        uint32_t best = kNone;
+        if (use_seed && valid && best_leaf != kNone)
+        { // the triangle that answered this lane's previous (neighbouring) query bounds this one
+            const LTri *tp = sv.ltri + best_leaf;
+            float4 t0, t1, t2, t3;
+            ld256(tp, t0, t1);
+            ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+            float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+            dist *= dist;
+            if (dist < INFINITY)
+            {
+                best2 = dist;
+                best = __float_as_uint(t0.w);
+            }
+            else best_leaf = kNone;
+        }
+        unsigned mask = __ballot_sync(kFull, valid);
+        uint32_t node = 0;
+        int sp = 0;
+        for (;;)
+        {
+            float4 a, b, c, d;
+            ld256(sv.bnode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y); // warp-uniform
+            const bool in = (mask >> lane) & 1u;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            { // leaf children are tested at once: they tighten the bounds before the sibling subtree is considered
+                const uint32_t r = ch ? r1 : r0;
+                if (!(r & kLeafFlag)) continue;
+                const bool w = in && ((ch ? m1 : m0) < best2);
+                if (!__any_sync(kFull, w)) continue;
+                const uint32_t k = r & ~kLeafFlag;
+                const LTri *tp = sv.ltri + k;
+                float4 t0, t1, t2, t3;
+                ld256(tp, t0, t1);
+                ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+                dist *= dist; // the reference squares the distance it got back (query.cuh:284-285)
+                if (w && dist < best2)
+                {
+                    best2 = dist;
+                    best = __float_as_uint(t0.w);
+                    best_leaf = k;
+                }
+            }
+            const bool w0 = in && !(r0 & kLeafFlag) && m0 < best2;
+            const bool w1 = in && !(r1 & kLeafFlag) && m1 < best2;
+            const unsigned b0 = __ballot_sync(kFull, w0), b1 = __ballot_sync(kFull, w1);
+            if (b0 && b1)
+            { // both needed: enter the child most lanes are nearer to, keep the other with the lanes that want it
+                const unsigned near1 = __ballot_sync(kFull, (w0 && w1) ? (m1 < m0) : w1);
+                const bool first1 = 2 * __popc(near1) > __popc(b0 | b1);
+                stk[sp] = first1 ? make_uint2(r0, b0) : make_uint2(r1, b1);
+                ++sp;
+                node = first1 ? r1 : r0;
+                mask = first1 ? b1 : b0;
+            }
+            else if (b0 | b1)
+            {
+                node = b0 ? r0 : r1;
+                mask = b0 | b1;
+            }
+            else
+            {
+                if (sp == 0) break;
+                --sp;
+                const uint2 e = stk[sp];
+                node = e.x;
+                mask = e.y;
+            }
+        }
+        if (valid)
+        {
+            out_idx[slot] = best;
+            out_dist[slot] = sqrtf(best2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // nearest silhouette                                                                     query.cuh:325-423
 // ---------------------------------------------------------------------------------------------------------------
 // The reference's view-cone test (cone.cuh:168-212) is, in real arithmetic,  |acos(t) - pi/2| <= alpha + beta  (or
@@ -345,6 +472,14 @@ template <bool kFilter> SNCH_DI bool cone_test(V3 axis, float half_angle, float 
     return cone_overlap(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
 }
 
+// Per-lane traversal with DEFERRED leaves.  A leaf costs up to three edge tests (~100 instructions each) and only one lane
+// in ~15 reaches one in a given step: tested inline, that code ran at 2 of 32 lanes and was 42% of all issued
+// instructions (profiles/r01b_*).  Instead a lane parks the leaves it reaches (at the top end of its stack array) and the
+// warp tests parked leaves together — when half the warp has some, when a lane's park is nearly full, or when a lane has
+// finished its walk and needs its answer.  A parked leaf only delays a tightening of that lane's own bound, so the
+// result is unchanged.
+constexpr int kParkCap = 8;     // parked leaves per lane (stack slots kStackDepth-1 downwards)
+constexpr int kParkFlushLanes = 16;
 template <bool kFilter>
 __global__ void __launch_bounds__(kQueryThreads)
     k_silhouette(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
@@ -352,18 +487,59 @@ __global__ void __launch_bounds__(kQueryThreads)
 {
     const int lane = threadIdx.x & 31;
     Feeder fd{0u, 0u, false};
-    StackEntry stk[kStackDepth];
-    int sp = 0;
+    StackEntry stk[kStackDepth + kParkCap];
+    int sp = 0, npark = 0;
     V3 p = V3{0.f, 0.f, 0.f};
-    bool flip = false, found = false;
+    bool flip = false, found = false, busy = false;
     float best = INFINITY, best2 = INFINITY;
     uint32_t slot = kNone, node = kNone;
     for (;;)
     {
-        const unsigned idle = __ballot_sync(kFull, node == kNone);
+        // ---- 1. parked leaves
+        const unsigned parked = __ballot_sync(kFull, npark > 0);
+        if (parked && (__popc(parked) >= kParkFlushLanes || __any_sync(kFull, npark >= kParkCap - 2 || (npark > 0 && node == kNone))))
+        {
+            while (__any_sync(kFull, npark > 0))
+            {
+                if (npark > 0)
+                {
+                    --npark;
+                    const StackEntry se = stk[kStackDepth + npark];
+                    if (se.key <= best2)
+                    {
+                        const uint32_t first = se.node >> 2, cnt = se.node & 3u;
+                        for (uint32_t k = 0; k < cnt; ++k)
+                        { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
+                            float4 e0, e1, e2, e3;
+                            ld256(sv.ledge + first + k, e0, e1);
+                            ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
+                            const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
+                            V3 cp;
+                            const float dist = point_segment_distance(pa, pb, p, &cp);
+                            if (dist * dist > best2) continue;
+                            bool is_sil = isnan(e1.z); // boundary edge
+                            if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
+                            if (is_sil && dist <= best)
+                            {
+                                best = dist;
+                                best2 = dist * dist;
+                                found = true;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- 2. finished walks hand in their answer; idle lanes take the next query
+        if (busy && node == kNone && npark == 0)
+        {
+            out_dist[slot] = found ? best : INFINITY;
+            busy = false;
+        }
+        const unsigned idle = __ballot_sync(kFull, !busy);
         if (idle)
         {
-            const uint32_t s = feeder_take(fd, idle, node == kNone, lane, n, counter);
+            const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter);
             if (s != kNone)
             {
                 slot = perm ? __ldg(perm + s) : s;
@@ -372,14 +548,15 @@ __global__ void __launch_bounds__(kQueryThreads)
                 best = rmax ? __ldg(rmax + slot) : INFINITY;
                 best2 = best * best;
                 found = false;
+                busy = true;
                 sp = 0;
                 node = 0;
             }
-            if (fd.exhausted && __all_sync(kFull, node == kNone)) break;
+            if (fd.exhausted && __all_sync(kFull, !busy)) break;
         }
+        // ---- 3. one traversal step
         if (node != kNone)
         {
-
             float4 a, b, c, d, e, f;
             ld256(sv.snode + node, a, b);
             ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
@@ -393,36 +570,18 @@ __global__ void __launch_bounds__(kQueryThreads)
             const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
             const bool swap = m1 < m0;
             uint32_t next = kNone;
-    #pragma unroll
+#pragma unroll
             for (int ch = 0; ch < 2; ++ch)
             {
                 const bool second = (ch == 1) != swap; // visit the nearer child first
                 const bool h = second ? h1 : h0;
                 const float m = second ? m1 : m0;
                 const uint32_t r = second ? r1 : r0;
-                if (!h || !(m <= best2)) continue;
+                if (!h) continue;
                 if (r & kLeafFlag)
                 {
-                    const uint32_t payload = r & ~kLeafFlag;
-                    const uint32_t first = payload >> 2, cnt = payload & 3u;
-                    for (uint32_t k = 0; k < cnt; ++k)
-                    { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
-                        float4 e0, e1, e2, e3;
-                        ld256(sv.ledge + first + k, e0, e1);
-                        ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
-                        const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
-                        V3 cp;
-                        const float dist = point_segment_distance(pa, pb, p, &cp);
-                        if (dist * dist > best2) continue;
-                        bool is_sil = isnan(e1.z); // boundary edge
-                        if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
-                        if (is_sil && dist <= best)
-                        {
-                            best = dist;
-                            best2 = dist * dist;
-                            found = true;
-                        }
-                    }
+                    stk[kStackDepth + npark] = StackEntry{r & ~kLeafFlag, m};
+                    ++npark;
                 }
                 else if (next == kNone) next = r;
                 else
@@ -443,10 +602,107 @@ __global__ void __launch_bounds__(kQueryThreads)
                         break;
                     }
                 }
-                if (next == kNone) out_dist[slot] = found ? best : INFINITY;
             }
             node = next;
         }
+    }
+}
+
+template <bool kFilter>
+__global__ void __launch_bounds__(kQueryThreads)
+    k_silhouette_packet(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
+                        const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+{
+    __shared__ PacketStack s_stack[kQueryThreads / 32];
+    const int lane = threadIdx.x & 31;
+    uint2 *stk = s_stack[threadIdx.x >> 5].e;
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 32ull);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        const uint32_t s = (uint32_t)base + lane;
+        const bool valid = s < n;
+        const uint32_t slot = valid ? __ldg(perm + s) : 0u;
+        const V3 p = valid ? load_point(q, slot) : V3{0.f, 0.f, 0.f};
+        const bool flip = (valid && flipv) ? (__ldg(flipv + slot) != 0) : false;
+        float best = (valid && rmax) ? __ldg(rmax + slot) : INFINITY;
+        float best2 = best * best;
+        bool found = false;
+        unsigned mask = __ballot_sync(kFull, valid);
+        uint32_t node = 0;
+        int sp = 0;
+        for (;;)
+        {
+            float4 a, b, c, d, e, f;
+            ld256(sv.snode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
+            ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w); // warp-uniform
+            const bool in = (mask >> lane) & 1u;
+            // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367)
+            bool h0 = in && (m0 <= best2) && (d.w >= 0.0f);
+            bool h1 = in && (m1 <= best2) && (f.x >= 0.0f);
+            if (h0) h0 = cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+            if (h1) h1 = cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const uint32_t r = ch ? r1 : r0;
+                if (!(r & kLeafFlag)) continue;
+                const bool w = (ch ? h1 : h0) && ((ch ? m1 : m0) <= best2);
+                if (!__any_sync(kFull, w)) continue;
+                const uint32_t payload = r & ~kLeafFlag;
+                const uint32_t first = payload >> 2, cnt = payload & 3u;
+                for (uint32_t k = 0; k < cnt; ++k)
+                { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
+                    float4 e0, e1, e2, e3;
+                    ld256(sv.ledge + first + k, e0, e1);
+                    ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
+                    const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
+                    V3 cp;
+                    const float dist = point_segment_distance(pa, pb, p, &cp);
+                    if (!w || dist * dist > best2) continue;
+                    bool is_sil = isnan(e1.z); // boundary edge
+                    if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
+                    if (is_sil && dist <= best)
+                    {
+                        best = dist;
+                        best2 = dist * dist;
+                        found = true;
+                    }
+                }
+            }
+            const bool w0 = h0 && !(r0 & kLeafFlag) && m0 <= best2;
+            const bool w1 = h1 && !(r1 & kLeafFlag) && m1 <= best2;
+            const unsigned b0 = __ballot_sync(kFull, w0), b1 = __ballot_sync(kFull, w1);
+            if (b0 && b1)
+            {
+                const unsigned near1 = __ballot_sync(kFull, (w0 && w1) ? (m1 < m0) : w1);
+                const bool first1 = 2 * __popc(near1) > __popc(b0 | b1);
+                stk[sp] = first1 ? make_uint2(r0, b0) : make_uint2(r1, b1);
+                ++sp;
+                node = first1 ? r1 : r0;
+                mask = first1 ? b1 : b0;
+            }
+            else if (b0 | b1)
+            {
+                node = b0 ? r0 : r1;
+                mask = b0 | b1;
+            }
+            else
+            {
+                if (sp == 0) break;
+                --sp;
+                const uint2 en = stk[sp];
+                node = en.x;
+                mask = en.y;
+            }
+        }
+        if (valid) out_dist[slot] = found ? best : INFINITY;
     }
 }
 
@@ -684,8 +940,8 @@ uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
 }
 
 // Lays the scratch out and, for batches worth ordering, produces the Morton permutation.  *perm_out = nullptr otherwise.
-static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, uint32_t n, unsigned char *scratch, cudaStream_t st,
-                         unsigned long long **counter_out, const uint32_t **perm_out)
+static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n,
+                         unsigned char *scratch, cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out)
 {
     SNCH_CUDA(cudaMemsetAsync(scratch, 0, 64, st));
     *counter_out = reinterpret_cast<unsigned long long *>(scratch);
@@ -701,7 +957,7 @@ static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int
     const unsigned g = (n + 255) / 256;
     k_query_box_init<<<1, 32, 0, st>>>(box);
     k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, n, box);
-    k_query_keys<<<g, 256, 0, st>>>(pts, stride, n, box, keys, perm);
+    k_query_keys<<<g, 256, 0, st>>>(pts, stride, n, box, radius, keys, perm);
     int bits = t.sort_bits < 8 ? 8 : (t.sort_bits > 30 ? 30 : t.sort_bits);
     radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
     SNCH_CUDA(cudaGetLastError());
@@ -740,9 +996,13 @@ int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uin
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, true, q, 3, (uint32_t)n, scratch, st, &counter, &perm);
+    const int rc = prepare_batch(t, true, q, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm);
     if (rc != SNCH_OK) return rc;
-    k_closest<<<persistent_grid(k_closest, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist, counter, t.seed);
+    if (perm && (t.packet & 1))
+        k_closest_packet<<<persistent_grid(k_closest_packet, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist,
+                                                                                                   counter, t.seed);
+    else
+        k_closest<<<persistent_grid(k_closest, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist, counter, t.seed);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
@@ -758,9 +1018,18 @@ int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, 
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, true, q, 3, (uint32_t)n, scratch, st, &counter, &perm);
+    const int rc = prepare_batch(t, true, q, 3, (t.packet & 2) ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm);
     if (rc != SNCH_OK) return rc;
-    if (t.cone_filter)
+    if (perm && (t.packet & 2))
+    {
+        if (t.cone_filter)
+            k_silhouette_packet<true><<<persistent_grid(k_silhouette_packet<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
+                v, q, flip, rmax, perm, (uint32_t)n, dist, counter);
+        else
+            k_silhouette_packet<false><<<persistent_grid(k_silhouette_packet<false>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
+                v, q, flip, rmax, perm, (uint32_t)n, dist, counter);
+    }
+    else if (t.cone_filter)
         k_silhouette<true><<<persistent_grid(k_silhouette<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, (uint32_t)n,
                                                                                                         dist, counter);
     else
@@ -781,7 +1050,7 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, (uint32_t)n, scratch, st, &counter, &perm);
+    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm);
     if (rc != SNCH_OK) return rc;
     if (any_hit)
         k_intersect<true><<<persistent_grid(k_intersect<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, (uint32_t)n, hits,

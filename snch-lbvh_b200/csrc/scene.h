@@ -15,6 +15,7 @@ struct QueryTuning
     int sort_min_n = 16384; // batches at least this large are visited in Morton order of the query points (0 = never)
     int sort_bits = 24;     // Morton key bits the ordering sorts on (top bits of the 30-bit code)
     int sort_rays = 0;      // also order ray batches by origin (off: random directions decorrelate the paths anyway)
+    int packet = 1;         // warp-cooperative traversal of ordered batches: bit 0 closest point, bit 1 silhouette
     int cone_filter = 1;    // silhouette: guard-banded sine-space normal-cone test (0 = always the reference's libm chain)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)

@@ -42,3 +42,7 @@ if has ncu; then
   echo "ncu full closest exit $?"
 fi
 ls -la "$OUT"
+if has parity; then
+  timeout 900 python tools/parity_report.py > "$OUT/parity_report.log" 2>&1
+  echo "parity report exit $?"; cp gpurun_out/parity_report.json "$OUT/parity_report.json" 2>/dev/null
+fi
