@@ -148,8 +148,16 @@ int snch_sample_in_sphere_batch(const snch_scene *s, const float *spheres_xyzr, 
  *   "query.cone_filter" silhouette: guard-banded sine-space evaluation of the normal-cone test (default 1; 0 = always cone.cuh:168-212 verbatim)
  *   "query.seed"        closest point: bound each query by the triangle that answered the lane's previous query (default 1)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
- * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel). */
+ * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel).
+ *   "query.time_kernels" bracket every traversal kernel with CUDA events on the launching stream (default 0; see snch_scene_counter) */
 int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
+
+/* Launch accounting since creation / the last reset (what bench.py reports as gpu_launches and roofline.achieved):
+ *   "query.launches"            kernels launched by the *_batch calls (ordering + traversal)
+ *   "query.traversal_launches"  traversal kernels among them
+ *   "query.traversal_ms"        device time of the traversal kernels alone; needs "query.time_kernels" = 1 (synchronises the last one)
+ *   "build.launches"            kernels of the last snch_scene_build */
+int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Replication (multi-GPU): the built scene lives in ONE pointer-free arena.  Rank 0 exposes it, the caller

@@ -659,12 +659,14 @@ int build_device(snch_scene *s, cudaStream_t stream)
     k_init_box<<<1, 32, 0, stream>>>(c.scene_box);
     k_scene_box<<<g256 < 1184 ? g256 : 1184, 256, 0, stream>>>(c);
     k_morton<<<g256, 256, 0, stream>>>(c);
-    radix_sort_pairs(c.morton, c.sorted_idx, (uint32_t *)(sc + o_ktmp), (uint32_t *)(sc + o_vtmp), nT, 30, (uint32_t *)(sc + o_sort),
-                     stream);
+    int launches = 3; // k_init_box, k_scene_box, k_morton
+    launches += radix_sort_pairs(c.morton, c.sorted_idx, (uint32_t *)(sc + o_ktmp), (uint32_t *)(sc + o_vtmp), nT, 30,
+                                 (uint32_t *)(sc + o_sort), stream);
     if (nT > 1) k_hierarchy<<<(nT - 1 + 255) / 256, 256, 0, stream>>>(c);
     k_owned_count<<<g256, 256, 0, stream>>>(c);
-    exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream);
+    launches += (nT > 1 ? 1 : 0) + 1 + exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream) + 1;
     k_refit<<<(nT + 127) / 128, 128, 0, stream>>>(c);
+    s->build_launches = (uint64_t)launches;
     SNCH_CUDA(cudaGetLastError());
     SNCH_CUDA(cudaEventRecord(ev1, stream));
 

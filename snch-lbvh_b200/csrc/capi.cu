@@ -216,6 +216,8 @@ int snch_scene_destroy(snch_scene *s)
     if (s->arena) cudaFree(s->arena);
     if (s->scratch) cudaFree(s->scratch);
     if (s->pool) cudaMemPoolDestroy(s->pool);
+    if (s->counters.ev0) cudaEventDestroy(s->counters.ev0);
+    if (s->counters.ev1) cudaEventDestroy(s->counters.ev1);
     delete s;
     return SNCH_OK;
 }
@@ -431,7 +433,7 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
         if (buf.status != SNCH_OK) return buf.status;
         if (k == PK_DEVICE)
         {
-            st = launch_closest(s->view, s->tuning, pts + 3 * off, m, out_index + off, out_distance + off, buf.p, cst);
+            st = launch_closest(s->view, s->tuning, pts + 3 * off, m, out_index + off, out_distance + off, buf.p, cst, &s->counters);
             if (st != SNCH_OK) return st;
             continue;
         }
@@ -440,7 +442,7 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
         uint32_t *di = sg.out(out_index + off, m * 4);
         float *dd = sg.out(out_distance + off, m * 4);
         if (sg.status != SNCH_OK) return sg.status;
-        st = launch_closest(s->view, s->tuning, dq, m, di, dd, buf.p, cst);
+        st = launch_closest(s->view, s->tuning, dq, m, di, dd, buf.p, cst, &s->counters);
         if (st != SNCH_OK) return st;
         st = sg.finish();
         if (st != SNCH_OK) return st;
@@ -479,7 +481,7 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
         const float *ro = r_max ? r_max + off : nullptr;
         if (k == PK_DEVICE)
         {
-            st = launch_silhouette(s->view, s->tuning, pts + 3 * off, fo, ro, m, out_distance + off, buf.p, cst);
+            st = launch_silhouette(s->view, s->tuning, pts + 3 * off, fo, ro, m, out_distance + off, buf.p, cst, &s->counters);
             if (st != SNCH_OK) return st;
             continue;
         }
@@ -489,7 +491,7 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
         const float *dr = sg.in(ro, m * 4);
         float *dd = sg.out(out_distance + off, m * 4);
         if (sg.status != SNCH_OK) return sg.status;
-        st = launch_silhouette(s->view, s->tuning, dq, df, dr, m, dd, buf.p, cst);
+        st = launch_silhouette(s->view, s->tuning, dq, df, dr, m, dd, buf.p, cst, &s->counters);
         if (st != SNCH_OK) return st;
         st = sg.finish();
         if (st != SNCH_OK) return st;
@@ -529,7 +531,7 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
         uint8_t *fo = out_found ? out_found + off : nullptr;
         if (k == PK_DEVICE)
         {
-            st = launch_intersect(s->view, s->tuning, org + 3 * off, dir + 3 * off, to, m, ho, fo, any_hit, buf.p, cst);
+            st = launch_intersect(s->view, s->tuning, org + 3 * off, dir + 3 * off, to, m, ho, fo, any_hit, buf.p, cst, &s->counters);
             if (st != SNCH_OK) return st;
             continue;
         }
@@ -540,7 +542,7 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
         snch_hit *dh = sg.out(ho, m * sizeof(snch_hit));
         uint8_t *df = sg.out(fo, m);
         if (sg.status != SNCH_OK) return sg.status;
-        st = launch_intersect(s->view, s->tuning, dor, ddi, dtm, m, dh, df, any_hit, buf.p, cst);
+        st = launch_intersect(s->view, s->tuning, dor, ddi, dtm, m, dh, df, any_hit, buf.p, cst, &s->counters);
         if (st != SNCH_OK) return st;
         st = sg.finish();
         if (st != SNCH_OK) return st;
@@ -578,7 +580,7 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
         float *po = out_point ? out_point + 3 * off : nullptr;
         if (k == PK_DEVICE)
         {
-            st = launch_sample(s->view, s->tuning, spheres + 4 * off, rnd + 3 * off, m, out_index + off, out_pdf + off, po, buf.p, cst);
+            st = launch_sample(s->view, s->tuning, spheres + 4 * off, rnd + 3 * off, m, out_index + off, out_pdf + off, po, buf.p, cst, &s->counters);
             if (st != SNCH_OK) return st;
             continue;
         }
@@ -589,10 +591,42 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
         float *dp = sg.out(out_pdf + off, m * 4);
         float *dpt = sg.out(po, m * 12);
         if (sg.status != SNCH_OK) return sg.status;
-        st = launch_sample(s->view, s->tuning, ds, dr, m, di, dp, dpt, buf.p, cst);
+        st = launch_sample(s->view, s->tuning, ds, dr, m, di, dp, dpt, buf.p, cst, &s->counters);
         if (st != SNCH_OK) return st;
         st = sg.finish();
         if (st != SNCH_OK) return st;
+    }
+    return SNCH_OK;
+}
+
+int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset)
+{
+    if (!s || !name || !value)
+    {
+        set_error("snch_scene_counter: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    const std::string k(name);
+    QueryCounters &c = s->counters;
+    if (k == "query.launches") *value = (double)c.launches;
+    else if (k == "query.traversal_launches") *value = (double)c.traversal_launches;
+    else if (k == "query.traversal_ms")
+    {
+        cudaSetDevice(s->device);
+        c.fold();
+        *value = c.traversal_ms;
+    }
+    else if (k == "build.launches") *value = (double)s->build_launches;
+    else
+    {
+        set_error("snch_scene_counter: unknown counter '" + k + "'");
+        return SNCH_ERR_INVALID;
+    }
+    if (reset)
+    {
+        c.fold();
+        c.launches = c.traversal_launches = 0;
+        c.traversal_ms = 0.0;
     }
     return SNCH_OK;
 }
@@ -613,6 +647,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.cone_filter") t.cone_filter = (int)value;
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
+    else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else
     {
         set_error("snch_scene_set_option: unknown option '" + k + "'");

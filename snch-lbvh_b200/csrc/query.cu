@@ -929,6 +929,44 @@ __global__ void k_fill_empty(uint64_t n, uint32_t *idx, float *dist, snch_hit *h
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+// Counts the traversal launch and, when kernel timing is on ("query.time_kernels"), brackets it with CUDA events on the
+// launching stream; the elapsed time of the PREVIOUS timed launch is folded into the counters lazily.
+struct TraversalTimer
+{
+    QueryCounters *qc;
+    cudaStream_t st;
+    TraversalTimer(QueryCounters *qc_, cudaStream_t st_) : qc(qc_), st(st_)
+    {
+        if (!qc) return;
+        qc->launches += 1;
+        qc->traversal_launches += 1;
+        if (!qc->time_kernels) return;
+        qc->fold();
+        if (!qc->ev0)
+        {
+            cudaEventCreate(&qc->ev0);
+            cudaEventCreate(&qc->ev1);
+        }
+        cudaEventRecord(qc->ev0, st);
+    }
+    ~TraversalTimer()
+    {
+        if (qc && qc->time_kernels && qc->ev0)
+        {
+            cudaEventRecord(qc->ev1, st);
+            qc->pending = true;
+        }
+    }
+};
+void QueryCounters::fold()
+{
+    if (!pending) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) traversal_ms += ms;
+    else cudaGetLastError();
+    pending = false;
+}
+
 static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kQueryThreads - 1) / kQueryThreads); }
 
 // bytes of device scratch one batch of n queries needs (ordering buffers + sort counters + the work counter)
@@ -941,7 +979,8 @@ uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
 
 // Lays the scratch out and, for batches worth ordering, produces the Morton permutation.  *perm_out = nullptr otherwise.
 static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n,
-                         unsigned char *scratch, cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out)
+                         unsigned char *scratch, cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out,
+                         QueryCounters *qc)
 {
     SNCH_CUDA(cudaMemsetAsync(scratch, 0, 64, st));
     *counter_out = reinterpret_cast<unsigned long long *>(scratch);
@@ -959,7 +998,8 @@ static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int
     k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, n, box);
     k_query_keys<<<g, 256, 0, st>>>(pts, stride, n, box, radius, keys, perm);
     int bits = t.sort_bits < 8 ? 8 : (t.sort_bits > 30 ? 30 : t.sort_bits);
-    radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
+    const int sort_launches = radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
+    if (qc) qc->launches += 3 + sort_launches;
     SNCH_CUDA(cudaGetLastError());
     *perm_out = perm;
     return SNCH_OK;
@@ -985,7 +1025,7 @@ template <typename K> static unsigned persistent_grid(K kernel, const QueryTunin
 }
 
 int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
-                   cudaStream_t st)
+                   cudaStream_t st, QueryCounters *qc)
 {
     if (n == 0) return SNCH_OK;
     if (v.n_tris == 0)
@@ -996,8 +1036,9 @@ int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uin
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, true, q, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm);
+    const int rc = prepare_batch(t, true, q, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
     if (rc != SNCH_OK) return rc;
+    TraversalTimer tt(qc, st);
     if (perm && (t.packet & 1))
         k_closest_packet<<<persistent_grid(k_closest_packet, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist,
                                                                                                    counter, t.seed);
@@ -1007,7 +1048,7 @@ int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uin
     return SNCH_OK;
 }
 int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax, uint64_t n,
-                      float *dist, unsigned char *scratch, cudaStream_t st)
+                      float *dist, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)
 {
     if (n == 0) return SNCH_OK;
     if (v.n_tris == 0)
@@ -1018,8 +1059,9 @@ int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, 
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, true, q, 3, (t.packet & 2) ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm);
+    const int rc = prepare_batch(t, true, q, 3, (t.packet & 2) ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
     if (rc != SNCH_OK) return rc;
+    TraversalTimer tt(qc, st);
     if (perm && (t.packet & 2))
     {
         if (t.cone_filter)
@@ -1039,7 +1081,7 @@ int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, 
     return SNCH_OK;
 }
 int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
-                     uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st)
+                     uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)
 {
     if (n == 0) return SNCH_OK;
     if (v.n_tris == 0)
@@ -1050,8 +1092,9 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm);
+    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
     if (rc != SNCH_OK) return rc;
+    TraversalTimer tt(qc, st);
     if (any_hit)
         k_intersect<true><<<persistent_grid(k_intersect<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, (uint32_t)n, hits,
                                                                                                       found, counter);
@@ -1062,7 +1105,7 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
     return SNCH_OK;
 }
 int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf,
-                  float *pt, unsigned char *scratch, cudaStream_t st)
+                  float *pt, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)
 {
     if (n == 0) return SNCH_OK;
     if (v.n_tris == 0)
@@ -1073,6 +1116,7 @@ int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, co
     }
     (void)t;
     (void)scratch; // one short root-to-leaf path per query: neither ordering nor work stealing pays for itself here
+    TraversalTimer tt(qc, st);
     k_sample<<<grid_for(n), kQueryThreads, 0, st>>>(v, sph, rnd, nullptr, (uint32_t)n, idx, pdf, pt);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;

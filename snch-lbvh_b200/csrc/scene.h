@@ -20,6 +20,17 @@ struct QueryTuning
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
 };
+// Launch accounting of the batched queries (snch_scene_counter): kernels launched, traversal kernels among them, and —
+// when "query.time_kernels" is set — device time of the traversal kernels alone (CUDA events on the launching stream).
+struct QueryCounters
+{
+    uint64_t launches = 0, traversal_launches = 0;
+    double traversal_ms = 0.0;
+    int time_kernels = 0;
+    bool pending = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void fold();
+};
 } // namespace snch
 
 struct snch_scene
@@ -43,6 +54,8 @@ struct snch_scene
     cudaMemPool_t pool = nullptr;
     std::mutex mu;
     snch::QueryTuning tuning;
+    snch::QueryCounters counters;
+    uint64_t build_launches = 0;
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0;
@@ -68,11 +81,11 @@ int patch_pointers(snch_scene *s, cudaStream_t stream);
 // query.cu — n <= 2^32 - 2^20 per launch (the C-ABI splits larger batches); `scratch` has query_scratch_bytes(n) bytes
 uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t);
 int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
-                   cudaStream_t st);
+                   cudaStream_t st, QueryCounters *qc);
 int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax, uint64_t n,
-                      float *dist, unsigned char *scratch, cudaStream_t st);
+                      float *dist, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
 int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
-                     uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st);
+                     uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
 int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf,
-                  float *pt, unsigned char *scratch, cudaStream_t st);
+                  float *pt, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
 } // namespace snch

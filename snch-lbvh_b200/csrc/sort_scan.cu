@@ -75,19 +75,20 @@ __global__ void __launch_bounds__(kScanThreads)
     }
 }
 
-void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *scratch, cudaStream_t stream)
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *scratch, cudaStream_t stream)
 {
-    if (n == 0) return;
+    if (n == 0) return 0;
     const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
     if (tiles == 1)
     {
         k_scan_apply<<<1, kScanThreads, 0, stream>>>(in, out, n, nullptr);
-        return;
+        return 1;
     }
     uint32_t *tile_sums = scratch;
     k_scan_reduce<<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, n, tile_sums);
-    exclusive_scan_u32(tile_sums, tile_sums, tiles, scratch + tiles + 1, stream);
+    const int inner = exclusive_scan_u32(tile_sums, tile_sums, tiles, scratch + tiles + 1, stream);
     k_scan_apply<<<(unsigned)tiles, kScanThreads, 0, stream>>>(in, out, n, tile_sums);
+    return inner + 2;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -172,10 +173,11 @@ __global__ void __launch_bounds__(kSortThreads)
     }
 }
 
-void radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
-                      uint32_t *scratch, cudaStream_t stream, int first_bit)
+int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
+                     uint32_t *scratch, cudaStream_t stream, int first_bit)
 {
-    if (n == 0) return;
+    if (n == 0) return 0;
+    int launches = 0;
     const uint32_t tiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
     uint32_t *counts = scratch;
     uint32_t *scan_scratch = scratch + (uint64_t)tiles * kSortBins;
@@ -185,7 +187,7 @@ void radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32
     {
         const int shift = first_bit + 8 * p;
         k_radix_hist<<<tiles, kSortThreads, 0, stream>>>(sk, n, shift, counts, tiles);
-        exclusive_scan_u32(counts, counts, (uint64_t)tiles * kSortBins, scan_scratch, stream);
+        launches += 2 + exclusive_scan_u32(counts, counts, (uint64_t)tiles * kSortBins, scan_scratch, stream);
         k_radix_scatter<<<tiles, kSortThreads, 0, stream>>>(sk, sv, dk, dv, n, shift, counts, tiles);
         uint32_t *t = sk;
         sk = dk;
@@ -199,6 +201,7 @@ void radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32
         cudaMemcpyAsync(keys, sk, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
         cudaMemcpyAsync(vals, sv, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream);
     }
+    return launches;
 }
 
 } // namespace snch

@@ -40,11 +40,12 @@ inline uint64_t sort_scratch_elems(uint64_t n)
     return counts + scan_scratch_elems(counts) + 8;
 }
 
-void exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *scratch, cudaStream_t stream);
+// both return the number of kernels they launched (the library reports launch counts, snch_scene_counter)
+int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *scratch, cudaStream_t stream);
 
 // Sorts (keys, vals) by key bits [first_bit, first_bit + bits), ascending, stable.  keys/vals are overwritten with the
 // result; keys_tmp/vals_tmp are ping-pong buffers of the same size; scratch has sort_scratch_elems(n) u32.
-void radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
+int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
                       uint32_t *scratch, cudaStream_t stream, int first_bit = 0);
 
 } // namespace snch
