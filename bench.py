@@ -37,6 +37,25 @@ TORUS = 708
 WORKLOAD = "C3: 16777216 nearest-silhouette queries, WoSt star radii (r_max = s*d_closest, s~U[0.5,4)), 1002528-triangle bumpy torus"
 
 
+class quiet_stdout:
+    """The reference prints "Morton code collision detected." on stdout from C++ (bvh.cuh:466); the bench line must be the
+    only thing on stdout, so fd 1 is pointed at stderr while reference code runs."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -353,25 +372,26 @@ def main():
         try:
             from oracle import RefScene, ref_available
             if ref_available("cuda"):
-                ns = 1 << 22
-                ref = RefScene(v, f, "cuda")
-                ref.time_construct(3)
-                rc = {"construct_ms": ref.timings()["construct_ms"], "build_bvh_ms_incl_host": ref.timings()["build_bvh_ms"],
-                      "compute_silhouettes_host_ms": ref.timings()["silhouettes_ms"], "sample": f"first {ns} of the C3 queries"}
-                d_h = m.unit_directions(ns, seed=77)
-                ref.silhouette(q_h[:ns])
-                ref.silhouette(q_h[:ns])
-                rc["silhouette_unbounded_mqps"] = ns / ref.last_ms / 1e3
-                ref.closest(q_h[:ns])
-                ref.closest(q_h[:ns])
-                rc["closest_mqps"] = ns / ref.last_ms / 1e3
-                ref.ray(q_h[:ns], d_h)
-                ref.ray(q_h[:ns], d_h)
-                rc["ray_mqps"] = ns / ref.last_ms / 1e3
-                rc["note"] = ("the reference has no r_max input (SURVEY Q5): its answer to the C3 workload is the unbounded "
-                              "query followed by a filter, i.e. silhouette_unbounded_mqps is its C3 throughput")
-                extra["reference_cuda"] = rc
-                extra["speedup_vs_reference_cuda_c3"] = value / world / rc["silhouette_unbounded_mqps"]
+                with quiet_stdout():
+                    ns = 1 << 22
+                    ref = RefScene(v, f, "cuda")
+                    ref.time_construct(3)
+                    rc = {"construct_ms": ref.timings()["construct_ms"], "build_bvh_ms_incl_host": ref.timings()["build_bvh_ms"],
+                          "compute_silhouettes_host_ms": ref.timings()["silhouettes_ms"], "sample": f"first {ns} of the C3 queries"}
+                    d_h = m.unit_directions(ns, seed=77)
+                    ref.silhouette(q_h[:ns])
+                    ref.silhouette(q_h[:ns])
+                    rc["silhouette_unbounded_mqps"] = ns / ref.last_ms / 1e3
+                    ref.closest(q_h[:ns])
+                    ref.closest(q_h[:ns])
+                    rc["closest_mqps"] = ns / ref.last_ms / 1e3
+                    ref.ray(q_h[:ns], d_h)
+                    ref.ray(q_h[:ns], d_h)
+                    rc["ray_mqps"] = ns / ref.last_ms / 1e3
+                    rc["note"] = ("the reference has no r_max input (SURVEY Q5): its answer to the C3 workload is the unbounded "
+                                  "query followed by a filter, i.e. silhouette_unbounded_mqps is its C3 throughput")
+                    extra["reference_cuda"] = rc
+                    extra["speedup_vs_reference_cuda_c3"] = value / world / rc["silhouette_unbounded_mqps"]
         except Exception as ex:  # baseline legs never break the bench line
             extra["reference_cuda_error"] = repr(ex)
         try:

@@ -82,7 +82,9 @@ def full(src, out):
         d = res[-1]
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
         tb = sum(d[k][0] * scale[d[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in d)
-        traffic[d["kernel"].split("::")[-1] + "_bytes_per_launch"] = tb
+        import re
+        short = re.sub(r"<.*", "", d["kernel"].split("::")[-1]).replace("void ", "").strip()
+        traffic[short + "_bytes_per_launch"] = tb
         print(name, {k: v for k, v in d.items() if k in ("kernel", "gpu__time_duration.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
                                                            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct")}, "dram bytes", tb)
     if traffic:
