@@ -160,6 +160,19 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
 int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Generic builder.  Replaces lbvh::bvh<Real,dim,Object,AABBGetter,ConeGetter,MortonCalc>::construct()   bvh.cuh:380-613
+ * for ANY object type: the caller (include/snch_lbvh/core/bvh.cuh) evaluates its getters per object and passes the leaf
+ * arrays; this runs scene box -> Morton (default_morton_code_calculator, bvh.cuh:232-304, unless morton_codes is given)
+ * -> stable sort -> Karras hierarchy on (code << 32 | index) -> one bottom-up box + cone refit.
+ * All pointers are DEVICE pointers.  dim = 2 or 3, float.  Record layouts are the reference's:
+ *   leaf_aabbs n x {upper[dim], lower[dim]}   leaf_cones n x {axis[dim], half_angle, radius}     (object order)
+ *   nodes (2n-1) x {parent,left,right,object}   aabbs / cones (2n-1) records, leaves at n-1.. in Morton order
+ * Optional outputs: sorted_index_out[n], morton_sorted_out[n] (device), *collision_out (host; forces a stream sync). */
+int snch_lbvh_build(int dim, uint32_t n, const void *leaf_aabbs, const void *leaf_cones, const uint32_t *morton_codes, void *nodes,
+                    void *aabbs, void *cones, uint32_t *sorted_index_out, uint32_t *morton_sorted_out, int *collision_out,
+                    snch_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Replication (multi-GPU): the built scene lives in ONE pointer-free arena.  Rank 0 exposes it, the caller
  * moves the bytes (ncclBroadcast / cudaMemcpyPeer / torch.distributed.broadcast) and every other rank adopts its copy.
  * ------------------------------------------------------------------------------------------------------------- */

@@ -18,7 +18,7 @@ ABI_SYMBOLS = [
     "snch_last_error", "snch_abi_version", "snch_scene3_create", "snch_scene_destroy", "snch_scene_compute_silhouettes",
     "snch_scene_build", "snch_scene_stats", "snch_scene_device_repr", "snch_scene_export", "snch_closest_point_batch",
     "snch_closest_silhouette_batch", "snch_intersect_batch", "snch_sample_in_sphere_batch", "snch_scene_arena",
-    "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter",
+    "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter", "snch_lbvh_build",
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
     L.snch_scene_adopt_arena.argtypes = [vp, u64, C.c_int, vp, C.POINTER(vp)]
     L.snch_scene_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.snch_scene_counter.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+    L.snch_lbvh_build.argtypes = [C.c_int, u32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]
     for name in ABI_SYMBOLS:
         if name not in ("snch_last_error",):
             getattr(L, name).restype = C.c_int

@@ -13,6 +13,7 @@
 #include "scene.h"
 #include "snch_math.cuh"
 #include "sort_scan.cuh"
+#include "build_ctx.h"
 
 #include <chrono>
 #include <cstdio>
@@ -152,29 +153,6 @@ void resolve_view(snch_scene *s)
 // ---------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
-struct BuildCtx
-{
-    uint32_t n, n_edges;
-    const float3 *verts;
-    const RefEdge *edges;
-    const RefTriangle *objects;
-    RefNode *nodes;
-    RefAabb *aabbs;
-    RefCone *cones;
-    uint32_t *morton, *sorted_idx;
-    uint2 *ranges;
-    uint8_t *q1;
-    BNode *bnode;
-    SNode *snode;
-    LTri *ltri;
-    LEdge *ledge;
-    uint32_t *edge_off;
-    // scratch
-    int *scene_box; // 6 ordered ints: lo xyz, hi xyz
-    uint32_t *flags;
-    uint32_t *counters; // [0] collision, [1] q1 events
-};
-
 SNCH_DI int f2ord(float f)
 {
     const int i = __float_as_int(f);

@@ -73,3 +73,21 @@ def test_product_never_touches_oracle():
                 assert not bad.search(txt), f"{fn} references the oracle"
     out = subprocess.check_output(["ldd", os.path.join(pk, "libsnch_b200.so")], text=True)
     assert "oracle" not in out and "snch_ref" not in out
+
+
+def test_cpp_dropin_headers_compile(tmp_path):
+    """include/snch_lbvh/*.cuh (the reference's header names) compile for sm_100a and instantiate both scene types."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    src = tmp_path / "tu.cu"
+    src.write_text('#include <snch_lbvh/lbvh.cuh>\n#include <snch_lbvh/scene.cuh>\n#include <snch_lbvh/scene_loader.cuh>\n'
+                   'template class lbvh::scene_loader<2>;\ntemplate class lbvh::scene_loader<3>;\n'
+                   '__global__ void k(lbvh::bvh_device<float, 3, lbvh::scene<3>::triangle> b, float3 p, float *o)\n'
+                   '{ *o = lbvh::query_device(b, lbvh::nearest(p), lbvh::scene<3>::distance_calculator()).second; }\n'
+                   'int main() { lbvh::scene<2> a; lbvh::scene<3> b; return a.lines.size() + b.triangles.size(); }\n')
+    out = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                          "-o", str(tmp_path / "tu.o")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
