@@ -189,7 +189,7 @@ int build_generic(uint32_t n, const void *leaf_aabbs, const void *leaf_cones, co
     k_gen_box_init<D><<<1, 32, 0, st>>>(box);
     k_gen_box<D><<<g < 1184 ? g : 1184, 256, 0, st>>>(lb, n, box);
     k_gen_morton<D><<<g, 256, 0, st>>>(lb, n, box, user_codes, keys, idx);
-    radix_sort_pairs(keys, idx, ktmp, vtmp, n, user_codes ? 32 : 10 * D, sscr, st);
+    radix_sort_pairs(keys, idx, ktmp, vtmp, n, user_codes ? 32 : 30, sscr, st); // 2-D codes interleave by 3 too (bits 0..28)
     k_gen_leaves<D><<<g, 256, 0, st>>>(lb, lc, idx, n, (RefNode *)nodes, (BoxT<D> *)aabbs, (ConeT<D> *)cones);
     if (n > 1)
     {
