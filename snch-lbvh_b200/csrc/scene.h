@@ -42,6 +42,13 @@ struct snch_scene
     std::vector<int32_t> h_tri;
     std::vector<int32_t> h_edges4, h_tri_edges, h_tri_owned;
     bool silhouettes_done = false, built = false, adopted = false;
+    // device-side adjacency (adjacency.cu): one allocation holding tri | tri_edges | tri_owned | edges4 until the first
+    // build assembles the reference-layout structs from it; then the arena is the only copy
+    int adjacency_mode = -1; // "adjacency.device": 1 = GPU, 0 = host passes, -1 = GPU when a CUDA device is present
+    bool adjacency_on_device = false, arena_has_topology = false;
+    unsigned char *adj = nullptr;
+    int32_t *adj_tri = nullptr, *adj_tri_edges = nullptr, *adj_tri_owned = nullptr;
+    int4 *adj_edges4 = nullptr;
     // one device arena
     unsigned char *arena = nullptr;
     uint64_t arena_bytes = 0;
@@ -71,6 +78,11 @@ int cuda_fail(cudaError_t e, const char *what);
         cudaError_t e__ = (call);                                    \
         if (e__ != cudaSuccess) return snch::cuda_fail(e__, #call);  \
     } while (0)
+
+// adjacency.cu
+int compute_adjacency_device(snch_scene *s);
+int fetch_adjacency_host(snch_scene *s);
+void free_adjacency(snch_scene *s);
 
 // build.cu
 void compute_adjacency_host(snch_scene *s);
