@@ -55,12 +55,19 @@ typedef struct snch_build_options
     uint32_t struct_size;       /* = sizeof(snch_build_options) */
     uint32_t keep_reference_layout; /* 1 (default): keep nodes/aabbs/cones/objects arrays of bvh_device (bvh.cuh:48-54) */
     uint32_t print_collision;   /* 1: print "Morton code collision detected." like bvh.cuh:466 (default 0) */
-    uint32_t reserved;
+    uint32_t refit_only;        /* 1: keep Morton order and topology of the previous build and only recompute leaf boxes/cones and
+                                 * the bottom-up box + cone merge (after snch_scene_update_vertices; the scene must be built).  The
+                                 * reference has no counterpart (it rebuilds); fcpw exposes refit() (ext/fcpw/include/fcpw/fcpw.h:97-106).
+                                 * With unchanged vertices the result is bit-identical to a full build. */
 } snch_build_options;
 
 /* Morton -> radix sort -> Karras hierarchy -> fused AABB + normal-cone refit -> traversal records; asynchronous on `stream`
  * except for the final stats read-back.  May be called again after snch_scene_update_vertices(). */
 int snch_scene_build(snch_scene *s, const snch_build_options *opts, snch_stream stream);
+
+/* New vertex positions for the same topology (n_verts x 3 floats, HOST or DEVICE pointer); takes effect at the next
+ * snch_scene_build().  No reference counterpart: lbvh::scene<3> must be re-created (scene.cuh:1128-1133). */
+int snch_scene_update_vertices(snch_scene *s, const float *xyz, snch_stream stream);
 
 typedef struct snch_build_stats
 {
@@ -139,6 +146,35 @@ int snch_intersect_batch(const snch_scene *s, const float *origins_xyz, const fl
 int snch_sample_in_sphere_batch(const snch_scene *s, const float *spheres_xyzr, const float *rnd_uvw, uint64_t n, int32_t *out_index,
                                 float *out_pdf, float *out_point_xyz, snch_stream stream);
 
+/* One wavefront walk-on-stars step per walker — the call sequence of an Elaina-style WoSt stage (README.md:5,9), as one
+ * launch sequence that shares the Morton ordering of the walkers and keeps the star radius on the device:
+ *   (closest_index, closest_distance) = query_device(bvh, nearest(p), distance_calculator())                 query.cuh:238-318
+ *   silhouette_distance = query_device(bvh, nearest_silhouette(p, flip), ...) restricted to r_max = closest_distance   query.cuh:325-423
+ *   star_radius = min(closest_distance, silhouette_distance)
+ *   hits/found  = query_device(bvh, ray_intersect(ray(p, dir), star_radius), intersect_test())              query.cuh:79-169
+ *   sample_*    = sample_object_in_sphere(bvh, sphere_intersect(sphere(p, star_radius)), ...) + sample_on_object   sample.cuh:7-92
+ * Every output equals what the four *_batch calls return for the same inputs.  Required: points_xyz; every other pointer may be
+ * NULL (dirs NULL skips the ray stage, rnd NULL the sampling stage; NULL outputs are not written).  All HOST or all DEVICE pointers. */
+typedef struct snch_wost_io
+{
+    uint32_t struct_size; /* = sizeof(snch_wost_io) */
+    uint32_t reserved;
+    const float *points_xyz;  /* n x 3 */
+    const uint8_t *flip;      /* n, or NULL = false */
+    const float *dirs_xyz;    /* n x 3 */
+    const float *rnd_uvw;     /* n x 3 */
+    uint32_t *closest_index;
+    float *closest_distance;
+    float *silhouette_distance;
+    float *star_radius;
+    snch_hit *hits;
+    uint8_t *found;
+    int32_t *sample_index;
+    float *sample_pdf;
+    float *sample_point_xyz;
+} snch_wost_io;
+int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n, snch_stream stream);
+
 /* Scheduling knobs of the batched kernels; results never depend on them (tests/test_gpu_queries.py sweeps them).
  *   "query.sort_min_n"  batches at least this large are visited in Morton order of the query points (default 16384; 0 = never)
  *   "query.sort_bits"   key bits of that ordering (8..30, default 24)
@@ -152,6 +188,9 @@ int snch_sample_in_sphere_batch(const snch_scene *s, const float *spheres_xyzr, 
  *   "query.time_kernels" bracket every traversal kernel with CUDA events on the launching stream (default 0; see snch_scene_counter) */
 int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
 
+/* Scene preparation:
+ *   "adjacency.device"  1 = snch_scene_compute_silhouettes runs on the GPU (half-edge sort, adjacency.cu), 0 = host passes
+ *                       (same arrays bit for bit), -1 (default) = GPU when a CUDA device is present */
 /* Launch accounting since creation / the last reset (what bench.py reports as gpu_launches and roofline.achieved):
  *   "query.launches"            kernels launched by the *_batch calls (ordering + traversal)
  *   "query.traversal_launches"  traversal kernels among them
@@ -179,6 +218,12 @@ int snch_lbvh_build(int dim, uint32_t n, const void *leaf_aabbs, const void *lea
 int snch_scene_arena(const snch_scene *s, void **device_ptr, uint64_t *bytes);
 /* arena_copy: DEVICE pointer on `device` holding a byte-exact copy of another scene's arena (copied; caller keeps ownership) */
 int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, snch_stream stream, snch_scene **out);
+
+/* Serialisation: the arena written to / read from a file verbatim (header with magic, version and size
+ * first).  A loaded scene answers queries and exports like the one that was saved; it cannot be rebuilt (like an adopted one).
+ * No reference counterpart: its scene embeds raw device pointers (scene.cuh:831-839). */
+int snch_scene_save(const snch_scene *s, const char *path);
+int snch_scene_load(const char *path, int device, snch_stream stream, snch_scene **out);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,8 @@ ABI_SYMBOLS = [
     "snch_last_error", "snch_abi_version", "snch_scene3_create", "snch_scene_destroy", "snch_scene_compute_silhouettes",
     "snch_scene_build", "snch_scene_stats", "snch_scene_device_repr", "snch_scene_export", "snch_closest_point_batch",
     "snch_closest_silhouette_batch", "snch_intersect_batch", "snch_sample_in_sphere_batch", "snch_scene_arena",
-    "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter", "snch_lbvh_build",
+    "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter", "snch_lbvh_build", "snch_scene_update_vertices",
+    "snch_wost_step_batch", "snch_scene_save", "snch_scene_load",
 ]
 
 
@@ -43,7 +44,14 @@ class ExportKind(IntEnum):
 
 class BuildOptions(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("keep_reference_layout", C.c_uint32), ("print_collision", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("refit_only", C.c_uint32)]
+
+
+class WostIO(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("points_xyz", C.c_void_p), ("flip", C.c_void_p),
+                ("dirs_xyz", C.c_void_p), ("rnd_uvw", C.c_void_p), ("closest_index", C.c_void_p), ("closest_distance", C.c_void_p),
+                ("silhouette_distance", C.c_void_p), ("star_radius", C.c_void_p), ("hits", C.c_void_p), ("found", C.c_void_p),
+                ("sample_index", C.c_void_p), ("sample_pdf", C.c_void_p), ("sample_point_xyz", C.c_void_p)]
 
 
 class BuildStats(C.Structure):
@@ -98,6 +106,10 @@ def lib():
     L.snch_scene_adopt_arena.argtypes = [vp, u64, C.c_int, vp, C.POINTER(vp)]
     L.snch_scene_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.snch_scene_counter.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+    L.snch_scene_update_vertices.argtypes = [vp, vp, vp]
+    L.snch_wost_step_batch.argtypes = [vp, C.POINTER(WostIO), u64, vp]
+    L.snch_scene_save.argtypes = [vp, C.c_char_p]
+    L.snch_scene_load.argtypes = [C.c_char_p, C.c_int, vp, C.POINTER(vp)]
     L.snch_lbvh_build.argtypes = [C.c_int, u32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]
     for name in ABI_SYMBOLS:
         if name not in ("snch_last_error",):
@@ -186,10 +198,33 @@ class Scene3:
         _check(self._L.snch_scene_compute_silhouettes(self._h))
         return self
 
-    def build_bvh(self, stream=None, print_collision=False):
-        opts = BuildOptions(C.sizeof(BuildOptions), 1, int(print_collision), 0)
+    def build_bvh(self, stream=None, print_collision=False, refit_only=False):
+        opts = BuildOptions(C.sizeof(BuildOptions), 1, int(print_collision), int(refit_only))
         _check(self._L.snch_scene_build(self._h, C.byref(opts), _stream_ptr(stream)))
         return self
+
+    def update_vertices(self, vertices, stream=None):
+        """New positions for the same topology (numpy array or torch CUDA tensor); takes effect at the next build_bvh()
+        (full rebuild, or ``refit_only=True`` to keep the Morton order and hierarchy)."""
+        a = _Arg(vertices, np.float32, (3,))
+        if a.n != self.stats()["num_vertices"]:
+            raise ValueError("update_vertices: vertex count differs from the scene's")
+        _check(self._L.snch_scene_update_vertices(self._h, a.ptr, _stream_ptr(stream)))
+        if not a.torch:
+            self.vertices_h = a.obj
+        return self
+
+    def save(self, path: str):
+        """Write the built scene (its pointer-free arena) to a file."""
+        _check(self._L.snch_scene_save(self._h, os.fsencode(path)))
+        return self
+
+    @classmethod
+    def load(cls, path: str, device: int = 0, stream=None):
+        """A scene saved with save(): answers queries and exports like the original; cannot be rebuilt."""
+        h = C.c_void_p()
+        _check(lib().snch_scene_load(os.fsencode(path), int(device), _stream_ptr(stream), C.byref(h)))
+        return cls._from_handle(h, device)
 
     def set_option(self, name: str, value: int):
         """Scheduling knobs of the batched kernels (include/snch_b200.h: snch_scene_set_option); results never depend on them."""
@@ -278,6 +313,37 @@ class Scene3:
         pt, tp = _out(s, (s.n, 3), np.float32)
         _check(self._L.snch_sample_in_sphere_batch(self._h, s.ptr, r.ptr, s.n, ip, pp, tp, _stream_ptr(stream)))
         return idx, pdf, pt
+
+    def wost_step(self, points, directions=None, rnd=None, flip=None, stream=None) -> dict:
+        """One wavefront walk-on-stars step per walker (include/snch_b200.h: snch_wost_step_batch): closest point, silhouette
+        within the closest distance, star radius = min of both, ray along `directions` up to the star radius, triangle sampled
+        in the star sphere.  Returns a dict of arrays (numpy in -> numpy out, torch CUDA in -> torch out)."""
+        q = _Arg(points, np.float32, (3,))
+        d = _Arg(directions, np.float32, (3,), allow_none=True)
+        r = _Arg(rnd, np.float32, (3,), allow_none=True)
+        f = _Arg(flip, np.uint8, None, allow_none=True)
+        out, io = {}, WostIO()
+        io.struct_size = C.sizeof(WostIO)
+        io.points_xyz, io.flip, io.dirs_xyz, io.rnd_uvw = q.ptr, f.ptr, d.ptr, r.ptr
+        out["closest_index"], io.closest_index = _out(q, (q.n,), np.uint32)
+        out["closest_distance"], io.closest_distance = _out(q, (q.n,), np.float32)
+        out["silhouette_distance"], io.silhouette_distance = _out(q, (q.n,), np.float32)
+        out["star_radius"], io.star_radius = _out(q, (q.n,), np.float32)
+        if d.ptr:
+            out["found"], io.found = _out(q, (q.n,), np.uint8)
+            if q.torch:
+                import torch
+                out["hits"] = torch.empty((q.n, 4), dtype=torch.float32, device=q.obj.device)
+                io.hits = out["hits"].data_ptr()
+            else:
+                out["hits"] = np.zeros(q.n, HIT_DTYPE)
+                io.hits = out["hits"].ctypes.data
+        if r.ptr:
+            out["sample_index"], io.sample_index = _out(q, (q.n,), np.int32)
+            out["sample_pdf"], io.sample_pdf = _out(q, (q.n,), np.float32)
+            out["sample_point"], io.sample_point_xyz = _out(q, (q.n, 3), np.float32)
+        _check(self._L.snch_wost_step_batch(self._h, C.byref(io), q.n, _stream_ptr(stream)))
+        return out
 
     # -- replication (multi-GPU) ---------------------------------------------------------------------------------
     def arena(self):

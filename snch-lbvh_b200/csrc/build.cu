@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
     cone.axis = V3{0.f, 0.f, 0.f};
     cone.half_angle = kPi;
     cone.radius = 0.f;
-    const uint32_t eoff = c.edge_off[k];
+    const uint32_t eoff = c.edge_off_packed ? c.edge_off[k] >> 2 : c.edge_off[k];
     uint32_t cnt = 0;
     bool all_two = true;
     V3 fn0[3], fn1[3];
@@ -507,6 +507,34 @@ __global__ void k_patch_pointers(RefEdge *edges, uint32_t n_edges, RefTriangle *
     }
 }
 
+// reference-layout edge / triangle structs from the device adjacency arrays (adjacency.cu)
+__global__ void k_assemble_topology(const int32_t *__restrict__ tri, const int32_t *__restrict__ tri_edges, const int32_t *__restrict__ owned,
+                                    const int4 *__restrict__ e4, uint32_t n_tris, uint32_t n_edges, RefEdge *edges, RefTriangle *objects,
+                                    int32_t *tri_edges_out, const float3 *verts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_edges)
+    {
+        RefEdge r;
+        r.indices = e4[i];
+        r.vertices = verts;
+        r.pad_ = 0;
+        edges[i] = r;
+    }
+    if (i < n_tris)
+    {
+        RefTriangle t;
+        t.v = make_int3(tri[3 * i], tri[3 * i + 1], tri[3 * i + 2]);
+        t.owned = make_int3(owned[3 * i], owned[3 * i + 1], owned[3 * i + 2]);
+        t.vertices = verts;
+        t.silhouettes = edges;
+        objects[i] = t;
+        tri_edges_out[3 * i] = tri_edges[3 * i];
+        tri_edges_out[3 * i + 1] = tri_edges[3 * i + 1];
+        tri_edges_out[3 * i + 2] = tri_edges[3 * i + 2];
+    }
+}
+
 int patch_pointers(snch_scene *s, cudaStream_t stream)
 {
     const ArenaHeader &h = s->hdr;
@@ -528,10 +556,14 @@ int build_device(snch_scene *s, cudaStream_t stream)
     const uint32_t nV = s->n_verts, nT = s->n_tris, nE = s->n_edges;
     ArenaHeader h;
     layout_arena(h, nV, nT, nE);
+    const uint32_t prev_collision = s->hdr.collision;
+    // refit-only: Morton order, hierarchy and edge slots of the previous build stay; only geometry-dependent products change
+    const bool refit = s->opt_refit_only && s->built && s->arena && s->arena_bytes == h.total_bytes && s->arena_has_topology;
     if (!s->arena || s->arena_bytes != h.total_bytes)
     {
         if (s->arena) cudaFree(s->arena);
         s->arena = nullptr;
+        s->arena_has_topology = false;
         if (cudaMalloc(&s->arena, h.total_bytes) != cudaSuccess)
         {
             cudaGetLastError();
@@ -544,30 +576,50 @@ int build_device(snch_scene *s, cudaStream_t stream)
     resolve_view(s);
     unsigned char *b = s->arena;
 
-    // ---- uploads (host arrays -> arena); the reference does these in its constructors (scene.cuh:1131, bvh.cuh:330)
+    // ---- uploads (host arrays -> arena); the reference does these in its constructors (scene.cuh:1131, bvh.cuh:330).
+    // Topology (edges, triangles, per-triangle edge ids) is written once per compute_silhouettes(); later builds of the
+    // same scene (snch_scene_update_vertices) only refresh the vertices.
     if (nV) SNCH_CUDA(cudaMemcpyAsync(b + h.off_vertices, s->h_xyz.data(), (size_t)nV * 12, cudaMemcpyHostToDevice, stream));
-    std::vector<RefEdge> he(nE);
-    for (uint32_t e = 0; e < nE; ++e)
+    std::vector<RefEdge> he;
+    std::vector<RefTriangle> ho;
+    if (!s->arena_has_topology && s->adjacency_on_device && nT)
     {
-        he[e].indices = make_int4(s->h_edges4[4 * e], s->h_edges4[4 * e + 1], s->h_edges4[4 * e + 2], s->h_edges4[4 * e + 3]);
-        he[e].vertices = (const float3 *)(b + h.off_vertices);
-        he[e].pad_ = 0;
+        const uint32_t m = nE > nT ? nE : nT;
+        k_assemble_topology<<<(m + 255) / 256, 256, 0, stream>>>(s->adj_tri, s->adj_tri_edges, s->adj_tri_owned, s->adj_edges4, nT, nE,
+                                                                  (RefEdge *)(b + h.off_edges), (RefTriangle *)(b + h.off_objects),
+                                                                  (int32_t *)(b + h.off_tri_edges), (const float3 *)(b + h.off_vertices));
+        SNCH_CUDA(cudaGetLastError());
     }
-    std::vector<RefTriangle> ho(nT);
-    for (uint32_t i = 0; i < nT; ++i)
+    else if (!s->arena_has_topology)
     {
-        ho[i].v = make_int3(s->h_tri[3 * i], s->h_tri[3 * i + 1], s->h_tri[3 * i + 2]);
-        ho[i].owned = make_int3(s->h_tri_owned[3 * i], s->h_tri_owned[3 * i + 1], s->h_tri_owned[3 * i + 2]);
-        ho[i].vertices = (const float3 *)(b + h.off_vertices);
-        ho[i].silhouettes = (const RefEdge *)(b + h.off_edges);
-    }
-    if (nE) SNCH_CUDA(cudaMemcpyAsync(b + h.off_edges, he.data(), (size_t)nE * sizeof(RefEdge), cudaMemcpyHostToDevice, stream));
-    if (nT)
-    {
-        SNCH_CUDA(cudaMemcpyAsync(b + h.off_objects, ho.data(), (size_t)nT * sizeof(RefTriangle), cudaMemcpyHostToDevice, stream));
-        SNCH_CUDA(cudaMemcpyAsync(b + h.off_tri_edges, s->h_tri_edges.data(), (size_t)nT * 12, cudaMemcpyHostToDevice, stream));
+        he.resize(nE);
+        for (uint32_t e = 0; e < nE; ++e)
+        {
+            he[e].indices = make_int4(s->h_edges4[4 * e], s->h_edges4[4 * e + 1], s->h_edges4[4 * e + 2], s->h_edges4[4 * e + 3]);
+            he[e].vertices = (const float3 *)(b + h.off_vertices);
+            he[e].pad_ = 0;
+        }
+        ho.resize(nT);
+        for (uint32_t i = 0; i < nT; ++i)
+        {
+            ho[i].v = make_int3(s->h_tri[3 * i], s->h_tri[3 * i + 1], s->h_tri[3 * i + 2]);
+            ho[i].owned = make_int3(s->h_tri_owned[3 * i], s->h_tri_owned[3 * i + 1], s->h_tri_owned[3 * i + 2]);
+            ho[i].vertices = (const float3 *)(b + h.off_vertices);
+            ho[i].silhouettes = (const RefEdge *)(b + h.off_edges);
+        }
+        if (nE) SNCH_CUDA(cudaMemcpyAsync(b + h.off_edges, he.data(), (size_t)nE * sizeof(RefEdge), cudaMemcpyHostToDevice, stream));
+        if (nT)
+        {
+            SNCH_CUDA(cudaMemcpyAsync(b + h.off_objects, ho.data(), (size_t)nT * sizeof(RefTriangle), cudaMemcpyHostToDevice, stream));
+            SNCH_CUDA(cudaMemcpyAsync(b + h.off_tri_edges, s->h_tri_edges.data(), (size_t)nT * 12, cudaMemcpyHostToDevice, stream));
+        }
     }
     SNCH_CUDA(cudaStreamSynchronize(stream)); // staging vectors go out of scope below; also isolates build_ms
+    s->arena_has_topology = true;
+    if (s->adjacency_on_device && s->adj)
+    { // the arena now holds the only copy the library needs; keep the host vectors for exports if they were fetched
+        free_adjacency(s);
+    }
     if (nT == 0)
     {
         SNCH_CUDA(cudaMemcpyAsync(b, &s->hdr, sizeof(ArenaHeader), cudaMemcpyHostToDevice, stream));
@@ -607,6 +659,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     BuildCtx c;
     c.n = nT;
     c.n_edges = nE;
+    c.edge_off_packed = refit ? 1u : 0u;
     c.verts = (const float3 *)(b + h.off_vertices);
     c.edges = (const RefEdge *)(b + h.off_edges);
     c.objects = (const RefTriangle *)(b + h.off_objects);
@@ -636,14 +689,18 @@ int build_device(snch_scene *s, cudaStream_t stream)
     SNCH_CUDA(cudaMemsetAsync(c.counters, 0, 64, stream));
     k_init_box<<<1, 32, 0, stream>>>(c.scene_box);
     k_scene_box<<<g256 < 1184 ? g256 : 1184, 256, 0, stream>>>(c);
-    k_morton<<<g256, 256, 0, stream>>>(c);
-    int launches = 3; // k_init_box, k_scene_box, k_morton
-    launches += radix_sort_pairs(c.morton, c.sorted_idx, (uint32_t *)(sc + o_ktmp), (uint32_t *)(sc + o_vtmp), nT, 30,
-                                 (uint32_t *)(sc + o_sort), stream);
-    if (nT > 1) k_hierarchy<<<(nT - 1 + 255) / 256, 256, 0, stream>>>(c);
-    k_owned_count<<<g256, 256, 0, stream>>>(c);
-    launches += (nT > 1 ? 1 : 0) + 1 + exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream) + 1;
+    int launches = 2; // k_init_box, k_scene_box
+    if (!refit)
+    {
+        k_morton<<<g256, 256, 0, stream>>>(c);
+        launches += 1 + radix_sort_pairs(c.morton, c.sorted_idx, (uint32_t *)(sc + o_ktmp), (uint32_t *)(sc + o_vtmp), nT, 30,
+                                         (uint32_t *)(sc + o_sort), stream);
+        if (nT > 1) k_hierarchy<<<(nT - 1 + 255) / 256, 256, 0, stream>>>(c);
+        k_owned_count<<<g256, 256, 0, stream>>>(c);
+        launches += (nT > 1 ? 1 : 0) + 1 + exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream);
+    }
     k_refit<<<(nT + 127) / 128, 128, 0, stream>>>(c);
+    launches += 1;
     s->build_launches = (uint64_t)launches;
     SNCH_CUDA(cudaGetLastError());
     SNCH_CUDA(cudaEventRecord(ev1, stream));
@@ -657,7 +714,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     SNCH_CUDA(cudaEventElapsedTime(&s->build_ms, ev0, ev1));
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    s->hdr.collision = counters[0];
+    s->hdr.collision = refit ? prev_collision : counters[0];
     s->hdr.q1_nodes = counters[1];
     for (int a = 0; a < 3; ++a)
     {

@@ -91,7 +91,7 @@ struct Stager
         void *dev;
         uint64_t bytes;
     };
-    Out outs[4];
+    Out outs[12];
     int n_outs = 0;
     Stager(unsigned char *base_, cudaStream_t st_) : st(st_), base(base_) {}
     static uint64_t pad(uint64_t b) { return align_up(b, 256); }
@@ -214,6 +214,7 @@ int snch_scene_destroy(snch_scene *s)
     if (!s) return SNCH_OK;
     cudaSetDevice(s->device);
     if (s->arena) cudaFree(s->arena);
+    if (s->adj) cudaFree(s->adj);
     if (s->scratch) cudaFree(s->scratch);
     if (s->pool) cudaMemPoolDestroy(s->pool);
     if (s->counters.ev0) cudaEventDestroy(s->counters.ev0);
@@ -229,6 +230,19 @@ int snch_scene_compute_silhouettes(snch_scene *s)
         set_error("snch_scene_compute_silhouettes: invalid scene");
         return SNCH_ERR_INVALID;
     }
+    // The reference does this on the host (scene.cuh:1135-1229).  Here it runs on the GPU (adjacency.cu) whenever a CUDA
+    // device is present; "adjacency.device" = 0 selects the host passes, which produce the same arrays bit for bit.
+    s->arena_has_topology = false;
+    bool on_device = s->adjacency_mode == 1;
+    if (s->adjacency_mode < 0)
+    {
+        int count = 0;
+        on_device = cudaGetDeviceCount(&count) == cudaSuccess && s->device < count;
+        if (!on_device) cudaGetLastError();
+    }
+    if (on_device) return compute_adjacency_device(s);
+    free_adjacency(s);
+    s->adjacency_on_device = false;
     compute_adjacency_host(s);
     return SNCH_OK;
 }
@@ -248,12 +262,21 @@ int snch_scene_build(snch_scene *s, const snch_build_options *opts, snch_stream 
             return SNCH_ERR_INVALID;
         }
         s->opt_print_collision = opts->print_collision;
+        s->opt_refit_only = opts->refit_only;
+    }
+    else s->opt_refit_only = 0;
+    if (s->opt_refit_only && !s->built)
+    {
+        set_error("BVH is not built yet.");
+        return SNCH_ERR_NOT_BUILT;
     }
     // the reference's build_bvh() silently uses whatever compute_silhouettes() left behind; an un-prepared scene has
     // no edges at all, which makes every leaf cone invalid.  Do the same (no implicit call).
     if (!s->silhouettes_done)
     {
         s->n_edges = 0;
+        s->adjacency_on_device = false;
+        s->arena_has_topology = false;
         s->h_edges4.clear();
         s->h_tri_edges.assign((size_t)3 * s->n_tris, -1);
         s->h_tri_owned.assign((size_t)3 * s->n_tris, -1);
@@ -332,9 +355,14 @@ int snch_scene_export(const snch_scene *s, int kind, void *host_dst, size_t byte
         set_error("snch_scene_export: null destination");
         return SNCH_ERR_INVALID;
     }
-    if (s && !s->adopted && s->silhouettes_done &&
+    if (s && !s->adopted && s->silhouettes_done && s->adjacency_on_device && s->adj)
+    {
+        const int fs = fetch_adjacency_host(const_cast<snch_scene *>(s));
+        if (fs != SNCH_OK) return fs;
+    }
+    if (s && !s->adopted && s->silhouettes_done && (!s->adjacency_on_device || !s->h_tri_edges.empty() || s->n_tris == 0) &&
         (kind == SNCH_EXPORT_EDGES || kind == SNCH_EXPORT_TRI_EDGES || kind == SNCH_EXPORT_TRI_OWNED))
-    { // host-side adjacency products are available as soon as compute_silhouettes() ran
+    { // adjacency products are available as soon as compute_silhouettes() ran
         const std::vector<int32_t> &v = kind == SNCH_EXPORT_EDGES ? s->h_edges4 : (kind == SNCH_EXPORT_TRI_EDGES ? s->h_tri_edges : s->h_tri_owned);
         if (bytes != v.size() * 4)
         {
@@ -648,6 +676,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
+    else if (k == "adjacency.device") s->adjacency_mode = (int)value;
     else
     {
         set_error("snch_scene_set_option: unknown option '" + k + "'");
@@ -671,22 +700,20 @@ int snch_scene_arena(const snch_scene *s, void **device_ptr, uint64_t *bytes)
     return SNCH_OK;
 }
 
-int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, snch_stream stream, snch_scene **out)
+static int adopt_from(const void *src, bool src_is_host, uint64_t bytes, int device, cudaStream_t cst, snch_scene **out, const char *who)
 {
-    if (!arena_copy || !out || bytes < sizeof(ArenaHeader))
-    {
-        set_error("snch_scene_adopt_arena: bad argument");
-        return SNCH_ERR_INVALID;
-    }
     *out = nullptr;
     SNCH_CUDA(cudaSetDevice(device));
-    cudaStream_t cst = (cudaStream_t)stream;
     ArenaHeader h;
-    SNCH_CUDA(cudaMemcpyAsync(&h, arena_copy, sizeof h, cudaMemcpyDeviceToHost, cst));
-    SNCH_CUDA(cudaStreamSynchronize(cst));
+    if (src_is_host) std::memcpy(&h, src, sizeof h);
+    else
+    {
+        SNCH_CUDA(cudaMemcpyAsync(&h, src, sizeof h, cudaMemcpyDeviceToHost, cst));
+        SNCH_CUDA(cudaStreamSynchronize(cst));
+    }
     if (h.magic != kArenaMagic || h.version != kArenaVersion || h.total_bytes != bytes)
     {
-        set_error("snch_scene_adopt_arena: not a scene arena (magic/version/size mismatch)");
+        set_error(std::string(who) + ": not a scene arena (magic/version/size mismatch)");
         return SNCH_ERR_INVALID;
     }
     snch_scene *s = new (std::nothrow) snch_scene();
@@ -709,7 +736,7 @@ int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, s
     }
     s->arena_bytes = bytes;
     s->hdr = h;
-    cudaError_t e = cudaMemcpyAsync(s->arena, arena_copy, bytes, cudaMemcpyDeviceToDevice, cst);
+    cudaError_t e = cudaMemcpyAsync(s->arena, src, bytes, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cst);
     if (e != cudaSuccess)
     {
         snch_scene_destroy(s);
@@ -729,6 +756,206 @@ int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, s
     }
     s->built = true;
     *out = s;
+    return SNCH_OK;
+}
+
+int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, snch_stream stream, snch_scene **out)
+{
+    if (!arena_copy || !out || bytes < sizeof(ArenaHeader))
+    {
+        set_error("snch_scene_adopt_arena: bad argument");
+        return SNCH_ERR_INVALID;
+    }
+    return adopt_from(arena_copy, false, bytes, device, (cudaStream_t)stream, out, "snch_scene_adopt_arena");
+}
+
+// ---- serialisation ----------------------------------------------------------------------------------------------------
+int snch_scene_save(const snch_scene *s, const char *path)
+{
+    const int st = check_built(s);
+    if (st != SNCH_OK) return st;
+    if (!path)
+    {
+        set_error("snch_scene_save: null path");
+        return SNCH_ERR_INVALID;
+    }
+    SNCH_CUDA(cudaSetDevice(s->device));
+    std::FILE *f = std::fopen(path, "wb");
+    if (!f)
+    {
+        set_error(std::string("snch_scene_save: cannot open '") + path + "' for writing");
+        return SNCH_ERR_INVALID;
+    }
+    // chunked D2H through one pinned bounce buffer: the arena can be GBs, the host copy need not be
+    const uint64_t chunk = 64ull << 20;
+    void *bounce = nullptr;
+    if (cudaMallocHost(&bounce, chunk) != cudaSuccess)
+    {
+        cudaGetLastError();
+        std::fclose(f);
+        set_error("snch_scene_save: out of pinned host memory");
+        return SNCH_ERR_OOM;
+    }
+    int rc = SNCH_OK;
+    for (uint64_t off = 0; off < s->arena_bytes && rc == SNCH_OK; off += chunk)
+    {
+        const uint64_t m = s->arena_bytes - off < chunk ? s->arena_bytes - off : chunk;
+        const cudaError_t e = cudaMemcpy(bounce, s->arena + off, m, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "arena D2H");
+        else if (std::fwrite(bounce, 1, m, f) != m)
+        {
+            set_error(std::string("snch_scene_save: short write to '") + path + "'");
+            rc = SNCH_ERR_INVALID;
+        }
+    }
+    cudaFreeHost(bounce);
+    if (std::fclose(f) != 0 && rc == SNCH_OK)
+    {
+        set_error(std::string("snch_scene_save: close of '") + path + "' failed");
+        rc = SNCH_ERR_INVALID;
+    }
+    return rc;
+}
+
+int snch_scene_load(const char *path, int device, snch_stream stream, snch_scene **out)
+{
+    if (!path || !out)
+    {
+        set_error("snch_scene_load: null argument");
+        return SNCH_ERR_INVALID;
+    }
+    *out = nullptr;
+    std::FILE *f = std::fopen(path, "rb");
+    if (!f)
+    {
+        set_error(std::string("snch_scene_load: cannot open '") + path + "'");
+        return SNCH_ERR_INVALID;
+    }
+    std::vector<unsigned char> buf;
+    ArenaHeader h;
+    int rc = SNCH_OK;
+    if (std::fread(&h, 1, sizeof h, f) != sizeof h || h.magic != kArenaMagic || h.version != kArenaVersion || h.total_bytes < sizeof h ||
+        h.total_bytes > (1ull << 40))
+    {
+        set_error(std::string("snch_scene_load: '") + path + "' is not a scene arena (magic/version mismatch)");
+        rc = SNCH_ERR_INVALID;
+    }
+    else
+    {
+        buf.resize(h.total_bytes);
+        std::memcpy(buf.data(), &h, sizeof h);
+        const size_t rest = (size_t)h.total_bytes - sizeof h;
+        if (std::fread(buf.data() + sizeof h, 1, rest, f) != rest || std::fgetc(f) != EOF)
+        {
+            set_error(std::string("snch_scene_load: '") + path + "' is truncated or has trailing bytes");
+            rc = SNCH_ERR_INVALID;
+        }
+    }
+    std::fclose(f);
+    if (rc != SNCH_OK) return rc;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+    {
+        cudaGetLastError();
+        set_error("snch_scene_load: no such CUDA device (this library has no CPU fallback)");
+        return SNCH_ERR_CUDA;
+    }
+    return adopt_from(buf.data(), true, buf.size(), device, (cudaStream_t)stream, out, "snch_scene_load");
+}
+
+int snch_scene_update_vertices(snch_scene *s, const float *xyz, snch_stream stream)
+{
+    if (!s || s->adopted || (!xyz && s->n_verts))
+    {
+        set_error("snch_scene_update_vertices: invalid scene or null vertices");
+        return SNCH_ERR_INVALID;
+    }
+    const size_t bytes = (size_t)s->n_verts * 12;
+    if (bytes == 0) return SNCH_OK;
+    if (ptr_kind(xyz) == PK_DEVICE)
+    {
+        SNCH_CUDA(cudaSetDevice(s->device));
+        SNCH_CUDA(cudaMemcpyAsync(s->h_xyz.data(), xyz, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        SNCH_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    else std::memcpy(s->h_xyz.data(), xyz, bytes);
+    return SNCH_OK;
+}
+
+int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t n, snch_stream stream)
+{
+    int st = check_built(cs);
+    if (st != SNCH_OK) return st;
+    if (!io || io->struct_size != sizeof(snch_wost_io))
+    {
+        set_error("snch_wost_step_batch: null io or snch_wost_io.struct_size mismatch");
+        return SNCH_ERR_INVALID;
+    }
+    if (n == 0) return SNCH_OK;
+    if (!io->points_xyz)
+    {
+        set_error("snch_wost_step_batch: points_xyz is required");
+        return SNCH_ERR_INVALID;
+    }
+    snch_scene *s = const_cast<snch_scene *>(cs);
+    SNCH_CUDA(cudaSetDevice(s->device));
+    const PtrKind k = common_kind({io->points_xyz, io->flip, io->dirs_xyz, io->rnd_uvw, io->closest_index, io->closest_distance,
+                                   io->silhouette_distance, io->star_radius, io->hits, io->found, io->sample_index, io->sample_pdf,
+                                   io->sample_point_xyz});
+    if (k == PK_NULL)
+    {
+        set_error("snch_wost_step_batch: mixed host/device pointers");
+        return SNCH_ERR_POINTER_KIND;
+    }
+    cudaStream_t cst = (cudaStream_t)stream;
+    for (uint64_t off = 0; off < n; off += kMaxLaunch)
+    {
+        const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
+        const uint64_t qs = wost_scratch_bytes(m, s->tuning);
+        const uint64_t stage = k == PK_DEVICE ? 0 : 4 * Stager::pad(m * 12) + 2 * Stager::pad(m) + 6 * Stager::pad(m * 4) + Stager::pad(m * 16);
+        PoolBuffer buf(s, cst, qs + stage);
+        if (buf.status != SNCH_OK) return buf.status;
+        WostBuffers w;
+        auto at = [&](auto *p, uint64_t stride) { return p ? p + stride * off : p; };
+        if (k == PK_DEVICE)
+        {
+            w.points = at(io->points_xyz, 3);
+            w.flip = at(io->flip, 1);
+            w.dirs = at(io->dirs_xyz, 3);
+            w.rnd = at(io->rnd_uvw, 3);
+            w.closest_index = at(io->closest_index, 1);
+            w.closest_distance = at(io->closest_distance, 1);
+            w.silhouette_distance = at(io->silhouette_distance, 1);
+            w.star_radius = at(io->star_radius, 1);
+            w.hits = at(io->hits, 1);
+            w.found = at(io->found, 1);
+            w.sample_index = at(io->sample_index, 1);
+            w.sample_pdf = at(io->sample_pdf, 1);
+            w.sample_point = at(io->sample_point_xyz, 3);
+            st = launch_wost_step(s->view, s->tuning, w, m, buf.p, cst, &s->counters);
+            if (st != SNCH_OK) return st;
+            continue;
+        }
+        Stager sg(buf.p + qs, cst);
+        w.points = sg.in(at(io->points_xyz, 3), m * 12);
+        w.flip = sg.in(at(io->flip, 1), m);
+        w.dirs = sg.in(at(io->dirs_xyz, 3), m * 12);
+        w.rnd = sg.in(at(io->rnd_uvw, 3), m * 12);
+        w.closest_index = sg.out(at(io->closest_index, 1), m * 4);
+        w.closest_distance = sg.out(at(io->closest_distance, 1), m * 4);
+        w.silhouette_distance = sg.out(at(io->silhouette_distance, 1), m * 4);
+        w.star_radius = sg.out(at(io->star_radius, 1), m * 4);
+        w.hits = sg.out(at(io->hits, 1), m * sizeof(snch_hit));
+        w.found = sg.out(at(io->found, 1), m);
+        w.sample_index = sg.out(at(io->sample_index, 1), m * 4);
+        w.sample_pdf = sg.out(at(io->sample_pdf, 1), m * 4);
+        w.sample_point = sg.out(at(io->sample_point_xyz, 3), m * 12);
+        if (sg.status != SNCH_OK) return sg.status;
+        st = launch_wost_step(s->view, s->tuning, w, m, buf.p, cst, &s->counters);
+        if (st != SNCH_OK) return st;
+        st = sg.finish();
+        if (st != SNCH_OK) return st;
+    }
     return SNCH_OK;
 }
 

@@ -1122,4 +1122,85 @@ int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, co
     return SNCH_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One wavefront walk-on-stars step: per walker the four reference calls an Elaina-style stage makes,
+//   (i, d) = nearest(p);  s = nearest_silhouette(p, flip) within d;  R = min(d, s)   [star radius]
+//   hit    = ray_intersect(p, dir, t_max = R);  (tri, pdf, y) = sample_object_in_sphere(sphere(p, R), u)
+// as ONE call: the Morton ordering of the walkers is computed once and shared by all four traversals, and the star
+// radius never leaves the device.  Every output equals what the four *_batch calls return for the same inputs.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_star_radius(const float *__restrict__ pts, const float *__restrict__ d_closest, const float *__restrict__ d_sil, uint32_t n,
+                              float *__restrict__ radius, float *__restrict__ spheres)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float r = fminf(d_closest[i], d_sil[i]);
+    if (radius) radius[i] = r;
+    reinterpret_cast<float4 *>(spheres)[i] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], r);
+}
+
+uint64_t wost_scratch_bytes(uint64_t n, const QueryTuning &t) { return query_scratch_bytes(n, t) + 4 * align_up(n * 4, 256) + align_up(n * 16, 256); }
+
+int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers &io, uint64_t n, unsigned char *scratch, cudaStream_t st,
+                     QueryCounters *qc)
+{
+    if (n == 0) return SNCH_OK;
+    const uint64_t qs = query_scratch_bytes(n, t), a4 = align_up(n * 4, 256);
+    float *d_closest = io.closest_distance ? io.closest_distance : reinterpret_cast<float *>(scratch + qs);
+    float *d_sil = io.silhouette_distance ? io.silhouette_distance : reinterpret_cast<float *>(scratch + qs + a4);
+    float *radius = io.star_radius ? io.star_radius : reinterpret_cast<float *>(scratch + qs + 2 * a4);
+    uint32_t *c_index = io.closest_index ? io.closest_index : reinterpret_cast<uint32_t *>(scratch + qs + 3 * a4);
+    float *spheres = reinterpret_cast<float *>(scratch + qs + 4 * a4);
+    if (v.n_tris == 0)
+    {
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, c_index, d_closest, io.hits, io.found, io.sample_index, io.sample_pdf,
+                                                            io.sample_point);
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, d_sil, nullptr, nullptr, nullptr, nullptr, nullptr);
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, radius, nullptr, nullptr, nullptr, nullptr, nullptr);
+        SNCH_CUDA(cudaGetLastError());
+        return SNCH_OK;
+    }
+    const uint32_t m = (uint32_t)n;
+    unsigned long long *counter;
+    const uint32_t *perm;
+    const int rc = prepare_batch(t, true, io.points, 3, nullptr, m, scratch, st, &counter, &perm, qc);
+    if (rc != SNCH_OK) return rc;
+    {
+        TraversalTimer tt(qc, st);
+        if (perm && (t.packet & 1))
+            k_closest_packet<<<persistent_grid(k_closest_packet, t, m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index, d_closest,
+                                                                                               counter, t.seed);
+        else
+            k_closest<<<persistent_grid(k_closest, t, m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index, d_closest, counter,
+                                                                                   t.seed);
+    }
+    SNCH_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+    {
+        TraversalTimer tt(qc, st);
+        if (t.cone_filter)
+            k_silhouette<true><<<persistent_grid(k_silhouette<true>, t, m), kQueryThreads, 0, st>>>(v, io.points, io.flip, d_closest, perm, m, d_sil,
+                                                                                                   counter);
+        else
+            k_silhouette<false><<<persistent_grid(k_silhouette<false>, t, m), kQueryThreads, 0, st>>>(v, io.points, io.flip, d_closest, perm, m,
+                                                                                                     d_sil, counter);
+    }
+    k_star_radius<<<(m + 255) / 256, 256, 0, st>>>(io.points, d_closest, d_sil, m, radius, spheres);
+    if (qc) qc->launches += 1;
+    if (io.dirs && (io.hits || io.found))
+    {
+        SNCH_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+        TraversalTimer tt(qc, st);
+        const uint32_t *rperm = t.sort_rays ? perm : nullptr;
+        k_intersect<false><<<persistent_grid(k_intersect<false>, t, m), kQueryThreads, 0, st>>>(v, io.points, io.dirs, radius, rperm, m, io.hits,
+                                                                                               io.found, counter);
+    }
+    if (io.rnd && io.sample_index && io.sample_pdf)
+    {
+        TraversalTimer tt(qc, st);
+        k_sample<<<grid_for(n), kQueryThreads, 0, st>>>(v, spheres, io.rnd, perm, m, io.sample_index, io.sample_pdf, io.sample_point);
+    }
+    SNCH_CUDA(cudaGetLastError());
+    return SNCH_OK;
+}
+
 } // namespace snch

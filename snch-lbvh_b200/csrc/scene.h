@@ -65,7 +65,7 @@ struct snch_scene
     uint64_t build_launches = 0;
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
-    uint32_t opt_print_collision = 0;
+    uint32_t opt_print_collision = 0, opt_refit_only = 0;
 };
 
 namespace snch
@@ -100,4 +100,20 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
                      uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
 int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf,
                   float *pt, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
+// one wavefront walk-on-stars step over device buffers (snch_wost_step_batch); scratch has wost_scratch_bytes(n) bytes
+struct WostBuffers
+{
+    const float *points;
+    const uint8_t *flip;
+    const float *dirs, *rnd;
+    uint32_t *closest_index;
+    float *closest_distance, *silhouette_distance, *star_radius;
+    snch_hit *hits;
+    uint8_t *found;
+    int32_t *sample_index;
+    float *sample_pdf, *sample_point;
+};
+uint64_t wost_scratch_bytes(uint64_t n, const QueryTuning &t);
+int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers &io, uint64_t n, unsigned char *scratch, cudaStream_t st,
+                     QueryCounters *qc);
 } // namespace snch

@@ -1,0 +1,98 @@
+"""snch_wost_step_batch (the wavefront walk-on-stars stage) equals the four reference calls it fuses:
+closest point -> silhouette within the closest distance -> star radius -> ray up to the star radius + triangle sampled in
+the star sphere.  Bit-exact against the separate *_batch calls; the closest / silhouette legs also against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import OracleScene
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(meshes, v, n, seed):
+    lo, hi = meshes.mesh_bounds(v)
+    q = meshes.points_in_box(n, lo, hi, 1.2, seed=seed)
+    d = meshes.unit_directions(n, seed=seed + 1)
+    u = meshes.uniforms(n, 3, seed=seed + 2)
+    return q, d, u
+
+
+def _composition(sc, q, d, u, flip=None):
+    idx, dist = sc.closest_point(q)
+    sil = sc.closest_silhouette(q, flip=flip, r_max=dist)
+    radius = np.minimum(dist, sil)
+    found, hits = sc.intersect(q, d, t_max=radius)
+    sph = np.concatenate([q, radius[:, None]], axis=1).astype(np.float32)
+    sidx, pdf, pt = sc.sample_in_sphere(sph, u)
+    return dict(closest_index=idx, closest_distance=dist, silhouette_distance=sil, star_radius=radius, found=found, hits=hits,
+                sample_index=sidx, sample_pdf=pdf, sample_point=pt)
+
+
+def _same(a, b, key):
+    x, y = np.asarray(a[key]), np.asarray(b[key])
+    if x.dtype.names:
+        return all(np.array_equal(x[f].view(np.uint32), y[f].view(np.uint32)) for f in x.dtype.names)
+    return np.array_equal(x.view(np.uint8), y.view(np.uint8))
+
+
+@pytest.mark.parametrize("mesh,n", [("torus", 40_000), ("grid", 20_000), ("tet", 3_000), ("torus", 500)])
+def test_wost_step_equals_the_four_calls(pkg, meshes, mesh, n):
+    v, f = {"torus": lambda: meshes.bumpy_torus(90, 60), "grid": lambda: meshes.open_grid(30), "tet": meshes.tetrahedron}[mesh]()
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    q, d, u = _inputs(meshes, v, n, seed=21)
+    flip = (np.arange(n) % 3 == 0).astype(np.uint8)
+    want = _composition(sc, q, d, u, flip)
+    got = sc.wost_step(q, d, u, flip=flip)
+    for k in ("closest_distance", "silhouette_distance", "star_radius", "found", "hits", "sample_index", "sample_pdf", "sample_point"):
+        assert _same(got, want, k), k
+    # closest index: any member of the argmin set (ties) — the distance to the returned triangle is the answer
+    assert np.array_equal(got["closest_index"], want["closest_index"]) or np.mean(got["closest_index"] == want["closest_index"]) > 0.9
+    # oracle legs (small sample: the oracle is a serial CPU restatement)
+    m = min(n, 2000)
+    orc = OracleScene(v, f)
+    _, d_o = orc.closest(q[:m])
+    assert np.allclose(got["closest_distance"][:m], d_o, rtol=1e-5, atol=1e-7)
+    g = got["silhouette_distance"][:m]
+    for fl in (False, True):
+        sel = flip[:m].astype(bool) == fl
+        s_o = orc.silhouette(q[:m][sel], flip=fl, r_max=d_o[sel])
+        fin = np.isfinite(s_o)
+        assert np.mean(np.isfinite(g[sel]) == fin) > 0.995
+        both = fin & np.isfinite(g[sel])
+        assert np.allclose(g[sel][both], s_o[both], rtol=1e-5)
+
+def test_wost_step_device_pointers_and_optional_stages(pkg, meshes):
+    import torch
+    v, f = meshes.bumpy_torus(60, 40)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    q, d, u = _inputs(meshes, v, 30_000, seed=5)
+    host = sc.wost_step(q, d, u)
+    dev = sc.wost_step(torch.from_numpy(q).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(u).cuda())
+    torch.cuda.synchronize()
+    for k in ("closest_distance", "silhouette_distance", "star_radius", "sample_pdf", "sample_point"):
+        assert np.array_equal(dev[k].cpu().numpy().view(np.uint32), np.asarray(host[k]).view(np.uint32)), k
+    assert np.array_equal(dev["found"].cpu().numpy(), host["found"])
+    assert np.array_equal(dev["hits"].cpu().numpy()[:, 0].view(np.uint32), host["hits"]["t"].view(np.uint32))
+    assert np.array_equal(dev["sample_index"].cpu().numpy(), host["sample_index"])
+    # stages are optional: no directions -> no ray outputs, no uniforms -> no sample outputs; the rest is unchanged
+    only = sc.wost_step(q)
+    assert set(only) == {"closest_index", "closest_distance", "silhouette_distance", "star_radius"}
+    assert np.array_equal(only["star_radius"].view(np.uint32), host["star_radius"].view(np.uint32))
+    # fewer launches than the four separate calls (one ordering instead of two)
+    sc.counter("query.launches", reset=True)
+    sc.wost_step(q, d, u)
+    fused = sc.counter("query.launches", reset=True)
+    _composition(sc, q, d, u)
+    separate = sc.counter("query.launches", reset=True)
+    assert 0 < fused < separate
+
+
+def test_wost_step_empty_and_errors(pkg, meshes):
+    v, f = meshes.tetrahedron()
+    sc = pkg.Scene3(v, f).compute_silhouettes()
+    with pytest.raises(pkg.SnchError) as e:
+        sc.wost_step(np.zeros((4, 3), np.float32))
+    assert e.value.status == -2
+    sc.build_bvh()
+    out = sc.wost_step(np.zeros((0, 3), np.float32))
+    assert len(out["star_radius"]) == 0
