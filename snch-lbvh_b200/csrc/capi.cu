@@ -674,6 +674,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.packet") t.packet = (int)value;
     else if (k == "query.cone_filter") t.cone_filter = (int)value;
     else if (k == "query.seed") t.seed = (int)value;
+    else if (k == "query.sil_kernel") t.sil_kernel = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;

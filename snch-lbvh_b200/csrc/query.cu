@@ -422,14 +422,41 @@ __global__ void __launch_bounds__(kQueryThreads)
 // every branch decision the reference takes on exact float values — it defers to cone_overlap(), the reference's own
 // operation sequence.  Decisions are therefore the reference's; only their cost changes.
 constexpr float kConeBand = 2e-5f;
-template <bool kFilter> SNCH_DI bool cone_test(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
+SNCH_DI float rsqrt_approx(float x)
 {
-    if (!kFilter) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+SNCH_DI float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// kMode 0: the reference's libm chain.  1: sine-space filter on correctly rounded sqrt/rcp.  2: the same filter on the
+// MUFU approximations (rel. error <= 2^-22, i.e. <= 5e-7 on every quantity compared against the 2e-5 band); the two
+// exact-value branch decisions of the reference (l > radius, s <= 0) and the ill-conditioned corner (view cone within
+// ~6 degrees of a half space, where cos(beta) amplifies the error of sin(beta)) are handed to the exact chain.
+template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
+{
+    if (kMode == 0) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
     if (half_angle >= kHalfPi || md2 < FLT_EPSILON) return true;
     const V3 c = V3{(hi.x + lo.x) * 0.5f, (hi.y + lo.y) * 0.5f, (hi.z + lo.z) * 0.5f};
     const V3 w = c - o;
-    const float l = len(w); // exact: the reference branches on l > radius
-    const float rl = __frcp_rn(l);
+    float l, rl;
+    if (kMode == 1)
+    {
+        l = len(w); // exact: the reference branches on l > radius
+        rl = __frcp_rn(l);
+    }
+    else
+    {
+        const float l2 = w.x * w.x + w.y * w.y + w.z * w.z;
+        rl = rsqrt_approx(l2);
+        l = l2 * rl;
+        if (!(fabsf(l - radius) > 4e-6f * radius)) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2); // also NaN / l2 == 0
+    }
     const float t = fabsf(__fmaf_rn(axis.x, w.x, __fmaf_rn(axis.y, w.y, axis.z * w.z))) * rl;
     float sa, ca;
     __sincosf(half_angle, &sa, &ca);
@@ -437,7 +464,13 @@ template <bool kFilter> SNCH_DI bool cone_test(V3 axis, float half_angle, float 
     if (l > radius)
     {
         sb = radius * rl;
-        cb = sqrtf(fmaxf(__fmaf_rn(-sb, sb, 1.0f), 0.0f));
+        const float cb2 = fmaxf(__fmaf_rn(-sb, sb, 1.0f), 0.0f);
+        if (kMode == 1) cb = sqrtf(cb2);
+        else
+        {
+            if (cb2 < 0.01f) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+            cb = sqrt_approx(cb2);
+        }
     }
     else
     {
@@ -480,7 +513,7 @@ template <bool kFilter> SNCH_DI bool cone_test(V3 axis, float half_angle, float 
 // result is unchanged.
 constexpr int kParkCap = 8;     // parked leaves per lane (stack slots kStackDepth-1 downwards)
 constexpr int kParkFlushLanes = 16;
-template <bool kFilter>
+template <int kFilter>
 __global__ void __launch_bounds__(kQueryThreads)
     k_silhouette(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                  const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
@@ -608,7 +641,181 @@ __global__ void __launch_bounds__(kQueryThreads)
     }
 }
 
-template <bool kFilter>
+// Per-lane traversal with a WARP-SHARED leaf queue (v4).  profiles/r01k: in k_silhouette the parked-leaf loop ran at 3-4 of
+// 32 lanes (24% of all warp instructions) because every lane walks its own park list while the others wait, and the
+// per-thread stacks (576 B of local memory x 1024 threads per SM) missed L1 on 73% of their loads.  Here
+//   * a lane that reaches a leaf appends (owner lane, first edge, edge count) to a queue in shared memory; when the
+//     queue holds a warp's worth — or a lane has finished walking and needs its answer — the warp tests the queued
+//     leaves one per lane, reading the owner's query through shuffles, and hands results back through a shared
+//     per-lane minimum.  The answer is min over the silhouette edges within the bound, which does not depend on the
+//     order or grouping of the tests, so results are identical to the sequential loop's;
+//   * the lowest kSStack levels of each lane's traversal stack live in shared memory (conflict-free: the bank depends
+//     on the lane only), deeper levels spill to local memory.
+constexpr int kSStack = 12;
+constexpr int kLeafQueue = 128;  // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
+constexpr int kLeafFlushAt = 32;
+constexpr uint32_t kCoopMaxPayload = 1u << 27; // (first_edge << 2 | count) must leave 5 bits for the owner lane
+template <int kFilter>
+__global__ void __launch_bounds__(kQueryThreads, 8)
+    k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
+                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+{
+    __shared__ StackEntry s_stk[kSStack][kQueryThreads];
+    __shared__ uint32_t s_queue[kQueryThreads / 32][kLeafQueue];
+    __shared__ uint32_t s_qcount[kQueryThreads / 32];
+    __shared__ uint32_t s_result[kQueryThreads];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *queue = s_queue[wid];
+    Feeder fd{0u, 0u, false};
+    StackEntry lstk[kStackDepth - kSStack];
+    int sp = 0;
+    V3 p = V3{0.f, 0.f, 0.f};
+    bool flip = false, found = false, busy = false, pend = false;
+    float best = INFINITY, best2 = INFINITY;
+    uint32_t slot = kNone, node = kNone;
+    s_result[threadIdx.x] = kNone;
+    if (lane == 0) s_qcount[wid] = 0;
+    __syncwarp();
+    for (;;)
+    {
+        // ---- 1. queued leaves
+        uint32_t qc = s_qcount[wid];
+        if (qc >= kLeafFlushAt || __any_sync(kFull, pend && node == kNone))
+        {
+            while (qc > 0)
+            {
+                const uint32_t take = qc < 32u ? qc : 32u;
+                qc -= take;
+                const bool mine = (uint32_t)lane < take;
+                const uint32_t ent = mine ? queue[qc + lane] : ((uint32_t)lane << 27);
+                const int owner = (int)(ent >> 27);
+                const float ox = __shfl_sync(kFull, p.x, owner), oy = __shfl_sync(kFull, p.y, owner), oz = __shfl_sync(kFull, p.z, owner);
+                float ob = __shfl_sync(kFull, best, owner);
+                const bool oflip = __shfl_sync(kFull, (int)flip, owner) != 0;
+                const uint32_t first = (ent >> 2) & 0x01FFFFFFu, cnt = ent & 3u;
+                const V3 op = V3{ox, oy, oz};
+                float ob2 = ob * ob;
+                bool hit = false;
+                for (uint32_t k = 0; k < cnt; ++k)
+                { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
+                    float4 e0, e1, e2, e3;
+                    ld256(sv.ledge + first + k, e0, e1);
+                    ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
+                    const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
+                    V3 cp;
+                    const float dist = point_segment_distance(pa, pb, op, &cp);
+                    if (dist * dist > ob2) continue;
+                    bool is_sil = isnan(e1.z); // boundary edge
+                    if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, op - cp, dist, oflip);
+                    if (is_sil && dist <= ob)
+                    {
+                        ob = dist;
+                        ob2 = dist * dist;
+                        hit = true;
+                    }
+                }
+                if (hit) atomicMin(&s_result[(wid << 5) + owner], __float_as_uint(ob)); // distances are >= +0: uint order = float order
+                __syncwarp();
+            }
+            const uint32_t rb = s_result[threadIdx.x];
+            if (rb != kNone)
+            {
+                const float v = __uint_as_float(rb);
+                if (v <= best)
+                {
+                    best = v;
+                    best2 = v * v;
+                    found = true;
+                }
+                s_result[threadIdx.x] = kNone;
+            }
+            pend = false;
+            if (lane == 0) s_qcount[wid] = 0;
+            __syncwarp();
+        }
+        // ---- 2. finished walks hand in their answer; idle lanes take the next query
+        if (busy && node == kNone)
+        {
+            out_dist[slot] = found ? best : INFINITY;
+            busy = false;
+        }
+        const unsigned idle = __ballot_sync(kFull, !busy);
+        if (idle)
+        {
+            const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter);
+            if (s != kNone)
+            {
+                slot = perm ? __ldg(perm + s) : s;
+                p = load_point(q, slot);
+                flip = flipv ? (__ldg(flipv + slot) != 0) : false;
+                best = rmax ? __ldg(rmax + slot) : INFINITY;
+                best2 = best * best;
+                found = false;
+                busy = true;
+                sp = 0;
+                node = 0;
+            }
+            if (fd.exhausted && __all_sync(kFull, !busy)) break;
+        }
+        // ---- 3. one traversal step
+        if (node != kNone)
+        {
+            float4 a, b, c, d, e, f;
+            ld256(sv.snode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
+            ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
+            // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367),
+            // evaluated only for children that can still beat the current best
+            const bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+            const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+            const bool swap = m1 < m0;
+            uint32_t next = kNone;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const bool second = (ch == 1) != swap; // visit the nearer child first
+                const bool h = second ? h1 : h0;
+                const float m = second ? m1 : m0;
+                const uint32_t r = second ? r1 : r0;
+                if (!h) continue;
+                if (r & kLeafFlag)
+                {
+                    const uint32_t pos = atomicAdd(&s_qcount[wid], 1u);
+                    queue[pos] = ((uint32_t)lane << 27) | (r & (kCoopMaxPayload - 1u));
+                    pend = true;
+                }
+                else if (next == kNone) next = r;
+                else
+                {
+                    const StackEntry se = StackEntry{r, m};
+                    if (sp < kSStack) s_stk[sp][threadIdx.x] = se;
+                    else lstk[sp - kSStack] = se;
+                    ++sp;
+                }
+            }
+            if (next == kNone)
+            {
+                while (sp > 0)
+                {
+                    --sp;
+                    const StackEntry se = sp < kSStack ? s_stk[sp][threadIdx.x] : lstk[sp - kSStack];
+                    if (se.key <= best2)
+                    {
+                        next = se.node;
+                        break;
+                    }
+                }
+            }
+            node = next;
+        }
+        __syncwarp(); // queue appends of this step are visible to the whole warp before the next count is read
+    }
+}
+
+template <int kFilter>
 __global__ void __launch_bounds__(kQueryThreads)
     k_silhouette_packet(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                         const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
@@ -1024,6 +1231,24 @@ template <typename K> static unsigned persistent_grid(K kernel, const QueryTunin
     return (unsigned)(need < full ? (need ? need : 1) : full);
 }
 
+// per-lane silhouette traversal: v4 (warp-shared leaf queue, shared-memory stack) unless the knob or the scene size
+// (queue entries pack the owner lane next to the leaf payload) asks for v3; cone test per "query.cone_filter"
+template <int kFilter>
+static void launch_silhouette_lanes_f(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,
+                                      const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
+{
+    const bool coop = t.sil_kernel != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopMaxPayload;
+    if (coop) k_silhouette_coop<kFilter><<<persistent_grid(k_silhouette_coop<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+    else k_silhouette<kFilter><<<persistent_grid(k_silhouette<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+}
+static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,
+                                    const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
+{
+    if (t.cone_filter >= 2) launch_silhouette_lanes_f<2>(v, t, q, flip, rmax, perm, n, dist, counter, st);
+    else if (t.cone_filter == 1) launch_silhouette_lanes_f<1>(v, t, q, flip, rmax, perm, n, dist, counter, st);
+    else launch_silhouette_lanes_f<0>(v, t, q, flip, rmax, perm, n, dist, counter, st);
+}
+
 int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
                    cudaStream_t st, QueryCounters *qc)
 {
@@ -1065,18 +1290,13 @@ int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, 
     if (perm && (t.packet & 2))
     {
         if (t.cone_filter)
-            k_silhouette_packet<true><<<persistent_grid(k_silhouette_packet<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
+            k_silhouette_packet<1><<<persistent_grid(k_silhouette_packet<1>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
                 v, q, flip, rmax, perm, (uint32_t)n, dist, counter);
         else
-            k_silhouette_packet<false><<<persistent_grid(k_silhouette_packet<false>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
+            k_silhouette_packet<0><<<persistent_grid(k_silhouette_packet<0>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
                 v, q, flip, rmax, perm, (uint32_t)n, dist, counter);
     }
-    else if (t.cone_filter)
-        k_silhouette<true><<<persistent_grid(k_silhouette<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, (uint32_t)n,
-                                                                                                        dist, counter);
-    else
-        k_silhouette<false><<<persistent_grid(k_silhouette<false>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm,
-                                                                                                          (uint32_t)n, dist, counter);
+    else launch_silhouette_lanes(v, t, q, flip, rmax, perm, (uint32_t)n, dist, counter, st);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
@@ -1177,12 +1397,7 @@ int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers
     SNCH_CUDA(cudaMemsetAsync(counter, 0, 8, st));
     {
         TraversalTimer tt(qc, st);
-        if (t.cone_filter)
-            k_silhouette<true><<<persistent_grid(k_silhouette<true>, t, m), kQueryThreads, 0, st>>>(v, io.points, io.flip, d_closest, perm, m, d_sil,
-                                                                                                   counter);
-        else
-            k_silhouette<false><<<persistent_grid(k_silhouette<false>, t, m), kQueryThreads, 0, st>>>(v, io.points, io.flip, d_closest, perm, m,
-                                                                                                     d_sil, counter);
+        launch_silhouette_lanes(v, t, io.points, io.flip, d_closest, perm, m, d_sil, counter, st);
     }
     k_star_radius<<<(m + 255) / 256, 256, 0, st>>>(io.points, d_closest, d_sil, m, radius, spheres);
     if (qc) qc->launches += 1;

@@ -16,7 +16,9 @@ struct QueryTuning
     int sort_bits = 24;     // Morton key bits the ordering sorts on (top bits of the 30-bit code)
     int sort_rays = 0;      // also order ray batches by origin (off: random directions decorrelate the paths anyway)
     int packet = 1;         // warp-cooperative traversal of ordered batches: bit 0 closest point, bit 1 silhouette
-    int cone_filter = 1;    // silhouette: guard-banded sine-space normal-cone test (0 = always the reference's libm chain)
+    int cone_filter = 2;    // silhouette normal-cone test: 0 = the reference's libm chain, 1 = guard-banded sine-space filter on
+                            // correctly rounded sqrt/rcp, 2 = the same filter on MUFU approximations (decisions identical)
+    int sil_kernel = 1;     // silhouette per-lane kernel: 1 = warp-shared leaf queue + shared-memory stack (v4), 0 = per-lane parks (v3)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
 };
