@@ -78,58 +78,178 @@ struct PoolBuffer
     PoolBuffer &operator=(const PoolBuffer &) = delete;
 };
 
-// Host-pointer batches: inputs are copied into a device staging area, results copied back.
+// Host-pointer batches: inputs are copied into a device staging area, results copied back.  The batch is cut into
+// chunks ("query.host_chunk" queries each) that flow through three streams — H2D copies on a scene-owned copy stream,
+// kernels on the caller's stream, D2H copies on a second copy stream — so chunk k+1's inputs and chunk k-1's results
+// cross PCIe while chunk k is traversed.  Results do not depend on the chunking (every query is answered on its own).
+static int ensure_copy_streams(snch_scene *s)
+{
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (s->copy_in) return SNCH_OK;
+    SNCH_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
+    SNCH_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    return SNCH_OK;
+}
 struct Stager
 {
-    cudaStream_t st;
+    static constexpr int kMaxArrays = 16, kMaxChunks = 32;
+    snch_scene *s;
+    cudaStream_t st; // the caller's stream: kernels, allocation order, final synchronisation
     unsigned char *base;
+    uint64_t m; // queries staged
     uint64_t used = 0;
     int status = SNCH_OK;
-    struct Out
+    struct Arr
     {
-        void *host;
-        void *dev;
-        uint64_t bytes;
+        const unsigned char *src; // host input  (null for outputs)
+        unsigned char *dst;       // host output (null for inputs)
+        unsigned char *dev;
+        uint32_t stride; // bytes per query
     };
-    Out outs[12];
-    int n_outs = 0;
-    Stager(unsigned char *base_, cudaStream_t st_) : st(st_), base(base_) {}
+    Arr arrs[kMaxArrays];
+    int n_arrs = 0;
+    cudaEvent_t ev[2 * kMaxChunks + 2];
+    int n_ev = 0;
+    uint64_t chunk = 0;
+    int n_chunks = 0;
+    Stager(snch_scene *s_, unsigned char *base_, cudaStream_t st_, uint64_t m_) : s(s_), st(st_), base(base_), m(m_) {}
+    ~Stager()
+    {
+        for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
+    }
+    Stager(const Stager &) = delete;
+    Stager &operator=(const Stager &) = delete;
     static uint64_t pad(uint64_t b) { return align_up(b, 256); }
-    template <typename T> const T *in(const T *host, uint64_t bytes)
+    template <typename T> const T *in(const T *host, uint32_t stride)
     {
         if (!host || status != SNCH_OK) return nullptr;
-        void *d = base + used;
-        used += pad(bytes);
-        const cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) status = cuda_fail(e, "H2D staging copy");
-        return (const T *)d;
+        unsigned char *d = base + used;
+        used += pad(m * stride);
+        arrs[n_arrs++] = Arr{reinterpret_cast<const unsigned char *>(host), nullptr, d, stride};
+        return reinterpret_cast<const T *>(d);
     }
-    template <typename T> T *out(T *host, uint64_t bytes)
+    template <typename T> T *out(T *host, uint32_t stride)
     {
         if (!host || status != SNCH_OK) return nullptr;
-        void *d = base + used;
-        used += pad(bytes);
-        outs[n_outs++] = Out{host, d, bytes};
-        return (T *)d;
+        unsigned char *d = base + used;
+        used += pad(m * stride);
+        arrs[n_arrs++] = Arr{nullptr, reinterpret_cast<unsigned char *>(host), d, stride};
+        return reinterpret_cast<T *>(d);
     }
-    int finish()
+    int fail(cudaError_t e, const char *what)
     {
-        for (int i = 0; i < n_outs && status == SNCH_OK; ++i)
-        {
-            const cudaError_t e = cudaMemcpyAsync(outs[i].host, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, st);
-            if (e != cudaSuccess) status = cuda_fail(e, "D2H staging copy");
-        }
-        if (status == SNCH_OK)
-        {
-            const cudaError_t e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) status = cuda_fail(e, "cudaStreamSynchronize");
+        status = cuda_fail(e, what);
+        if (s->copy_in)
+        { // nothing may still be touching the staging area when the caller releases it
+            cudaStreamSynchronize(s->copy_in);
+            cudaStreamSynchronize(s->copy_out);
+            cudaGetLastError();
         }
         return status;
+    }
+    cudaEvent_t new_event()
+    {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+        {
+            fail(cudaGetLastError(), "cudaEventCreate");
+            return nullptr;
+        }
+        ev[n_ev++] = e;
+        return e;
+    }
+    // launch(o, c) enqueues the kernels for queries [o, o + c) of the staged arrays on `st`
+    template <typename Launch> int run(uint64_t chunk_queries, Launch &&launch)
+    {
+        if (status != SNCH_OK) return status;
+        chunk = chunk_queries ? chunk_queries : m;
+        if ((m + chunk - 1) / chunk > (uint64_t)kMaxChunks) chunk = (m + kMaxChunks - 1) / kMaxChunks;
+        chunk = (chunk + 31) & ~31ull; // keep every chunk's staged arrays 32 B aligned (float3 x 32, byte x 32)
+        n_chunks = (int)((m + chunk - 1) / chunk);
+        if (n_chunks <= 1)
+        { // small batch: everything on the caller's stream
+            for (int i = 0; i < n_arrs; ++i)
+                if (arrs[i].src)
+                {
+                    const cudaError_t e = cudaMemcpyAsync(arrs[i].dev, arrs[i].src, m * arrs[i].stride, cudaMemcpyHostToDevice, st);
+                    if (e != cudaSuccess) return fail(e, "H2D staging copy");
+                }
+            const int rc = launch((uint64_t)0, m);
+            if (rc != SNCH_OK) return status = rc;
+            for (int i = 0; i < n_arrs; ++i)
+                if (arrs[i].dst)
+                {
+                    const cudaError_t e = cudaMemcpyAsync(arrs[i].dst, arrs[i].dev, m * arrs[i].stride, cudaMemcpyDeviceToHost, st);
+                    if (e != cudaSuccess) return fail(e, "D2H staging copy");
+                }
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+            return SNCH_OK;
+        }
+        if (ensure_copy_streams(s) != SNCH_OK) return status = SNCH_ERR_CUDA;
+        cudaError_t e;
+        // the staging area was allocated in `st` order: the copy stream starts after it
+        cudaEvent_t ready = new_event();
+        if (!ready) return status;
+        if ((e = cudaEventRecord(ready, st)) != cudaSuccess) return fail(e, "cudaEventRecord");
+        if ((e = cudaStreamWaitEvent(s->copy_in, ready, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+        cudaEvent_t h2d_done[kMaxChunks];
+        for (int c = 0; c < n_chunks; ++c)
+        {
+            const uint64_t o = (uint64_t)c * chunk, cnt = m - o < chunk ? m - o : chunk;
+            for (int i = 0; i < n_arrs; ++i)
+                if (arrs[i].src)
+                {
+                    e = cudaMemcpyAsync(arrs[i].dev + o * arrs[i].stride, arrs[i].src + o * arrs[i].stride, cnt * arrs[i].stride,
+                                        cudaMemcpyHostToDevice, s->copy_in);
+                    if (e != cudaSuccess) return fail(e, "H2D staging copy");
+                }
+            if (!(h2d_done[c] = new_event())) return status;
+            if ((e = cudaEventRecord(h2d_done[c], s->copy_in)) != cudaSuccess) return fail(e, "cudaEventRecord");
+        }
+        for (int c = 0; c < n_chunks; ++c)
+        {
+            const uint64_t o = (uint64_t)c * chunk, cnt = m - o < chunk ? m - o : chunk;
+            if ((e = cudaStreamWaitEvent(st, h2d_done[c], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+            const int rc = launch(o, cnt);
+            if (rc != SNCH_OK)
+            {
+                cudaStreamSynchronize(s->copy_in); // nothing may still be touching the staging area when it is released
+                cudaStreamSynchronize(s->copy_out);
+                return status = rc;
+            }
+            cudaEvent_t kernels_done = new_event();
+            if (!kernels_done) return status;
+            if ((e = cudaEventRecord(kernels_done, st)) != cudaSuccess) return fail(e, "cudaEventRecord");
+            if ((e = cudaStreamWaitEvent(s->copy_out, kernels_done, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+            for (int i = 0; i < n_arrs; ++i)
+                if (arrs[i].dst)
+                {
+                    e = cudaMemcpyAsync(arrs[i].dst + o * arrs[i].stride, arrs[i].dev + o * arrs[i].stride, cnt * arrs[i].stride,
+                                        cudaMemcpyDeviceToHost, s->copy_out);
+                    if (e != cudaSuccess) return fail(e, "D2H staging copy");
+                }
+        }
+        cudaEvent_t all_out = new_event();
+        if (!all_out) return status;
+        if ((e = cudaEventRecord(all_out, s->copy_out)) != cudaSuccess) return fail(e, "cudaEventRecord");
+        if ((e = cudaStreamWaitEvent(st, all_out, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent"); // release after the last D2H
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(e, "cudaStreamSynchronize");
+        return SNCH_OK;
     }
 };
 
 // one launch handles at most this many queries (32-bit slots in the kernels); larger batches are split
 constexpr uint64_t kMaxLaunch = 1ull << 30;
+
+// queries per pipeline chunk of a host-pointer batch of m queries ("query.host_chunk"; 0 = one chunk)
+static uint64_t host_chunk(const snch_scene *s, uint64_t m)
+{
+    uint64_t c = s->tuning.host_chunk > 0 ? (uint64_t)s->tuning.host_chunk : m;
+    if (c > m) c = m;
+    if ((m + c - 1) / c > (uint64_t)Stager::kMaxChunks) c = (m + Stager::kMaxChunks - 1) / Stager::kMaxChunks;
+    return (c + 31) & ~31ull;
+}
 
 static int check_built(const snch_scene *s)
 {
@@ -455,7 +575,8 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
     for (uint64_t off = 0; off < n; off += kMaxLaunch)
     {
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
-        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
+        const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + 2 * Stager::pad(m * 4);
         PoolBuffer buf(s, cst, qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
@@ -465,14 +586,11 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(buf.p + qs, cst);
-        const float *dq = sg.in(pts + 3 * off, m * 12);
-        uint32_t *di = sg.out(out_index + off, m * 4);
-        float *dd = sg.out(out_distance + off, m * 4);
-        if (sg.status != SNCH_OK) return sg.status;
-        st = launch_closest(s->view, s->tuning, dq, m, di, dd, buf.p, cst, &s->counters);
-        if (st != SNCH_OK) return st;
-        st = sg.finish();
+        Stager sg(s, buf.p + qs, cst, m);
+        const float *dq = sg.in(pts + 3 * off, 12);
+        uint32_t *di = sg.out(out_index + off, 4);
+        float *dd = sg.out(out_distance + off, 4);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c) { return launch_closest(s->view, s->tuning, dq + 3 * o, c, di + o, dd + o, buf.p, cst, &s->counters); });
         if (st != SNCH_OK) return st;
     }
     return SNCH_OK;
@@ -501,7 +619,8 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
     for (uint64_t off = 0; off < n; off += kMaxLaunch)
     {
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
-        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
+        const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + Stager::pad(m) + 2 * Stager::pad(m * 4);
         PoolBuffer buf(s, cst, qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
@@ -513,15 +632,14 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(buf.p + qs, cst);
-        const float *dq = sg.in(pts + 3 * off, m * 12);
-        const uint8_t *df = sg.in(fo, m);
-        const float *dr = sg.in(ro, m * 4);
-        float *dd = sg.out(out_distance + off, m * 4);
-        if (sg.status != SNCH_OK) return sg.status;
-        st = launch_silhouette(s->view, s->tuning, dq, df, dr, m, dd, buf.p, cst, &s->counters);
-        if (st != SNCH_OK) return st;
-        st = sg.finish();
+        Stager sg(s, buf.p + qs, cst, m);
+        const float *dq = sg.in(pts + 3 * off, 12);
+        const uint8_t *df = sg.in(fo, 1);
+        const float *dr = sg.in(ro, 4);
+        float *dd = sg.out(out_distance + off, 4);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
+            return launch_silhouette(s->view, s->tuning, dq + 3 * o, df ? df + o : nullptr, dr ? dr + o : nullptr, c, dd + o, buf.p, cst, &s->counters);
+        });
         if (st != SNCH_OK) return st;
     }
     return SNCH_OK;
@@ -550,7 +668,8 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
     for (uint64_t off = 0; off < n; off += kMaxLaunch)
     {
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
-        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
+        const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : 2 * Stager::pad(m * 12) + Stager::pad(m * 4) + Stager::pad(m * 16) + Stager::pad(m);
         PoolBuffer buf(s, cst, qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
@@ -563,16 +682,16 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(buf.p + qs, cst);
-        const float *dor = sg.in(org + 3 * off, m * 12);
-        const float *ddi = sg.in(dir + 3 * off, m * 12);
-        const float *dtm = sg.in(to, m * 4);
-        snch_hit *dh = sg.out(ho, m * sizeof(snch_hit));
-        uint8_t *df = sg.out(fo, m);
-        if (sg.status != SNCH_OK) return sg.status;
-        st = launch_intersect(s->view, s->tuning, dor, ddi, dtm, m, dh, df, any_hit, buf.p, cst, &s->counters);
-        if (st != SNCH_OK) return st;
-        st = sg.finish();
+        Stager sg(s, buf.p + qs, cst, m);
+        const float *dor = sg.in(org + 3 * off, 12);
+        const float *ddi = sg.in(dir + 3 * off, 12);
+        const float *dtm = sg.in(to, 4);
+        snch_hit *dh = sg.out(ho, (uint32_t)sizeof(snch_hit));
+        uint8_t *df = sg.out(fo, 1);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
+            return launch_intersect(s->view, s->tuning, dor + 3 * o, ddi + 3 * o, dtm ? dtm + o : nullptr, c, dh ? dh + o : nullptr,
+                                    df ? df + o : nullptr, any_hit, buf.p, cst, &s->counters);
+        });
         if (st != SNCH_OK) return st;
     }
     return SNCH_OK;
@@ -601,7 +720,8 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
     for (uint64_t off = 0; off < n; off += kMaxLaunch)
     {
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
-        const uint64_t qs = query_scratch_bytes(m, s->tuning);
+        const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
+        const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 16) + 2 * Stager::pad(m * 12) + 2 * Stager::pad(m * 4);
         PoolBuffer buf(s, cst, qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
@@ -612,16 +732,15 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(buf.p + qs, cst);
-        const float *ds = sg.in(spheres + 4 * off, m * 16);
-        const float *dr = sg.in(rnd + 3 * off, m * 12);
-        int32_t *di = sg.out(out_index + off, m * 4);
-        float *dp = sg.out(out_pdf + off, m * 4);
-        float *dpt = sg.out(po, m * 12);
-        if (sg.status != SNCH_OK) return sg.status;
-        st = launch_sample(s->view, s->tuning, ds, dr, m, di, dp, dpt, buf.p, cst, &s->counters);
-        if (st != SNCH_OK) return st;
-        st = sg.finish();
+        Stager sg(s, buf.p + qs, cst, m);
+        const float *ds = sg.in(spheres + 4 * off, 16);
+        const float *dr = sg.in(rnd + 3 * off, 12);
+        int32_t *di = sg.out(out_index + off, 4);
+        float *dp = sg.out(out_pdf + off, 4);
+        float *dpt = sg.out(po, 12);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
+            return launch_sample(s->view, s->tuning, ds + 4 * o, dr + 3 * o, c, di + o, dp + o, dpt ? dpt + 3 * o : nullptr, buf.p, cst, &s->counters);
+        });
         if (st != SNCH_OK) return st;
     }
     return SNCH_OK;
@@ -676,6 +795,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.sil_kernel") t.sil_kernel = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
+    else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;
     else
@@ -912,7 +1032,8 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
     for (uint64_t off = 0; off < n; off += kMaxLaunch)
     {
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
-        const uint64_t qs = wost_scratch_bytes(m, s->tuning);
+        const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
+        const uint64_t qs = wost_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : 4 * Stager::pad(m * 12) + 2 * Stager::pad(m) + 6 * Stager::pad(m * 4) + Stager::pad(m * 16);
         PoolBuffer buf(s, cst, qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
@@ -937,24 +1058,38 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(buf.p + qs, cst);
-        w.points = sg.in(at(io->points_xyz, 3), m * 12);
-        w.flip = sg.in(at(io->flip, 1), m);
-        w.dirs = sg.in(at(io->dirs_xyz, 3), m * 12);
-        w.rnd = sg.in(at(io->rnd_uvw, 3), m * 12);
-        w.closest_index = sg.out(at(io->closest_index, 1), m * 4);
-        w.closest_distance = sg.out(at(io->closest_distance, 1), m * 4);
-        w.silhouette_distance = sg.out(at(io->silhouette_distance, 1), m * 4);
-        w.star_radius = sg.out(at(io->star_radius, 1), m * 4);
-        w.hits = sg.out(at(io->hits, 1), m * sizeof(snch_hit));
-        w.found = sg.out(at(io->found, 1), m);
-        w.sample_index = sg.out(at(io->sample_index, 1), m * 4);
-        w.sample_pdf = sg.out(at(io->sample_pdf, 1), m * 4);
-        w.sample_point = sg.out(at(io->sample_point_xyz, 3), m * 12);
-        if (sg.status != SNCH_OK) return sg.status;
-        st = launch_wost_step(s->view, s->tuning, w, m, buf.p, cst, &s->counters);
-        if (st != SNCH_OK) return st;
-        st = sg.finish();
+        Stager sg(s, buf.p + qs, cst, m);
+        w.points = sg.in(at(io->points_xyz, 3), 12);
+        w.flip = sg.in(at(io->flip, 1), 1);
+        w.dirs = sg.in(at(io->dirs_xyz, 3), 12);
+        w.rnd = sg.in(at(io->rnd_uvw, 3), 12);
+        w.closest_index = sg.out(at(io->closest_index, 1), 4);
+        w.closest_distance = sg.out(at(io->closest_distance, 1), 4);
+        w.silhouette_distance = sg.out(at(io->silhouette_distance, 1), 4);
+        w.star_radius = sg.out(at(io->star_radius, 1), 4);
+        w.hits = sg.out(at(io->hits, 1), (uint32_t)sizeof(snch_hit));
+        w.found = sg.out(at(io->found, 1), 1);
+        w.sample_index = sg.out(at(io->sample_index, 1), 4);
+        w.sample_pdf = sg.out(at(io->sample_pdf, 1), 4);
+        w.sample_point = sg.out(at(io->sample_point_xyz, 3), 12);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
+            WostBuffers wc;
+            auto sl = [&](auto *p, uint64_t stride) { return p ? p + stride * o : p; };
+            wc.points = sl(w.points, 3);
+            wc.flip = sl(w.flip, 1);
+            wc.dirs = sl(w.dirs, 3);
+            wc.rnd = sl(w.rnd, 3);
+            wc.closest_index = sl(w.closest_index, 1);
+            wc.closest_distance = sl(w.closest_distance, 1);
+            wc.silhouette_distance = sl(w.silhouette_distance, 1);
+            wc.star_radius = sl(w.star_radius, 1);
+            wc.hits = sl(w.hits, 1);
+            wc.found = sl(w.found, 1);
+            wc.sample_index = sl(w.sample_index, 1);
+            wc.sample_pdf = sl(w.sample_pdf, 1);
+            wc.sample_point = sl(w.sample_point, 3);
+            return launch_wost_step(s->view, s->tuning, wc, c, buf.p, cst, &s->counters);
+        });
         if (st != SNCH_OK) return st;
     }
     return SNCH_OK;

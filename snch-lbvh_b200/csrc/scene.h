@@ -21,6 +21,7 @@ struct QueryTuning
     int sil_kernel = 1;     // silhouette per-lane kernel: 1 = warp-shared leaf queue + shared-memory stack (v4), 0 = per-lane parks (v3)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
+    int host_chunk = 1 << 21; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk
 };
 // Launch accounting of the batched queries (snch_scene_counter): kernels launched, traversal kernels among them, and —
 // when "query.time_kernels" is set — device time of the traversal kernels alone (CUDA events on the launching stream).
@@ -61,6 +62,7 @@ struct snch_scene
     uint64_t scratch_bytes = 0;
     // stream-ordered pool for per-call scratch (query ordering, work counters, staging of host-pointer batches)
     cudaMemPool_t pool = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr; // copy streams of the host-pointer pipeline (created on first use)
     std::mutex mu;
     snch::QueryTuning tuning;
     snch::QueryCounters counters;

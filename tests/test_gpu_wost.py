@@ -74,6 +74,13 @@ def test_wost_step_device_pointers_and_optional_stages(pkg, meshes):
     assert np.array_equal(dev["found"].cpu().numpy(), host["found"])
     assert np.array_equal(dev["hits"].cpu().numpy()[:, 0].view(np.uint32), host["hits"]["t"].view(np.uint32))
     assert np.array_equal(dev["sample_index"].cpu().numpy(), host["sample_index"])
+    # host-pointer batches are pipelined in chunks (H2D / kernels / D2H on three streams): same results for any chunking
+    sc.set_option("query.host_chunk", 4001)
+    chunked = sc.wost_step(q, d, u)
+    sc.set_option("query.host_chunk", 1 << 21)
+    for k in host:
+        a, b = np.asarray(chunked[k]), np.asarray(host[k])
+        assert a.tobytes() == b.tobytes(), k
     # stages are optional: no directions -> no ray outputs, no uniforms -> no sample outputs; the rest is unchanged
     only = sc.wost_step(q)
     assert set(only) == {"closest_index", "closest_distance", "silhouette_distance", "star_radius"}
