@@ -184,6 +184,48 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def other_config(cfg, pkg, m, dev, stream):
+    """BASELINE.json configs C4 / C5 at their per-GPU share of the 8-GPU batch (one rank's shard: the tree is replicated,
+    so a rank's throughput does not depend on the other ranks).  Device-resident, CUDA events on `stream`."""
+    import torch
+    nu, per_gpu = {"c4": (1416, (1 << 24) // 8), "c5": (2240, (1 << 26) // 8)}[cfg]
+    v, f = m.bumpy_torus(nu, nu)
+    t0 = time.perf_counter()
+    sc = pkg.Scene3(v, f, device=dev).compute_silhouettes().build_bvh(stream=stream)
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    st = sc.stats()
+    lo, hi = m.mesh_bounds(v)
+    out = {"triangles": int(st["num_objects"]), "queries_per_gpu": per_gpu, "build_ms": st["build_ms"], "adjacency_ms": st["adjacency_ms"],
+           "arena_bytes": st["arena_bytes"], "scene_setup_wall_ms": setup_ms}
+    q = torch.from_numpy(m.points_in_box(per_gpu, lo, hi, 1.1 if cfg == "c4" else 1.0, seed=31)).to(f"cuda:{dev}")
+    d = torch.from_numpy(m.unit_directions(per_gpu, seed=32)).to(f"cuda:{dev}")
+
+    def timed(fn, reps=5):
+        fn()
+        stream.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        stream.synchronize()
+        return a.elapsed_time(b) / reps
+
+    with torch.cuda.stream(stream):
+        if cfg == "c4":
+            ms = timed(lambda: sc.intersect(q, d, stream=stream))
+            out.update(workload="C4 shard: closest-hit rays, t_max = inf", ms_per_step=ms, ray_mqps=per_gpu / ms / 1e3)
+        else:
+            u = torch.from_numpy(m.uniforms(per_gpu, 3, seed=33)).to(f"cuda:{dev}")
+            ms = timed(lambda: sc.wost_step(q, d, u, stream=stream), reps=3)
+            out.update(workload="C5 shard: one wavefront WoSt step per walker = closest point + silhouette (r_max = d) + ray (t_max = star "
+                                "radius) + sample-in-sphere, fused in snch_wost_step_batch",
+                       ms_per_step=ms, walker_steps_mqps=per_gpu / ms / 1e3, queries_mqps=4 * per_gpu / ms / 1e3)
+    del sc
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -193,6 +235,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--queries", type=int, default=N_QUERIES, help="queries per GPU per step (default: the C3 batch)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (closest/ray/build/reference CUDA)")
+    ap.add_argument("--also", default="", help="comma list of further BASELINE.json configs to time into `extra` on rank 0: "
+                    "c4 (16M rays / 8 GPUs on a 4M-triangle mesh), c5 (wavefront WoSt step, 64M walkers / 8 GPUs on a 10M-triangle mesh)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -326,7 +370,7 @@ def main():
         kernel_ms = trav_ms / max(trav_launches, 1)  # the traversal kernel alone (CUDA events on its stream, inside the timed region)
         achieved = b_q * n / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "snch::k_silhouette", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / statistics.mean(step_ms),
+                    "kernel": "snch::k_silhouette_coop<2>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / statistics.mean(step_ms),
                     "algorithmic_bytes_per_query": b_q, "must_visit_internal": V, "must_visit_leaves": Lv,
                     "peak_source": peak_src,
                     "note": "divergent gather over SNode 96 MB + LEdge 96 MB; the kernel is issue/L1-bound, not DRAM-bound: traffic << algorithmic "
@@ -335,7 +379,7 @@ def main():
         if os.path.exists(tp):
             roofline["traffic"] = json.load(open(tp)).get("k_silhouette_bytes_per_launch")
 
-    extra = {"build_ms": stats["build_ms"], "adjacency_host_ms": stats["adjacency_ms"], "arena_bytes": stats["arena_bytes"],
+    extra = {"build_ms": stats["build_ms"], "adjacency_ms": stats["adjacency_ms"], "arena_bytes": stats["arena_bytes"],
              "replicate_ms": replicate_ms if world > 1 else 0.0, "scene_setup_wall_ms": (t1 - t0) * 1e3,
              "finite_fraction": finite_frac, "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)}
     cpu_base = None
@@ -368,6 +412,11 @@ def main():
             if builds:
                 extra["build_ms"] = min(builds)
                 extra["build_roofline_frac"] = (334.0 * stats["num_objects"] / (min(builds) * 1e-3) / 1e9) / peak
+        for cfg in [c for c in args.also.split(",") if c]:
+            try:
+                extra[cfg] = other_config(cfg, pkg, m, dev, stream)
+            except Exception as ex:
+                extra[cfg] = {"error": repr(ex)}
         # the reference's own CUDA path on this B200 (prebuilt from the unmodified headers; absent -> skipped)
         try:
             from oracle import RefScene, ref_available

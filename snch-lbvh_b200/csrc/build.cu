@@ -347,19 +347,16 @@ SNCH_DI void store_records(BNode *bn, SNode *sn, Box lb, Box rb, Cone lc, Cone r
     sp[5] = make_float4(rc.half_angle, rc.radius, __uint_as_float(lsref), __uint_as_float(rsref));
 }
 
-// Leaf pass + fused bottom-up refit.  One thread per leaf in Morton order.
-//   leaf box      scene.cuh:870-885           leaf cone   scene.cuh:887-961
-//   climb         bvh.cuh:520-554 (boxes) and :556-604 (cones) fused into one pass, with the fences the reference's
-//                 cone pass lacks (quirk Q7).
-__global__ void __launch_bounds__(128) k_refit(BuildCtx c)
+// Leaf part of the refit, one thread per leaf k in Morton order: leaf box (scene.cuh:870-885), leaf normal cone from the
+// owned silhouette edges (scene.cuh:887-961), the LTri / LEdge traversal records, and the reference-layout leaf entries.
+// Returns the packed edge reference (first_edge << 2 | count).
+SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
 {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= c.n) return;
     const uint32_t ni = c.n - 1;
     const uint32_t obj = c.sorted_idx[k];
     const RefTriangle t = c.objects[obj];
     const V3 pa = ldv(c.verts, t.v.x), pb = ldv(c.verts, t.v.y), pc = ldv(c.verts, t.v.z);
-    Box box = tri_box(pa, pb, pc);
+    box = tri_box(pa, pb, pc);
     {
         float4 *lt = reinterpret_cast<float4 *>(c.ltri + k);
         lt[0] = make_float4(pa.x, pa.y, pa.z, __uint_as_float(obj));
@@ -369,7 +366,6 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
     }
     // ---- leaf normal cone from the owned silhouette edges, and their traversal records
     const V3 bc = box_centroid(box);
-    Cone cone;
     cone.axis = V3{0.f, 0.f, 0.f};
     cone.half_angle = kPi;
     cone.radius = 0.f;
@@ -434,36 +430,46 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
     const uint32_t packed = (eoff << 2) | cnt;
     c.edge_off[k] = packed;
 
-    uint32_t cur = ni + k;
+    const uint32_t cur = ni + k;
     store_aabb(c.aabbs + cur, box);
     store_cone(c.cones + cur, cone);
     c.nodes[cur].left = kNone;
     c.nodes[cur].right = kNone;
     c.nodes[cur].object = obj;
     c.q1[cur] = 0;
-    if (c.n == 1)
-    { // single-leaf tree: dummy root record whose second child can never be entered (NaN box, invalid cone)
-        c.nodes[cur].parent = kNone;
-        const float qnan = __int_as_float(0x7FC00000);
-        Box nb;
-        nb.lo = nb.hi = V3{qnan, qnan, qnan};
-        Cone ncone;
-        ncone.axis = V3{0.f, 0.f, 0.f};
-        ncone.half_angle = -kPi;
-        ncone.radius = 0.f;
-        store_records(c.bnode, c.snode, box, nb, cone, ncone, kLeafFlag | 0u, kLeafFlag | 0u, kLeafFlag | packed, kLeafFlag | 0u, kNone);
-        return;
-    }
-    bool taint = false;
-    uint32_t cur_bref = kLeafFlag | k, cur_sref = kLeafFlag | packed;
-    uint32_t parent = c.nodes[cur].parent;
+    return packed;
+}
+
+// single-leaf tree: dummy root record whose second child can never be entered (NaN box, invalid cone)
+SNCH_DI void refit_single_leaf(const BuildCtx &c, Box box, Cone cone, uint32_t packed)
+{
+    c.nodes[0].parent = kNone;
+    const float qnan = __int_as_float(0x7FC00000);
+    Box nb;
+    nb.lo = nb.hi = V3{qnan, qnan, qnan};
+    Cone ncone;
+    ncone.axis = V3{0.f, 0.f, 0.f};
+    ncone.half_angle = -kPi;
+    ncone.radius = 0.f;
+    store_records(c.bnode, c.snode, box, nb, cone, ncone, kLeafFlag | 0u, kLeafFlag | 0u, kLeafFlag | packed, kLeafFlag | 0u, kNone);
+}
+
+// The reference's bottom-up climb (bvh.cuh:520-554 boxes, :556-604 cones, fused; with the fences its cone pass lacks, Q7)
+// from node `cur` whose box / cone / record references the thread holds: the second arriver at a parent merges.
+SNCH_DI void refit_climb(const BuildCtx &c, uint32_t cur, Box box, Cone cone, uint32_t cur_bref, uint32_t cur_sref, bool taint,
+                         uint32_t parent)
+{
+    const uint32_t ni = c.n - 1;
     while (parent != kNone)
     {
-        __threadfence();
-        const uint32_t old = atomicAdd(c.flags + parent, 1u);
+        // topology is immutable here: fetched while the arrival atomic is in flight
+        const uint4 nd = __ldg(reinterpret_cast<const uint4 *>(c.nodes + parent)); // parent, left, right, object
+        // one acq_rel atomic instead of fence / atomic / fence: releases this thread's stores to the first arriver's
+        // sibling, acquires the sibling's stores for the second arriver (MEMBAR.ALL instead of two MEMBAR.SC)
+        uint32_t old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(c.flags + parent) : "memory");
         if (old == 0) return; // first arriver: the sibling subtree is not finished yet
-        __threadfence();
-        const uint32_t l = c.nodes[parent].left, r = c.nodes[parent].right;
+        const uint32_t l = nd.y, r = nd.z;
         const bool cur_is_left = (l == cur);
         const uint32_t sib = cur_is_left ? r : l;
         const Box sbox = load_aabb_cg(c.aabbs + sib);
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
         store_aabb(c.aabbs + parent, pbx);
         store_cone(c.cones + parent, pcn);
         c.q1[parent] = taint ? 1 : 0;
-        const uint32_t gp = c.nodes[parent].parent;
+        const uint32_t gp = nd.x;
         store_records(c.bnode + parent, c.snode + parent, lb, rb, lc, rc, cur_is_left ? cur_bref : sib_bref,
                       cur_is_left ? sib_bref : cur_bref, cur_is_left ? cur_sref : sib_sref, cur_is_left ? sib_sref : cur_sref, gp);
         cur = parent;
@@ -493,6 +499,190 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
         cone = pcn;
         cur_bref = cur_sref = parent;
         parent = gp;
+    }
+}
+
+// v1 refit ("build.refit_kernel" = 0): one thread per leaf, every thread climbs on its own.  profiles/r01k: the climb ran
+// at 4.1 of 32 lanes and was 75% of the kernel's warp instructions; the two fences per level were 44% of its stall samples.
+__global__ void __launch_bounds__(128) k_refit(BuildCtx c)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= c.n) return;
+    Box box;
+    Cone cone;
+    const uint32_t packed = refit_leaf(c, k, box, cone);
+    if (c.n == 1)
+    {
+        refit_single_leaf(c, box, cone, packed);
+        return;
+    }
+    const uint32_t cur = c.n - 1 + k;
+    refit_climb(c, cur, box, cone, kLeafFlag | k, kLeafFlag | packed, false, c.nodes[cur].parent);
+}
+
+// v2 refit (default): one CTA per kRefitLeaves consecutive leaves (Morton order).  An internal node whose Karras range lies
+// inside the CTA's leaf interval has its index, both subtrees and its arrival flag inside the CTA, so those nodes — all but
+// ~2% — are merged in ROUNDS out of shared memory: every thread that holds a finished node bumps its parent's flag (a
+// shared-memory atomic, no fence), second arrivers merge, then the surviving holders are compacted to the low threads, so
+// a round's merges run on full warps.  The CTA's slice of the topology (parent / children / range of internal nodes
+// [b0, b1)) is staged in shared memory once, so a round touches global memory only to store its products.  Nodes whose
+// parent's range leaves the interval ("escapes": the roots of the maximal in-CTA subtrees) are appended to a list that
+// k_refit_top finishes with the global flags and fences of the v1 climb.  Every merge is the same pure function of the same
+// two children as in v1, so all products are bit-identical (tests/test_gpu_build.py).
+constexpr int kRefitLeaves = 256;
+struct RefitShared
+{
+    float f[11][2 * kRefitLeaves]; // lo.xyz hi.xyz axis.xyz half_angle radius, by local id: leaves [0,B), internal B + (i - b0)
+    uint32_t bref[2 * kRefitLeaves], sref[2 * kRefitLeaves];
+    uint32_t n_parent[kRefitLeaves], n_left[kRefitLeaves], n_right[kRefitLeaves]; // topology of internal nodes b0 + j
+    uint2 range[kRefitLeaves];
+    uint32_t flag[kRefitLeaves];
+    uint2 queue[kRefitLeaves]; // (local id, parent)
+    uint8_t taint[2 * kRefitLeaves]; // Q1 taint of the subtree (exported as q1)
+    uint32_t count[2];
+};
+SNCH_DI void sh_put(RefitShared &sh, uint32_t id, Box b, Cone cn, uint32_t bref, uint32_t sref)
+{
+    sh.f[0][id] = b.lo.x;
+    sh.f[1][id] = b.lo.y;
+    sh.f[2][id] = b.lo.z;
+    sh.f[3][id] = b.hi.x;
+    sh.f[4][id] = b.hi.y;
+    sh.f[5][id] = b.hi.z;
+    sh.f[6][id] = cn.axis.x;
+    sh.f[7][id] = cn.axis.y;
+    sh.f[8][id] = cn.axis.z;
+    sh.f[9][id] = cn.half_angle;
+    sh.f[10][id] = cn.radius;
+    sh.bref[id] = bref;
+    sh.sref[id] = sref;
+}
+SNCH_DI void sh_get(const RefitShared &sh, uint32_t id, Box &b, Cone &cn)
+{
+    b.lo = V3{sh.f[0][id], sh.f[1][id], sh.f[2][id]};
+    b.hi = V3{sh.f[3][id], sh.f[4][id], sh.f[5][id]};
+    cn.axis = V3{sh.f[6][id], sh.f[7][id], sh.f[8][id]};
+    cn.half_angle = sh.f[9][id];
+    cn.radius = sh.f[10][id];
+}
+__global__ void __launch_bounds__(kRefitLeaves, 4) k_refit_coop(BuildCtx c)
+{
+    __shared__ RefitShared sh;
+    constexpr uint32_t B = kRefitLeaves;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t b0 = blockIdx.x * B, b1 = min(b0 + B, c.n);
+    const uint32_t ni = c.n - 1;
+    const uint32_t k = b0 + tid;
+    sh.flag[tid] = 0;
+    sh.taint[tid] = 0;
+    if (tid < 2) sh.count[tid] = 0;
+    if (k < ni)
+    { // internal node k: its range ends or starts at leaf k, so only nodes [b0, b1) can lie inside the interval
+        const uint4 nd = *reinterpret_cast<const uint4 *>(c.nodes + k); // parent, left, right, object
+        sh.n_parent[tid] = nd.x;
+        sh.n_left[tid] = nd.y;
+        sh.n_right[tid] = nd.z;
+        sh.range[tid] = c.ranges[k];
+    }
+    else sh.range[tid] = make_uint2(0u, 0xFFFFFFFFu); // never inside
+    // item held by this thread: a finished node (local id) and its parent
+    bool active = k < c.n;
+    uint32_t cl = tid, parent = kNone;
+    if (active)
+    {
+        Box box;
+        Cone cone;
+        const uint32_t packed = refit_leaf(c, k, box, cone);
+        sh_put(sh, tid, box, cone, kLeafFlag | k, kLeafFlag | packed);
+        if (c.n == 1)
+        {
+            refit_single_leaf(c, box, cone, packed);
+            active = false;
+        }
+        else parent = c.nodes[ni + k].parent;
+    }
+    __syncthreads();
+    for (uint32_t round = 0;; ++round)
+    {
+        if (active)
+        {
+            active = false;
+            if (parent != kNone)
+            {
+                const uint32_t pj = parent - b0; // (wraps for parent < b0: then >= B)
+                bool inside = false;
+                if (pj < B)
+                {
+                    const uint2 rg = sh.range[pj];
+                    inside = rg.x >= b0 && rg.y < b1;
+                }
+                const uint32_t cur = cl < B ? ni + b0 + cl : b0 + (cl - B);
+                if (!inside) c.escapes[atomicAdd(c.counters + 2, 1u)] = cur;
+                else if (atomicAdd(&sh.flag[pj], 1u) != 0)
+                { // second arriver: the sibling's entry was written in an earlier round (or by the leaf pass)
+                    const uint32_t l = sh.n_left[pj], r = sh.n_right[pj], gp = sh.n_parent[pj];
+                    const bool cur_is_left = (l == cur);
+                    const uint32_t sib = cur_is_left ? r : l;
+                    const uint32_t sl = sib >= ni ? sib - ni - b0 : B + (sib - b0);
+                    Box box, sbox;
+                    Cone cone, scone;
+                    sh_get(sh, cl, box, cone);
+                    sh_get(sh, sl, sbox, scone);
+                    const uint32_t l_id = cur_is_left ? cl : sl, r_id = cur_is_left ? sl : cl;
+                    const Box lb = cur_is_left ? box : sbox, rb = cur_is_left ? sbox : box;
+                    const Cone lc = cur_is_left ? cone : scone, rc = cur_is_left ? scone : cone;
+                    const Box pbx = box_merge(lb, rb);
+                    bool q1;
+                    const Cone pcn = cone_merge(lc, rc, box_centroid(lb), box_centroid(rb), box_centroid(pbx), &q1);
+                    if (q1) atomicAdd(c.counters + 1, 1u);
+                    const bool taint = sh.taint[cl] || sh.taint[sl] || q1;
+                    store_aabb(c.aabbs + parent, pbx);
+                    store_cone(c.cones + parent, pcn);
+                    c.q1[parent] = taint ? 1 : 0;
+                    store_records(c.bnode + parent, c.snode + parent, lb, rb, lc, rc, sh.bref[l_id], sh.bref[r_id], sh.sref[l_id], sh.sref[r_id],
+                                  gp);
+                    const uint32_t pl = B + pj;
+                    sh_put(sh, pl, pbx, pcn, parent, parent);
+                    sh.taint[pl] = taint ? 1 : 0;
+                    cl = pl;
+                    parent = gp;
+                    active = true;
+                }
+            }
+        }
+        // compact the surviving holders onto the low threads
+        if (tid == 0) sh.count[(round + 1) & 1] = 0;
+        if (active) sh.queue[atomicAdd(&sh.count[round & 1], 1u)] = make_uint2(cl, parent);
+        __syncthreads();
+        const uint32_t total = sh.count[round & 1];
+        if (total == 0) break;
+        active = tid < total;
+        uint2 it = make_uint2(0u, kNone);
+        if (active) it = sh.queue[tid];
+        __syncthreads();
+        cl = it.x;
+        parent = it.y;
+    }
+}
+
+// Finishes the refit above the CTA subtrees: one thread per escape (the root of a maximal in-CTA subtree, ~12 per CTA),
+// each continuing the reference's climb with the global arrival flags.  Everything it reads was stored by k_refit_coop.
+__global__ void __launch_bounds__(128) k_refit_top(BuildCtx c)
+{
+    const uint32_t n_esc = c.counters[2];
+    const uint32_t ni = c.n - 1;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_esc; e += gridDim.x * blockDim.x)
+    {
+        const uint32_t cur = c.escapes[e];
+        const Box box = load_aabb_cg(c.aabbs + cur);
+        const Cone cone = load_cone_cg(c.cones + cur);
+        uint32_t bref = cur, sref = cur;
+        if (cur >= ni)
+        {
+            bref = kLeafFlag | (cur - ni);
+            sref = kLeafFlag | c.edge_off[cur - ni];
+        }
+        refit_climb(c, cur, box, cone, bref, sref, c.q1[cur] != 0, c.nodes[cur].parent);
     }
 }
 
@@ -641,7 +831,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     };
     const uint64_t o_ktmp = stake((uint64_t)nT * 4), o_vtmp = stake((uint64_t)nT * 4);
     const uint64_t o_sort = stake(sort_elems * 4), o_scan = stake(scan_elems * 4);
-    const uint64_t o_flags = stake((uint64_t)nT * 4), o_box = stake(64), o_cnt = stake(64);
+    const uint64_t o_flags = stake((uint64_t)nT * 4), o_esc = stake((uint64_t)nT * 4), o_box = stake(64), o_cnt = stake(64);
     if (s->scratch_bytes < so)
     {
         if (s->scratch) cudaFree(s->scratch);
@@ -677,6 +867,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     c.edge_off = (uint32_t *)(b + h.off_edge_off);
     c.scene_box = (int *)(sc + o_box);
     c.flags = (uint32_t *)(sc + o_flags);
+    c.escapes = (uint32_t *)(sc + o_esc);
     c.counters = (uint32_t *)(sc + o_cnt);
 
     cudaEvent_t ev0, ev1;
@@ -699,7 +890,17 @@ int build_device(snch_scene *s, cudaStream_t stream)
         k_owned_count<<<g256, 256, 0, stream>>>(c);
         launches += (nT > 1 ? 1 : 0) + 1 + exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream);
     }
-    k_refit<<<(nT + 127) / 128, 128, 0, stream>>>(c);
+    if (s->opt_refit_kernel == 0) k_refit<<<(nT + 127) / 128, 128, 0, stream>>>(c);
+    else
+    {
+        const unsigned ctas = (nT + kRefitLeaves - 1) / kRefitLeaves;
+        k_refit_coop<<<ctas, kRefitLeaves, 0, stream>>>(c);
+        if (nT > 1)
+        {
+            k_refit_top<<<ctas < 8 ? 1 : ctas / 8, 128, 0, stream>>>(c); // 16 threads per CTA of the pass above (~12 escapes each); grid-stride beyond
+            launches += 1;
+        }
+    }
     launches += 1;
     s->build_launches = (uint64_t)launches;
     SNCH_CUDA(cudaGetLastError());

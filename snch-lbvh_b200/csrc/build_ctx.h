@@ -26,7 +26,8 @@ struct BuildCtx
     // scratch
     int *scene_box; // 6 ordered ints: lo xyz, hi xyz
     uint32_t *flags;
-    uint32_t *counters; // [0] collision, [1] q1 events
+    uint32_t *escapes;  // k_refit_coop -> k_refit_top: roots of the per-CTA subtrees (node ids), counters[2] of them
+    uint32_t *counters; // [0] collision, [1] q1 events, [2] escapes
 };
 
 // Karras 2012 on the augmented key (morton << 32 | index): uses n, morton, sorted_idx, nodes, ranges, counters[0]

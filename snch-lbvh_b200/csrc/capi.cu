@@ -1,5 +1,6 @@
 // capi.cu — the C-ABI (include/snch_b200.h): scene lifetime, build, exports, batched query entry points, replication.
 #include "scene.h"
+#include "sort_scan.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -81,18 +82,23 @@ struct PoolBuffer
 // Host-pointer batches: inputs are copied into a device staging area, results copied back.  The batch is cut into
 // chunks ("query.host_chunk" queries each) that flow through three streams — H2D copies on a scene-owned copy stream,
 // kernels on the caller's stream, D2H copies on a second copy stream — so chunk k+1's inputs and chunk k-1's results
-// cross PCIe while chunk k is traversed.  Results do not depend on the chunking (every query is answered on its own).
+// cross PCIe while chunk k is traversed.  Consecutive chunks alternate between the caller's stream and a second compute
+// stream (each with its own ordering scratch): a persistent traversal kernel ends with a tail of a few expensive queries
+// that occupy single lanes for 2-3 ms (measured: 8 back-to-back chunks on one stream cost +20 ms), and the next chunk's
+// CTAs fill the SMs as the previous chunk's drain.  Results do not depend on the chunking (every query is answered on
+// its own).
 static int ensure_copy_streams(snch_scene *s)
 {
     std::lock_guard<std::mutex> lock(s->mu);
     if (s->copy_in) return SNCH_OK;
     SNCH_CUDA(cudaStreamCreateWithFlags(&s->copy_in, cudaStreamNonBlocking));
     SNCH_CUDA(cudaStreamCreateWithFlags(&s->copy_out, cudaStreamNonBlocking));
+    SNCH_CUDA(cudaStreamCreateWithFlags(&s->compute_b, cudaStreamNonBlocking));
     return SNCH_OK;
 }
 struct Stager
 {
-    static constexpr int kMaxArrays = 16, kMaxChunks = 32;
+    static constexpr int kMaxArrays = 16, kMaxChunks = 32, kLanes = 2;
     snch_scene *s;
     cudaStream_t st; // the caller's stream: kernels, allocation order, final synchronisation
     unsigned char *base;
@@ -143,6 +149,7 @@ struct Stager
         { // nothing may still be touching the staging area when the caller releases it
             cudaStreamSynchronize(s->copy_in);
             cudaStreamSynchronize(s->copy_out);
+            cudaStreamSynchronize(s->compute_b);
             cudaGetLastError();
         }
         return status;
@@ -158,7 +165,8 @@ struct Stager
         ev[n_ev++] = e;
         return e;
     }
-    // launch(o, c) enqueues the kernels for queries [o, o + c) of the staged arrays on `st`
+    // launch(o, c, stream, lane) enqueues the kernels for queries [o, o + c) of the staged arrays on `stream`, using the
+    // lane's (0 or 1) scratch area
     template <typename Launch> int run(uint64_t chunk_queries, Launch &&launch)
     {
         if (status != SNCH_OK) return status;
@@ -174,7 +182,7 @@ struct Stager
                     const cudaError_t e = cudaMemcpyAsync(arrs[i].dev, arrs[i].src, m * arrs[i].stride, cudaMemcpyHostToDevice, st);
                     if (e != cudaSuccess) return fail(e, "H2D staging copy");
                 }
-            const int rc = launch((uint64_t)0, m);
+            const int rc = launch((uint64_t)0, m, st, 0);
             if (rc != SNCH_OK) return status = rc;
             for (int i = 0; i < n_arrs; ++i)
                 if (arrs[i].dst)
@@ -193,6 +201,8 @@ struct Stager
         if (!ready) return status;
         if ((e = cudaEventRecord(ready, st)) != cudaSuccess) return fail(e, "cudaEventRecord");
         if ((e = cudaStreamWaitEvent(s->copy_in, ready, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+        if ((e = cudaStreamWaitEvent(s->compute_b, ready, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+        cudaStream_t lanes[2] = {st, s->compute_b};
         cudaEvent_t h2d_done[kMaxChunks];
         for (int c = 0; c < n_chunks; ++c)
         {
@@ -210,17 +220,19 @@ struct Stager
         for (int c = 0; c < n_chunks; ++c)
         {
             const uint64_t o = (uint64_t)c * chunk, cnt = m - o < chunk ? m - o : chunk;
-            if ((e = cudaStreamWaitEvent(st, h2d_done[c], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
-            const int rc = launch(o, cnt);
+            cudaStream_t cs = lanes[c & 1];
+            if ((e = cudaStreamWaitEvent(cs, h2d_done[c], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
+            const int rc = launch(o, cnt, cs, c & 1);
             if (rc != SNCH_OK)
             {
                 cudaStreamSynchronize(s->copy_in); // nothing may still be touching the staging area when it is released
                 cudaStreamSynchronize(s->copy_out);
+                cudaStreamSynchronize(s->compute_b);
                 return status = rc;
             }
             cudaEvent_t kernels_done = new_event();
             if (!kernels_done) return status;
-            if ((e = cudaEventRecord(kernels_done, st)) != cudaSuccess) return fail(e, "cudaEventRecord");
+            if ((e = cudaEventRecord(kernels_done, cs)) != cudaSuccess) return fail(e, "cudaEventRecord");
             if ((e = cudaStreamWaitEvent(s->copy_out, kernels_done, 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
             for (int i = 0; i < n_arrs; ++i)
                 if (arrs[i].dst)
@@ -337,6 +349,9 @@ int snch_scene_destroy(snch_scene *s)
     if (s->adj) cudaFree(s->adj);
     if (s->scratch) cudaFree(s->scratch);
     if (s->pool) cudaMemPoolDestroy(s->pool);
+    if (s->copy_in) cudaStreamDestroy(s->copy_in);
+    if (s->copy_out) cudaStreamDestroy(s->copy_out);
+    if (s->compute_b) cudaStreamDestroy(s->compute_b);
     if (s->counters.ev0) cudaEventDestroy(s->counters.ev0);
     if (s->counters.ev1) cudaEventDestroy(s->counters.ev1);
     delete s;
@@ -578,7 +593,7 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + 2 * Stager::pad(m * 4);
-        PoolBuffer buf(s, cst, qs + stage);
+        PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         if (k == PK_DEVICE)
         {
@@ -586,11 +601,13 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(s, buf.p + qs, cst, m);
+        Stager sg(s, buf.p + Stager::kLanes * qs, cst, m);
         const float *dq = sg.in(pts + 3 * off, 12);
         uint32_t *di = sg.out(out_index + off, 4);
         float *dd = sg.out(out_distance + off, 4);
-        st = sg.run(cm, [&](uint64_t o, uint64_t c) { return launch_closest(s->view, s->tuning, dq + 3 * o, c, di + o, dd + o, buf.p, cst, &s->counters); });
+        st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
+            return launch_closest(s->view, s->tuning, dq + 3 * o, c, di + o, dd + o, buf.p + lane * qs, ls, &s->counters);
+        });
         if (st != SNCH_OK) return st;
     }
     return SNCH_OK;
@@ -622,7 +639,7 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + Stager::pad(m) + 2 * Stager::pad(m * 4);
-        PoolBuffer buf(s, cst, qs + stage);
+        PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         const uint8_t *fo = flip ? flip + off : nullptr;
         const float *ro = r_max ? r_max + off : nullptr;
@@ -632,13 +649,14 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(s, buf.p + qs, cst, m);
+        Stager sg(s, buf.p + Stager::kLanes * qs, cst, m);
         const float *dq = sg.in(pts + 3 * off, 12);
         const uint8_t *df = sg.in(fo, 1);
         const float *dr = sg.in(ro, 4);
         float *dd = sg.out(out_distance + off, 4);
-        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
-            return launch_silhouette(s->view, s->tuning, dq + 3 * o, df ? df + o : nullptr, dr ? dr + o : nullptr, c, dd + o, buf.p, cst, &s->counters);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
+            return launch_silhouette(s->view, s->tuning, dq + 3 * o, df ? df + o : nullptr, dr ? dr + o : nullptr, c, dd + o, buf.p + lane * qs, ls,
+                                     &s->counters);
         });
         if (st != SNCH_OK) return st;
     }
@@ -671,7 +689,7 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : 2 * Stager::pad(m * 12) + Stager::pad(m * 4) + Stager::pad(m * 16) + Stager::pad(m);
-        PoolBuffer buf(s, cst, qs + stage);
+        PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         const float *to = t_max ? t_max + off : nullptr;
         snch_hit *ho = out_hits ? out_hits + off : nullptr;
@@ -682,15 +700,15 @@ int snch_intersect_batch(const snch_scene *cs, const float *org, const float *di
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(s, buf.p + qs, cst, m);
+        Stager sg(s, buf.p + Stager::kLanes * qs, cst, m);
         const float *dor = sg.in(org + 3 * off, 12);
         const float *ddi = sg.in(dir + 3 * off, 12);
         const float *dtm = sg.in(to, 4);
         snch_hit *dh = sg.out(ho, (uint32_t)sizeof(snch_hit));
         uint8_t *df = sg.out(fo, 1);
-        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
+        st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
             return launch_intersect(s->view, s->tuning, dor + 3 * o, ddi + 3 * o, dtm ? dtm + o : nullptr, c, dh ? dh + o : nullptr,
-                                    df ? df + o : nullptr, any_hit, buf.p, cst, &s->counters);
+                                    df ? df + o : nullptr, any_hit, buf.p + lane * qs, ls, &s->counters);
         });
         if (st != SNCH_OK) return st;
     }
@@ -723,7 +741,7 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = query_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 16) + 2 * Stager::pad(m * 12) + 2 * Stager::pad(m * 4);
-        PoolBuffer buf(s, cst, qs + stage);
+        PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         float *po = out_point ? out_point + 3 * off : nullptr;
         if (k == PK_DEVICE)
@@ -732,14 +750,15 @@ int snch_sample_in_sphere_batch(const snch_scene *cs, const float *spheres, cons
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(s, buf.p + qs, cst, m);
+        Stager sg(s, buf.p + Stager::kLanes * qs, cst, m);
         const float *ds = sg.in(spheres + 4 * off, 16);
         const float *dr = sg.in(rnd + 3 * off, 12);
         int32_t *di = sg.out(out_index + off, 4);
         float *dp = sg.out(out_pdf + off, 4);
         float *dpt = sg.out(po, 12);
-        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
-            return launch_sample(s->view, s->tuning, ds + 4 * o, dr + 3 * o, c, di + o, dp + o, dpt ? dpt + 3 * o : nullptr, buf.p, cst, &s->counters);
+        st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
+            return launch_sample(s->view, s->tuning, ds + 4 * o, dr + 3 * o, c, di + o, dp + o, dpt ? dpt + 3 * o : nullptr, buf.p + lane * qs, ls,
+                                 &s->counters);
         });
         if (st != SNCH_OK) return st;
     }
@@ -798,6 +817,8 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;
+    else if (k == "build.refit_kernel") s->opt_refit_kernel = (int)value;
+    else if (k == "sort.onesweep") set_sort_onesweep((int)value); // process-wide (A/B of the two radix sorts)
     else
     {
         set_error("snch_scene_set_option: unknown option '" + k + "'");
@@ -1035,7 +1056,7 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = wost_scratch_bytes(cm, s->tuning);
         const uint64_t stage = k == PK_DEVICE ? 0 : 4 * Stager::pad(m * 12) + 2 * Stager::pad(m) + 6 * Stager::pad(m * 4) + Stager::pad(m * 16);
-        PoolBuffer buf(s, cst, qs + stage);
+        PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         WostBuffers w;
         auto at = [&](auto *p, uint64_t stride) { return p ? p + stride * off : p; };
@@ -1058,7 +1079,7 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
             if (st != SNCH_OK) return st;
             continue;
         }
-        Stager sg(s, buf.p + qs, cst, m);
+        Stager sg(s, buf.p + Stager::kLanes * qs, cst, m);
         w.points = sg.in(at(io->points_xyz, 3), 12);
         w.flip = sg.in(at(io->flip, 1), 1);
         w.dirs = sg.in(at(io->dirs_xyz, 3), 12);
@@ -1072,7 +1093,7 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
         w.sample_index = sg.out(at(io->sample_index, 1), 4);
         w.sample_pdf = sg.out(at(io->sample_pdf, 1), 4);
         w.sample_point = sg.out(at(io->sample_point_xyz, 3), 12);
-        st = sg.run(cm, [&](uint64_t o, uint64_t c) {
+        st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
             WostBuffers wc;
             auto sl = [&](auto *p, uint64_t stride) { return p ? p + stride * o : p; };
             wc.points = sl(w.points, 3);
@@ -1088,7 +1109,7 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
             wc.sample_index = sl(w.sample_index, 1);
             wc.sample_pdf = sl(w.sample_pdf, 1);
             wc.sample_point = sl(w.sample_point, 3);
-            return launch_wost_step(s->view, s->tuning, wc, c, buf.p, cst, &s->counters);
+            return launch_wost_step(s->view, s->tuning, wc, c, buf.p + lane * qs, ls, &s->counters);
         });
         if (st != SNCH_OK) return st;
     }

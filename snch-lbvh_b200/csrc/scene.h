@@ -21,7 +21,9 @@ struct QueryTuning
     int sil_kernel = 1;     // silhouette per-lane kernel: 1 = warp-shared leaf queue + shared-memory stack (v4), 0 = per-lane parks (v3)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
-    int host_chunk = 1 << 21; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk
+    int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
+                              // Measured on C3 (16.7M queries): 0 -> 60.5 ms, 8M -> 59.5, 4M -> 60.0, 2M -> 63.5, 1M -> 73.1: every extra
+                              // launch pays its own tail and orders a sparser batch, so chunks stay large
 };
 // Launch accounting of the batched queries (snch_scene_counter): kernels launched, traversal kernels among them, and —
 // when "query.time_kernels" is set — device time of the traversal kernels alone (CUDA events on the launching stream).
@@ -62,7 +64,7 @@ struct snch_scene
     uint64_t scratch_bytes = 0;
     // stream-ordered pool for per-call scratch (query ordering, work counters, staging of host-pointer batches)
     cudaMemPool_t pool = nullptr;
-    cudaStream_t copy_in = nullptr, copy_out = nullptr; // copy streams of the host-pointer pipeline (created on first use)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr, compute_b = nullptr; // streams of the host-pointer pipeline (created on first use)
     std::mutex mu;
     snch::QueryTuning tuning;
     snch::QueryCounters counters;
@@ -70,6 +72,7 @@ struct snch_scene
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0, opt_refit_only = 0;
+    int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds (v2), 0 = one climbing thread per leaf (v1)
 };
 
 namespace snch

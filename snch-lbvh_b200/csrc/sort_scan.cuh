@@ -1,6 +1,8 @@
 // sort_scan.cuh — device-wide primitives used by the build (and by query re-ordering):
 //   * exclusive_scan_u32 : reduce-then-scan over up to 16 Mi elements per level (recursive above that)
-//   * radix_sort_pairs   : stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass
+//   * radix_sort_pairs   : stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass — onesweep (one histogram
+//                          kernel + one decoupled-look-back kernel per pass); the histogram/scan/scatter multi-kernel form
+//                          remains for n >= 2^30 and for A/B ("sort.onesweep" = 0)
 //
 // Replaces thrust::stable_sort_by_key in the reference (bvh.cuh:452-454), which drags a 48-byte payload through every
 // pass; here only (key, index) = 8 bytes move and the payload is gathered once afterwards.
@@ -37,7 +39,9 @@ inline uint64_t sort_scratch_elems(uint64_t n)
 {
     const uint64_t tiles = (n + kSortTile - 1) / kSortTile;
     const uint64_t counts = tiles * kSortBins;
-    return counts + scan_scratch_elems(counts) + 8;
+    const uint64_t multipass = counts + scan_scratch_elems(counts) + 8;
+    const uint64_t onesweep = 4 * kSortBins + 8 + 4 * (2 * counts + kSortBins); // global histograms, tile counters, per-pass status of (half) tiles
+    return multipass > onesweep ? multipass : onesweep;
 }
 
 // both return the number of kernels they launched (the library reports launch counts, snch_scene_counter)
@@ -47,5 +51,8 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, uint32_t *
 // result; keys_tmp/vals_tmp are ping-pong buffers of the same size; scratch has sort_scratch_elems(n) u32.
 int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
                       uint32_t *scratch, cudaStream_t stream, int first_bit = 0);
+
+// process-wide switch between the onesweep and the multi-kernel sort (snch_scene_set_option "sort.onesweep")
+void set_sort_onesweep(int on);
 
 } // namespace snch

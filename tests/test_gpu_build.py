@@ -78,6 +78,29 @@ def test_rebuild_is_deterministic(pkg, meshes):
         assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(sc.export(k)) if a.dtype == np.float32 else sc.export(k))
 
 
+@pytest.mark.parametrize("name", ["tet", "one", "ico2", "grid6", "grid40", "torus97x61", "flat", "dups", "torus300", "torus708"])
+def test_refit_kernels_produce_identical_arenas(pkg, meshes, name):
+    """"build.refit_kernel": the block-cooperative refit (v2, rounds in shared memory) and the per-thread climb (v1) apply the
+    same merges to the same children; "sort.onesweep": both radix sorts are stable.  The whole arena — reference-layout
+    arrays and traversal records — is bit-identical for every combination."""
+    if name == "one":
+        v, f = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.int32)
+    else:
+        v, f = _mesh(meshes, name)
+    sc = pkg.Scene3(v, f).compute_silhouettes()
+    arenas = []
+    import torch
+    try:
+        for kern, onesweep in ((0, 0), (1, 1), (1, 0), (1, 1)):  # "sort.onesweep" is process-wide: restored below
+            sc.set_option("build.refit_kernel", kern).set_option("sort.onesweep", onesweep).build_bvh()
+            arenas.append(sc.arena_tensor().clone())
+    finally:
+        sc.set_option("build.refit_kernel", 1).set_option("sort.onesweep", 1)
+    for a in arenas[1:]:
+        assert a.shape == arenas[0].shape
+        assert torch.equal(arenas[0], a), f"{int((arenas[0] != a).sum())} arena bytes differ between refit kernels / radix sorts"
+
+
 def test_tree_invariants_full_size(pkg, meshes):
     """Size-independent structure checks on the 1M-triangle build: sortedness, permutation, parent/child consistency,
     every internal box encloses its children, ranges partition."""

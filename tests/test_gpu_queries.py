@@ -188,7 +188,7 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
     d = meshes.unit_directions(n, seed=49)
     flip = (np.arange(n) % 3 == 0).astype(np.uint8)
     rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(n)).astype(np.float32)
-    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 2, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.host_chunk": 1 << 21}
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 2, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.host_chunk": 1 << 23}
 
     def run():
         idx, dist = sc.closest_point(q)

@@ -1,0 +1,9 @@
+set -u
+OUT=gpurun_out/r01o
+mkdir -p $OUT
+timeout 300 python tools/scratch/build_only.py > $OUT/build_only.log 2>&1; cat $OUT/build_only.log
+timeout 900 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -5 $OUT/pytest_gpu.log
+timeout 300 python tools/scratch/build_only.py 2240 > $OUT/build_only_10m.log 2>&1; tail -2 $OUT/build_only_10m.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/build_launches.csv python tools/scratch/build_only.py > /dev/null 2>&1
+timeout 600 python bench.py --steps 5 --warmup 3 --no-extra > $OUT/bench_noextra.json 2> $OUT/bench.err; python -c "
+import json;d=json.load(open('$OUT/bench_noextra.json'));print(d['value'],d['ms_per_step'],d['e2e'],d['gpu_launches'])"
