@@ -783,6 +783,17 @@ int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset
         *value = c.traversal_ms;
     }
     else if (k == "build.launches") *value = (double)s->build_launches;
+    else if (k.rfind("query.sil_stats.", 0) == 0 && k.size() == 17 && k[16] >= '0' && k[16] <= '7')
+    { // cone tests, undecided, exact-only codes, warp steps, warp steps with an undecided test, node visits
+        unsigned long long st[8];
+        cudaSetDevice(s->device);
+        cudaDeviceSynchronize();
+        const int rc = read_sil_stats(st, false);
+        if (rc != SNCH_OK) return rc;
+        *value = (double)st[k[16] - '0'];
+        if (reset && k[16] == '7') read_sil_stats(st, true);
+        return SNCH_OK;
+    }
     else
     {
         set_error("snch_scene_counter: unknown counter '" + k + "'");
@@ -813,11 +824,14 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.cone_filter") t.cone_filter = (int)value;
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.sil_kernel") t.sil_kernel = (int)value;
+    else if (k == "query.sil_nodes") t.sil_nodes = (int)value;
+    else if (k == "query.sil_stats") t.sil_stats = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;
     else if (k == "build.refit_kernel") s->opt_refit_kernel = (int)value;
+    else if (k == "build.compact_nodes") s->opt_compact_nodes = (int)value; // takes effect at the next build
     else if (k == "sort.onesweep") set_sort_onesweep((int)value); // process-wide (A/B of the two radix sorts)
     else
     {

@@ -505,6 +505,70 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
     return cone_overlap(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
 }
 
+// The same filter on the 48-bit cone codes of a CNode (snch_math.cuh qcone_*): 1 = overlap, 0 = no overlap, 2 = undecided
+// (the caller fetches the exact cone from the SNode record and runs cone_test on it).  The decoded axis, half-angle and
+// radius are within kQAxisErr / kQAlphaErr / kQRadiusErr * S of the exact ones (checked by the encoder for every cone it
+// does not mark kQExact), so each quantity the filter compares moves by at most that much: the guard band is widened by
+// those bounds and an answer here implies the same answer from cone_test<2> on the exact cone, i.e. the reference's.
+SNCH_DI int cone_test_compact(uint32_t qx, uint32_t qy, uint32_t qa, uint32_t qr, V3 o, V3 lo, V3 hi, float md2)
+{
+    if (qa >= kQExact) return qa == kQInvalid ? 0 : (qa == kQWide ? 1 : 2);
+    if (md2 < FLT_EPSILON) return 1;
+    const float scale = qcone_scale(lo, hi);
+    const QCone q = qcone_decode(qx, qy, qa, qr, scale);
+    const V3 c = V3{(hi.x + lo.x) * 0.5f, (hi.y + lo.y) * 0.5f, (hi.z + lo.z) * 0.5f};
+    const V3 w = c - o;
+    const float l2 = w.x * w.x + w.y * w.y + w.z * w.z;
+    const float rl = rsqrt_approx(l2);
+    const float l = l2 * rl;
+    const float dr = kQRadiusErr * scale;
+    if (!(fabsf(l - q.radius) > __fmaf_rn(4e-6f, q.radius, dr))) return 2; // the reference branches on l > radius (also NaN / l2 == 0)
+    const float t = fabsf(__fmaf_rn(q.axis.x, w.x, __fmaf_rn(q.axis.y, w.y, q.axis.z * w.z))) * rl;
+    float sa, ca;
+    __sincosf(q.half_angle, &sa, &ca);
+    float band = kConeBand + kQAxisErr + kQAlphaErr;
+    float sb, cb;
+    if (l > q.radius)
+    {
+        sb = q.radius * rl;
+        const float dsb = dr * rl; // |sb' - sb|
+        const float cb2 = fmaxf(__fmaf_rn(-sb, sb, 1.0f), 0.0f);
+        if (!(dsb <= 0.005f) || cb2 < 0.02f) return 2;
+        cb = sqrt_approx(cb2);
+        band = __fmaf_rn(dsb * 1.01f, rsqrt_approx(cb2 - 2.0f * dsb), band); // |beta' - beta| <= dsb / min(cos beta, cos beta')
+    }
+    else
+    {
+        const V3 v = V3{w.x * rl, w.y * rl, w.z * rl};
+        const V3 e = hi - c;
+        const float d = __fmaf_rn(e.x, fabsf(v.x), __fmaf_rn(e.y, fabsf(v.y), e.z * fabsf(v.z)));
+        const float s = l - d;
+        const float sband = kConeBand * l;
+        if (s < -sband) return 1; // the reference returns true for s <= 0
+        if (!(s > sband)) return 2;
+        const float sign = copysignf(1.0f, v.z);
+        const float ia = -__frcp_rn(sign + v.z);
+        const float bb = v.x * v.y * ia;
+        const float b1x = __fmaf_rn(sign * v.x * v.x, ia, 1.0f), b1y = sign * bb, b1z = -sign * v.x;
+        const float b2x = bb, b2y = __fmaf_rn(v.y * v.y, ia, sign), b2z = -v.y;
+        const float r1 = __fmaf_rn(e.x, fabsf(b1x), __fmaf_rn(e.y, fabsf(b1y), e.z * fabsf(b1z)));
+        const float r2 = __fmaf_rn(e.x, fabsf(b2x), __fmaf_rn(e.y, fabsf(b2y), e.z * fabsf(b2z)));
+        const float pr2 = __fmaf_rn(r1, r1, r2 * r2);
+        const float rh = rsqrtf(__fmaf_rn(s, s, pr2));
+        sb = sqrtf(pr2) * rh;
+        cb = s * rh;
+    }
+    const float cg = __fmaf_rn(ca, cb, -sa * sb); // cos(alpha + beta)
+    const float sg = __fmaf_rn(sa, cb, ca * sb);  // sin(alpha + beta)
+    if (cg <= -band) return 1;
+    if (cg >= band)
+    {
+        if (t <= sg - band) return 1;
+        if (t >= sg + band) return 0;
+    }
+    return 2;
+}
+
 // Per-lane traversal with DEFERRED leaves.  A leaf costs up to three edge tests (~100 instructions each) and only one lane
 // in ~15 reaches one in a given step: tested inline, that code ran at 2 of 32 lanes and was 42% of all issued
 // instructions (profiles/r01b_*).  Instead a lane parks the leaves it reaches (at the top end of its stack array) and the
@@ -655,7 +719,12 @@ constexpr int kSStack = 12;
 constexpr int kLeafQueue = 128;  // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
 constexpr int kLeafFlushAt = 32;
 constexpr uint32_t kCoopMaxPayload = 1u << 27; // (first_edge << 2 | count) must leave 5 bits for the owner lane
-template <int kFilter>
+//   * kCompact: the walk reads the 64 B CNode (boxes + split + 48-bit cone codes: 2 sectors) instead of the 96 B SNode.
+//     profiles/r01j: the kernel is bound by the L1 data pipe (88% of peak), which serves a divergent warp one 32 B sector per
+//     cycle, and 3 of every ~4 sectors are node records.  The exact cones are fetched only for the tests the codes leave
+//     undecided (cone_test_compact); a leaf child carries its sorted position and its edge payload comes from edge_off[].
+__device__ unsigned long long g_sil_stats[8]; // "query.sil_stats" instrumentation (kStats instantiation only)
+template <int kFilter, bool kCompact, bool kStats>
 __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
@@ -692,7 +761,9 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 const float ox = __shfl_sync(kFull, p.x, owner), oy = __shfl_sync(kFull, p.y, owner), oz = __shfl_sync(kFull, p.z, owner);
                 float ob = __shfl_sync(kFull, best, owner);
                 const bool oflip = __shfl_sync(kFull, (int)flip, owner) != 0;
-                const uint32_t first = (ent >> 2) & 0x01FFFFFFu, cnt = ent & 3u;
+                uint32_t payload = ent & (kCoopMaxPayload - 1u);
+                if (kCompact) payload = mine ? __ldg(sv.edge_off + payload) : 0u; // queue entries carry the sorted leaf position
+                const uint32_t first = payload >> 2, cnt = payload & 3u;
                 const V3 op = V3{ox, oy, oz};
                 float ob2 = ob * ob;
                 bool hit = false;
@@ -761,16 +832,66 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         if (node != kNone)
         {
             float4 a, b, c, d, e, f;
-            ld256(sv.snode + node, a, b);
-            ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
-            ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
-            const NodeBoxes nb = unpack_boxes(a, b, c);
-            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
-            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
-            // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367),
-            // evaluated only for children that can still beat the current best
-            const bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-            const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+            NodeBoxes nb;
+            float m0, m1;
+            uint32_t r0, r1;
+            bool h0, h1;
+            if (kCompact)
+            {
+                ld256(sv.cnode + node, a, b);
+                ld256(reinterpret_cast<const char *>(sv.cnode + node) + 32, c, d);
+                nb = unpack_boxes(a, b, c);
+                m0 = box_mindist2(nb.lo0, nb.hi0, p);
+                m1 = box_mindist2(nb.lo1, nb.hi1, p);
+                const uint32_t sw = __float_as_uint(d.x), q0 = __float_as_uint(d.y), q1 = __float_as_uint(d.z), q2 = __float_as_uint(d.w);
+                const uint32_t split = sw & 0x3FFFFFFFu;
+                r0 = (sw & 0x40000000u) ? (kLeafFlag | split) : split;
+                r1 = (sw & 0x80000000u) ? (kLeafFlag | (split + 1u)) : split + 1u;
+                int t0 = 0, t1 = 0;
+                if (kStats)
+                {
+                    atomicAdd(&g_sil_stats[0], (unsigned long long)((m0 <= best2) + (m1 <= best2)));
+                    atomicAdd(&g_sil_stats[5], 1ull);
+                }
+                if (m0 <= best2) t0 = cone_test_compact(q0 & 0xFFFu, (q0 >> 12) & 0xFFFu, (q0 >> 24) | ((q1 & 0xFu) << 8), (q1 >> 4) & 0xFFFu, p, nb.lo0, nb.hi0, m0);
+                if (m1 <= best2) t1 = cone_test_compact((q1 >> 16) & 0xFFFu, (q1 >> 28) | ((q2 & 0xFFu) << 4), (q2 >> 8) & 0xFFFu, q2 >> 20, p, nb.lo1, nb.hi1, m1);
+                if (kStats)
+                {
+                    atomicAdd(&g_sil_stats[1], (unsigned long long)((t0 == 2) + (t1 == 2)));
+                    const uint32_t qa0 = (q0 >> 24) | ((q1 & 0xFu) << 8), qa1 = (q2 >> 8) & 0xFFFu;
+                    atomicAdd(&g_sil_stats[2], (unsigned long long)((t0 == 2 && qa0 == kQExact) + (t1 == 2 && qa1 == kQExact)));
+                    const unsigned any = __ballot_sync(__activemask(), t0 == 2 || t1 == 2);
+                    if ((threadIdx.x & 31) == __ffs(__activemask()) - 1)
+                    {
+                        atomicAdd(&g_sil_stats[3], 1ull);
+                        if (any) atomicAdd(&g_sil_stats[4], 1ull);
+                    }
+                }
+                if (t0 == 2 || t1 == 2)
+                { // undecided by the codes: the exact cones of this node
+                    ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
+                    ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
+                    if (t0 == 2) t0 = (d.w >= 0.0f) && cone_test<2>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+                    if (t1 == 2) t1 = (f.x >= 0.0f) && cone_test<2>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+                }
+                h0 = t0 != 0;
+                h1 = t1 != 0;
+            }
+            else
+            {
+                ld256(sv.snode + node, a, b);
+                ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
+                ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
+                nb = unpack_boxes(a, b, c);
+                m0 = box_mindist2(nb.lo0, nb.hi0, p);
+                m1 = box_mindist2(nb.lo1, nb.hi1, p);
+                r0 = __float_as_uint(f.z);
+                r1 = __float_as_uint(f.w);
+                // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367),
+                // evaluated only for children that can still beat the current best
+                h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+                h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+            }
             const bool swap = m1 < m0;
             uint32_t next = kNone;
 #pragma unroll
@@ -1165,6 +1286,16 @@ struct TraversalTimer
         }
     }
 };
+int read_sil_stats(unsigned long long out[8], bool reset)
+{
+    SNCH_CUDA(cudaMemcpyFromSymbol(out, g_sil_stats, 64));
+    if (reset)
+    {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        SNCH_CUDA(cudaMemcpyToSymbol(g_sil_stats, z, 64));
+    }
+    return SNCH_OK;
+}
 void QueryCounters::fold()
 {
     if (!pending) return;
@@ -1238,7 +1369,12 @@ static void launch_silhouette_lanes_f(const SceneView &v, const QueryTuning &t, 
                                       const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
 {
     const bool coop = t.sil_kernel != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopMaxPayload;
-    if (coop) k_silhouette_coop<kFilter><<<persistent_grid(k_silhouette_coop<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+    if (coop && kFilter == 2 && t.sil_nodes != 0 && v.cnode && t.sil_stats)
+        k_silhouette_coop<2, true, true><<<persistent_grid(k_silhouette_coop<2, true, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+    else if (coop && kFilter == 2 && t.sil_nodes != 0 && v.cnode)
+        k_silhouette_coop<2, true, false><<<persistent_grid(k_silhouette_coop<2, true, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+    else if (coop)
+        k_silhouette_coop<kFilter, false, false><<<persistent_grid(k_silhouette_coop<kFilter, false, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
     else k_silhouette<kFilter><<<persistent_grid(k_silhouette<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
 }
 static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,

@@ -19,6 +19,10 @@ struct QueryTuning
     int cone_filter = 2;    // silhouette normal-cone test: 0 = the reference's libm chain, 1 = guard-banded sine-space filter on
                             // correctly rounded sqrt/rcp, 2 = the same filter on MUFU approximations (decisions identical)
     int sil_kernel = 1;     // silhouette per-lane kernel: 1 = warp-shared leaf queue + shared-memory stack (v4), 0 = per-lane parks (v3)
+    int sil_nodes = 0;      // v4 kernel walks 1 = the 64 B compact records when the scene was built with "build.compact_nodes" (48-bit cone
+                            // codes, exact cones fetched when undecided), 0 = the 96 B records.  Bit-identical results; measured SLOWER on
+                            // C3 (69.1 vs 54.0 ms): 3.4% of the coded tests are undecided, so 73% of warp steps take the exact detour
+    int sil_stats = 0;      // instrumented instantiation of the compact kernel: counters "query.sil_stats.0..7" (slow; analysis only)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
@@ -72,6 +76,7 @@ struct snch_scene
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0, opt_refit_only = 0;
+    int opt_compact_nodes = 0; // "build.compact_nodes": also emit the 64 B CNode records ("query.sil_nodes" = 1 walks them)
     int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds (v2), 0 = one climbing thread per leaf (v1)
 };
 
@@ -97,6 +102,7 @@ int build_device(snch_scene *s, cudaStream_t stream);
 void resolve_view(snch_scene *s);
 int patch_pointers(snch_scene *s, cudaStream_t stream);
 
+int read_sil_stats(unsigned long long out[8], bool reset);
 // query.cu — n <= 2^32 - 2^20 per launch (the C-ABI splits larger batches); `scratch` has query_scratch_bytes(n) bytes
 uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t);
 int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,

@@ -57,6 +57,30 @@ def test_silhouette_full_size(big, meshes):
     check_silhouette(bnd.cpu().numpy()[sel], orc.silhouette(q[sel], r_max=rmax.cpu().numpy()[sel], nthreads=8))
 
 
+def test_silhouette_compact_records_full_size(big, meshes):
+    """"query.sil_nodes": walking the 64 B compact records (48-bit cone codes + exact fallback) gives bit-identical distances
+    to walking the 96 B records, bounded and unbounded, on the C3 mesh.  (Opt-in: measured slower)"""
+    import torch
+    sc, orc, q, d, qd, dd = big
+    _, dcp = sc.closest_point(qd)
+    rmax = dcp * torch.from_numpy(meshes.star_radius_scale(NQ)).cuda()
+    try:
+        sc.set_option("build.compact_nodes", 1).build_bvh()  # re-lays the arena with the optional CNode array
+        sc.set_option("query.sil_nodes", 0)
+        full_b, full_u = sc.closest_silhouette(qd, r_max=rmax), sc.closest_silhouette(qd)
+        sc.set_option("query.sil_nodes", 1)
+        comp_b, comp_u = sc.closest_silhouette(qd, r_max=rmax), sc.closest_silhouette(qd)
+        flip = (torch.arange(NQ, device="cuda") % 2).to(torch.uint8)
+        comp_f = sc.closest_silhouette(qd, flip=flip)
+        sc.set_option("query.sil_nodes", 0)
+        full_f = sc.closest_silhouette(qd, flip=flip)
+    finally:
+        sc.set_option("query.sil_nodes", 0).set_option("build.compact_nodes", 0).build_bvh()
+    torch.cuda.synchronize()
+    for a, b in ((full_b, comp_b), (full_u, comp_u), (full_f, comp_f)):
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), f"{int((a.view(torch.int32) != b.view(torch.int32)).sum())} distances differ"
+
+
 def test_rays_full_size(big):
     import torch
     sc, orc, q, d, qd, dd = big
