@@ -158,7 +158,7 @@ def cpu_silhouette_baseline(v, f, q, rmax, target_s=12.0, max_n=1 << 21):
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     import snch_lbvh_b200 as pkg
     from oracle import OracleScene
     m = pkg.meshes
@@ -181,7 +181,7 @@ def run_reference_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of the workload"},
             "cpu_baseline": info, "e2e": {"value": val, "unit": "M queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def other_config(cfg, pkg, m, dev, stream):
@@ -228,6 +228,15 @@ def other_config(cfg, pkg, m, dev, stream):
 
 # ----------------------------------------------------------------------------------------------------------------
 def main():
+    """Everything but the result line is kept off stdout (NCCL prints its version banner there, the reference prints its
+    collision notice): fd 1 points at stderr until the line is ready."""
+    with quiet_stdout():
+        line = _run()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -240,8 +249,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        run_reference_arm(args)
-        return
+        return run_reference_arm(args)
 
     import torch
     import snch_lbvh_b200 as pkg
@@ -352,7 +360,7 @@ def main():
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
-        return
+        return None
 
     # ---- rank 0: roofline, secondary numbers, CPU baseline ------------------------------------------------------------
     ms_per_step = total_ms_max / args.steps
@@ -454,14 +462,16 @@ def main():
             "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": n, "triangles": stats["num_objects"],
                        "parallelism": f"replicated tree, query batch sharded x{world}",
                        "l2": "inputs larger than L2 (268 MB of queries + 192 MB of tree records + 201 MB of ordering buffers per step vs 126 MB L2); no explicit flush",
-                       "step": "Morton ordering of the batch (bounds, keys, 3-pass radix sort) + persistent traversal kernel"},
+                       "step": "Morton ordering of the batch (bounds, keys, 3-pass onesweep radix sort) + persistent traversal kernel",
+                       "e2e": "snch_closest_silhouette_batch on pinned HOST buffers: H2D, kernels and D2H inside the call, pipelined in chunks "
+                              "of query.host_chunk = 8388608 queries over a copy-in stream, two compute streams and a copy-out stream"},
             "e2e": {"value": world * n * e2e_steps / (e2e_ms_max * 1e-3) / 1e6, "unit": "M queries/s", "h2d_bytes_per_step": n * 16,
                     "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_ms_max / e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "extra": extra}
-    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":
