@@ -283,6 +283,9 @@ def _run():
     torch.cuda.synchronize()
     replicate_ms = (time.perf_counter() - t1) * 1e3
     stats = scene.stats()
+    for kv in filter(None, os.environ.get("SNCH_OPTIONS", "").replace(",", " ").split()):  # diagnostic runs only (tools/gpu_exp.sh)
+        k, val = kv.split("=")
+        scene.set_option(k, int(val))
 
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):

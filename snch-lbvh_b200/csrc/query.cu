@@ -70,12 +70,64 @@ struct Feeder
 {
     uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
     bool exhausted;     // the global counter ran past n
+    uint32_t hop = 0;   // region feed: regions this warp has seen run dry (it draws from region (home + hop) % regions)
 };
+// Region feed ("query.feed" = 1 per CTA, 2 per SM): the ordered batch is cut into `regions` contiguous ranges of `per` slots,
+// each with its own counter; a warp draws its chunks from its home region and moves on to the next region only when one
+// has run dry (counters only grow, so a dry region stays dry and `hop` never goes back).  Warps that share an L1 thus
+// work on neighbouring queries and re-read each other's node records.
+struct RegionFeed
+{
+    unsigned long long *counters; // regions x u64, zeroed per batch (scratch + kScratchCounters)
+    uint32_t regions, per, home;
+};
+constexpr uint32_t kMaxRegions = 2048;
+constexpr uint64_t kScratchCounters = 256, kScratchHeader = kScratchCounters + kMaxRegions * 8; // work counter + query box | region counters
+SNCH_DI uint32_t smid()
+{
+    uint32_t r;
+    asm("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+SNCH_DI void region_draw(Feeder &f, const RegionFeed &rf, int lane, uint32_t n)
+{
+    unsigned long long base = ~0ull;
+    uint32_t hop = f.hop;
+    if (lane == 0)
+    {
+        for (; hop < rf.regions; ++hop)
+        {
+            const uint32_t r = (rf.home + hop) % rf.regions;
+            const unsigned long long lo = (unsigned long long)r * rf.per;
+            if (lo >= n) continue;
+            const unsigned long long len = min((unsigned long long)rf.per, (unsigned long long)n - lo);
+            if (*reinterpret_cast<volatile unsigned long long *>(rf.counters + r) >= len) continue;
+            const unsigned long long off = atomicAdd(rf.counters + r, (unsigned long long)kChunk);
+            if (off < len)
+            {
+                base = lo + off;
+                f.end = (uint32_t)min(lo + len, base + kChunk);
+                break;
+            }
+        }
+    }
+    base = __shfl_sync(kFull, base, 0);
+    f.hop = __shfl_sync(kFull, hop, 0);
+    f.end = __shfl_sync(kFull, f.end, 0);
+    if (base == ~0ull)
+    {
+        f.exhausted = true;
+        f.end = f.next;
+    }
+    else f.next = (uint32_t)base;
+}
 // Gives every idle lane (bit set in `idle`) the next query slot of the warp's chunk; draws a new chunk when needed.
 // Returns the slot for this lane or kNone.  Warp-convergent call.
-SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter)
+SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter,
+                             const RegionFeed *rf = nullptr)
 {
-    if (f.next == f.end && !f.exhausted)
+    if (f.next == f.end && !f.exhausted && rf && rf->regions) region_draw(f, *rf, lane, n);
+    else if (f.next == f.end && !f.exhausted)
     {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)kChunk);
@@ -438,6 +490,17 @@ SNCH_DI float sqrt_approx(float x)
 // MUFU approximations (rel. error <= 2^-22, i.e. <= 5e-7 on every quantity compared against the 2e-5 band); the two
 // exact-value branch decisions of the reference (l > radius, s <= 0) and the ill-conditioned corner (view cone within
 // ~6 degrees of a half space, where cos(beta) amplifies the error of sin(beta)) are handed to the exact chain.
+//    3: mode 2 with the exact chain kept OUT OF LINE (one copy per kernel instead of one per hand-off site: the walk's hot loop
+//       shrinks by ~2000 instructions, profiles/r01j showed 0.74 "no instruction" stall cycles per issue).
+__device__ __noinline__ bool cone_overlap_ool(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
+{
+    return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+}
+template <int kMode> SNCH_DI bool cone_exact(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
+{
+    if (kMode == 3) return cone_overlap_ool(axis, half_angle, radius, o, lo, hi, md2);
+    return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+}
 template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
 {
     if (kMode == 0) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
@@ -455,7 +518,7 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
         const float l2 = w.x * w.x + w.y * w.y + w.z * w.z;
         rl = rsqrt_approx(l2);
         l = l2 * rl;
-        if (!(fabsf(l - radius) > 4e-6f * radius)) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2); // also NaN / l2 == 0
+        if (!(fabsf(l - radius) > 4e-6f * radius)) return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2); // also NaN / l2 == 0
     }
     const float t = fabsf(__fmaf_rn(axis.x, w.x, __fmaf_rn(axis.y, w.y, axis.z * w.z))) * rl;
     float sa, ca;
@@ -468,7 +531,7 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
         if (kMode == 1) cb = sqrtf(cb2);
         else
         {
-            if (cb2 < 0.01f) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+            if (cb2 < 0.01f) return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2);
             cb = sqrt_approx(cb2);
         }
     }
@@ -480,7 +543,7 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
         const float s = l - d;
         const float sband = kConeBand * l;
         if (s < -sband) return true; // the reference returns true for s <= 0
-        if (!(s > sband)) return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
+        if (!(s > sband)) return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2);
         // project_to_plane(v, e)                                                        cone.cuh:34-42, 58-66
         const float sign = copysignf(1.0f, v.z);
         const float ia = -__frcp_rn(sign + v.z);
@@ -502,7 +565,7 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
         if (t <= sg - kConeBand) return true;
         if (t >= sg + kConeBand) return false;
     }
-    return cone_overlap(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
+    return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
 }
 
 // The same filter on the 48-bit cone codes of a CNode (snch_math.cuh qcone_*): 1 = overlap, 0 = no overlap, 2 = undecided
@@ -727,7 +790,8 @@ __device__ unsigned long long g_sil_stats[8]; // "query.sil_stats" instrumentati
 template <int kFilter, bool kCompact, bool kStats>
 __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter,
+                      int feed_mode, uint32_t feed_regions, uint32_t feed_per)
 {
     __shared__ StackEntry s_stk[kSStack][kQueryThreads];
     __shared__ uint32_t s_queue[kQueryThreads / 32][kLeafQueue];
@@ -736,6 +800,8 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *queue = s_queue[wid];
     Feeder fd{0u, 0u, false};
+    const RegionFeed rf{counter + kScratchCounters / 8, feed_mode ? feed_regions : 0u, feed_per,
+                        feed_mode == 1 ? blockIdx.x % (feed_regions ? feed_regions : 1u) : smid() % (feed_regions ? feed_regions : 1u)};
     StackEntry lstk[kStackDepth - kSStack];
     int sp = 0;
     V3 p = V3{0.f, 0.f, 0.f};
@@ -813,7 +879,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         const unsigned idle = __ballot_sync(kFull, !busy);
         if (idle)
         {
-            const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter);
+            const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter, &rf);
             if (s != kNone)
             {
                 slot = perm ? __ldg(perm + s) : s;
@@ -1310,7 +1376,7 @@ static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kQueryThrea
 // bytes of device scratch one batch of n queries needs (ordering buffers + sort counters + the work counter)
 uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
 {
-    uint64_t b = 256; // work counter + query box
+    uint64_t b = kScratchHeader; // work counter + query box + region counters
     if (t.sort_min_n > 0 && n >= (uint64_t)t.sort_min_n) b += 4 * align_up(n * 4, 256) + align_up(sort_scratch_elems(n) * 4, 256);
     return b;
 }
@@ -1320,17 +1386,17 @@ static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int
                          unsigned char *scratch, cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out,
                          QueryCounters *qc)
 {
-    SNCH_CUDA(cudaMemsetAsync(scratch, 0, 64, st));
+    SNCH_CUDA(cudaMemsetAsync(scratch, 0, t.feed ? kScratchHeader : 64, st));
     *counter_out = reinterpret_cast<unsigned long long *>(scratch);
     *perm_out = nullptr;
     if (!(order && t.sort_min_n > 0 && n >= (uint32_t)t.sort_min_n)) return SNCH_OK;
     int *box = reinterpret_cast<int *>(scratch + 64);
     const uint64_t a = align_up((uint64_t)n * 4, 256);
-    uint32_t *keys = reinterpret_cast<uint32_t *>(scratch + 256);
-    uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + 256 + a);
-    uint32_t *ktmp = reinterpret_cast<uint32_t *>(scratch + 256 + 2 * a);
-    uint32_t *vtmp = reinterpret_cast<uint32_t *>(scratch + 256 + 3 * a);
-    uint32_t *sscr = reinterpret_cast<uint32_t *>(scratch + 256 + 4 * a);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(scratch + kScratchHeader);
+    uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + a);
+    uint32_t *ktmp = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 2 * a);
+    uint32_t *vtmp = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 3 * a);
+    uint32_t *sscr = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 4 * a);
     const unsigned g = (n + 255) / 256;
     k_query_box_init<<<1, 32, 0, st>>>(box);
     k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, n, box);
@@ -1369,18 +1435,31 @@ static void launch_silhouette_lanes_f(const SceneView &v, const QueryTuning &t, 
                                       const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
 {
     const bool coop = t.sil_kernel != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopMaxPayload;
+    // region feed: per CTA (1) or per SM (2); `per` is a whole number of chunks so regions never share a chunk
+    const unsigned grid = persistent_grid(k_silhouette_coop<kFilter, false, false>, t, n);
+    int sms = 1;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    uint32_t regions = t.feed == 1 ? grid : (t.feed == 2 ? (uint32_t)sms : 0u);
+    if (regions > kMaxRegions) regions = kMaxRegions;
+    const int fm = regions ? t.feed : 0;
+    const uint32_t per = regions ? (uint32_t)((((uint64_t)n + regions - 1) / regions + kChunk - 1) / kChunk * kChunk) : 0u;
     if (coop && kFilter == 2 && t.sil_nodes != 0 && v.cnode && t.sil_stats)
-        k_silhouette_coop<2, true, true><<<persistent_grid(k_silhouette_coop<2, true, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+        k_silhouette_coop<2, true, true><<<persistent_grid(k_silhouette_coop<2, true, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
     else if (coop && kFilter == 2 && t.sil_nodes != 0 && v.cnode)
-        k_silhouette_coop<2, true, false><<<persistent_grid(k_silhouette_coop<2, true, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+        k_silhouette_coop<2, true, false><<<persistent_grid(k_silhouette_coop<2, true, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
     else if (coop)
-        k_silhouette_coop<kFilter, false, false><<<persistent_grid(k_silhouette_coop<kFilter, false, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+        k_silhouette_coop<kFilter, false, false><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
     else k_silhouette<kFilter><<<persistent_grid(k_silhouette<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
 }
 static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,
                                     const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
 {
-    if (t.cone_filter >= 2) launch_silhouette_lanes_f<2>(v, t, q, flip, rmax, perm, n, dist, counter, st);
+    if (t.cone_filter >= 3) launch_silhouette_lanes_f<3>(v, t, q, flip, rmax, perm, n, dist, counter, st);
+    else if (t.cone_filter == 2) launch_silhouette_lanes_f<2>(v, t, q, flip, rmax, perm, n, dist, counter, st);
     else if (t.cone_filter == 1) launch_silhouette_lanes_f<1>(v, t, q, flip, rmax, perm, n, dist, counter, st);
     else launch_silhouette_lanes_f<0>(v, t, q, flip, rmax, perm, n, dist, counter, st);
 }
