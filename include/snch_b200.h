@@ -212,6 +212,42 @@ int snch_lbvh_build(int dim, uint32_t n, const void *leaf_aabbs, const void *lea
                     snch_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * 2-D scenes (polylines).  Replaces lbvh::scene<2> (scene.cuh:287-703): scene<2>::scene(vFirst,vLast,iFirst,iLast) :621-627,
+ * compute_silhouettes() :629-656 (one silhouette_vertex {previous, self, next} per vertex), build_bvh() :658-681 (a vertex is
+ * owned by the first segment in input order that touches it) -> bvh::construct(), and the per-thread calls a user kernel makes
+ * on its bvh_device<float, 2, line_segment>:
+ *   query_device(bvh, nearest(p), scene<2>::distance_calculator())                                       query.cuh:238-318
+ *   query_device(bvh, nearest_silhouette(p, flip), scene<2>::silhouette_distance_calculator())           query.cuh:325-423
+ *   query_device(bvh, ray_intersect<TestOnly>(ray, max_dist), scene<2>::intersect_test())                query.cuh:79-169
+ *   sample_object_in_sphere(bvh, sphere_intersect(circle), scene<2>::intersect_sphere(), measurement_getter(), green_weight(), u)
+ *   + sample_on_object(bvh, idx, scene<2>::sample_on_object(), u1, .)                                    sample.cuh:7-92
+ * xy: n_verts x 2 floats, seg: n_segs x 2 vertex indices (HOST pointers, copied).  Query / result pointers are all DEVICE or
+ * all HOST pointers (staged inside the call, which then synchronises `stream`).  Sentinels as in 3-D.
+ * snch_scene2_device_repr fills the reference-layout view: nodes 16 B, aabbs 16 B {upper xy, lower xy}, cones 16 B {axis xy,
+ * half_angle, radius}, objects 32 B scene<2>::line_segment, silhouettes 32 B scene<2>::silhouette_vertex, vertices float2.
+ * snch_scene2_export kinds: NODES, AABBS (4 f32), CONES (4 f32), MORTON_SORTED, SORTED_INDEX, EDGES (= silhouette_vertex::indices,
+ * n_verts x 4 i32), TRI_OWNED (= line_segment::silhouette_indices, n_segs x 2 i32).
+ * snch_hit for a 2-D ray: t, u = segment parameter s, v = 0, prim.   Circles: x, y, radius.  rnd2: {u (branch), u1 (point)}.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct snch_scene2 snch_scene2;
+int snch_scene2_create(const float *xy, uint32_t n_verts, const int32_t *seg, uint32_t n_segs, int device, snch_scene2 **out);
+int snch_scene2_destroy(snch_scene2 *s);
+int snch_scene2_compute_silhouettes(snch_scene2 *s);
+int snch_scene2_build(snch_scene2 *s, snch_stream stream);
+int snch_scene2_stats(const snch_scene2 *s, snch_build_stats *out);
+int snch_scene2_device_repr(const snch_scene2 *s, snch_bvh_device_pod *out);
+int snch_scene2_export(const snch_scene2 *s, int kind, void *host_dst, uint64_t bytes);
+int snch_scene2_set_option(snch_scene2 *s, const char *name, int64_t value); /* "query.sort_min_n", "query.sort_bits", "query.sort_rays", "query.blocks_per_sm" */
+int snch_closest_point_batch2(const snch_scene2 *s, const float *points_xy, uint64_t n, uint32_t *out_index, float *out_distance,
+                              snch_stream stream);
+int snch_closest_silhouette_batch2(const snch_scene2 *s, const float *points_xy, const uint8_t *flip, const float *r_max, uint64_t n,
+                                   float *out_distance, snch_stream stream);
+int snch_intersect_batch2(const snch_scene2 *s, const float *origins_xy, const float *dirs_xy, const float *t_max, uint64_t n,
+                          snch_hit *out_hits, uint8_t *out_found, int any_hit, snch_stream stream);
+int snch_sample_in_sphere_batch2(const snch_scene2 *s, const float *circles_xyr, const float *rnd2, uint64_t n, int32_t *out_index,
+                                 float *out_pdf, float *out_point_xy, snch_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Replication (multi-GPU): the built scene lives in ONE pointer-free arena.  Rank 0 exposes it, the caller
  * moves the bytes (ncclBroadcast / cudaMemcpyPeer / torch.distributed.broadcast) and every other rank adopts its copy.
  * ------------------------------------------------------------------------------------------------------------- */

@@ -244,6 +244,23 @@ def _ref_lib(kind):
     L.ref3_ray.restype = C.c_double
     L.ref3_sample.argtypes = [vp, _f32p, _f32p, C.c_long, _i32p, _f32p, C.c_int]
     L.ref3_sample.restype = C.c_double
+    if hasattr(L, "ref2_create"):  # 2-D wrappers (older prebuilt libraries lack them)
+        L.ref2_create.argtypes = [_f32p, C.c_int, _i32p, C.c_int]
+        L.ref2_create.restype = vp
+        L.ref2_destroy.argtypes = [vp]
+        for name in ("ref2_num_objects", "ref2_num_nodes"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = C.c_int
+        L.ref2_export_tree.argtypes = [vp, _u32p, _f32p, _f32p]
+        L.ref2_export_adjacency.argtypes = [vp, _i32p, _i32p]
+        L.ref2_closest.argtypes = [vp, _f32p, C.c_long, _u32p, _f32p, C.c_int]
+        L.ref2_closest.restype = C.c_double
+        L.ref2_silhouette.argtypes = [vp, _f32p, C.c_long, C.c_int, _f32p, C.c_int]
+        L.ref2_silhouette.restype = C.c_double
+        L.ref2_ray.argtypes = [vp, _f32p, _f32p, _f32p, C.c_long, _i32p, _f32p, _f32p, _u32p, C.c_int]
+        L.ref2_ray.restype = C.c_double
+        L.ref2_sample.argtypes = [vp, _f32p, _f32p, C.c_long, _i32p, _f32p, C.c_int]
+        L.ref2_sample.restype = C.c_double
     _ref_libs[kind] = L
     return L
 
@@ -337,6 +354,79 @@ class RefScene:
 
 
 _fcpw_lib = None
+
+
+class RefScene2:
+    """lbvh::scene<2> of the UNMODIFIED reference headers (polylines: segments / silhouette vertices), kind 'cpu' or 'cuda'."""
+
+    def __init__(self, verts, segs, kind="cpu"):
+        self.kind = kind
+        self.L = _ref_lib(kind)
+        if not hasattr(self.L, "ref2_create"):
+            raise RuntimeError("oracle/_ref was built without the 2-D wrappers: rebuild it (make -C oracle ref)")
+        self.verts = _f32(verts).reshape(-1, 2)
+        self.segs = _i32(segs).reshape(-1, 2)
+        self.h = self.L.ref2_create(self.verts, len(self.verts), self.segs, len(self.segs))
+        self.n = len(self.segs)
+        self.num_nodes = self.L.ref2_num_nodes(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.ref2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tree(self):
+        nn = self.num_nodes
+        nodes = np.zeros((nn, 4), np.uint32)
+        aabbs = np.zeros((nn, 4), np.float32)
+        cones = np.zeros((nn, 4), np.float32)
+        self.L.ref2_export_tree(self.h, nodes, aabbs, cones)
+        return nodes, aabbs, cones
+
+    def adjacency(self):
+        v4 = np.zeros((len(self.verts), 4), np.int32)
+        owned = np.zeros((self.n, 2), np.int32)
+        self.L.ref2_export_adjacency(self.h, v4, owned)
+        return v4, owned
+
+    def closest(self, q, nthreads=1):
+        q = _f32(q).reshape(-1, 2)
+        idx = np.zeros(len(q), np.uint32)
+        dist = np.zeros(len(q), np.float32)
+        self.L.ref2_closest(self.h, q, len(q), idx, dist, nthreads)
+        return idx, dist
+
+    def silhouette(self, q, flip=False, nthreads=1):
+        q = _f32(q).reshape(-1, 2)
+        dist = np.zeros(len(q), np.float32)
+        self.L.ref2_silhouette(self.h, q, len(q), int(flip), dist, nthreads)
+        return dist
+
+    def ray(self, org, dirs, tmax=None, nthreads=1):
+        org = _f32(org).reshape(-1, 2)
+        dirs = _f32(dirs).reshape(-1, 2)
+        n = len(org)
+        tm = np.full(n, np.inf, np.float32) if tmax is None else _f32(np.broadcast_to(tmax, (n,)))
+        found = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        s = np.zeros(n, np.float32)
+        prim = np.zeros(n, np.uint32)
+        self.L.ref2_ray(self.h, org, dirs, tm, n, found, t, s, prim, nthreads)
+        return found, t, s, prim
+
+    def sample(self, sph, u, nthreads=1):
+        sph = _f32(sph).reshape(-1, 3)
+        u = _f32(u).reshape(-1)
+        idx = np.zeros(len(sph), np.int32)
+        pdf = np.zeros(len(sph), np.float32)
+        self.L.ref2_sample(self.h, sph, u, len(sph), idx, pdf, nthreads)
+        return idx, pdf
 
 
 def _fcpw():

@@ -358,3 +358,218 @@ extern "C"
 #endif
     }
 }
+
+/* =====================================================================================================================
+ * 2-D: lbvh::scene<2> (line segments / silhouette vertices), scene.cuh:287-703.  Same conventions as ref3_*.
+ * ===================================================================================================================== */
+using scene2 = lbvh::scene<2>;
+using seg_t = scene2::line_segment;
+using refdev2_t = lbvh::bvh_device<float, 2, seg_t>;
+struct ref2
+{
+    scene2 *sc;
+};
+#if REF_IS_CUDA
+__global__ void k2_closest(refdev2_t bvh, const float2 *q, long n, unsigned *idx, float *dist)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto r = lbvh::query_device(bvh, lbvh::nearest(q[i]), scene2::distance_calculator());
+    idx[i] = r.first;
+    dist[i] = r.second;
+}
+__global__ void k2_silhouette(refdev2_t bvh, const float2 *q, long n, bool flip, float *dist)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dist[i] = lbvh::query_device(bvh, lbvh::nearest_silhouette(q[i], flip), scene2::silhouette_distance_calculator());
+}
+__global__ void k2_ray(refdev2_t bvh, const float2 *o, const float2 *d, const float *tmax, long n, int *found, float *t, float *s,
+                       unsigned *prim)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lbvh::ray<float, 2> r(o[i], d[i]);
+    auto h = lbvh::query_device(bvh, lbvh::ray_intersect(r, tmax[i]), scene2::intersect_test());
+    found[i] = thrust::get<0>(h) ? 1 : 0;
+    t[i] = thrust::get<1>(h);
+    s[i] = thrust::get<0>(h) ? thrust::get<2>(h) : 0.f;
+    prim[i] = thrust::get<3>(h);
+}
+__global__ void k2_sample(refdev2_t bvh, const float3 *sph, const float *u, long n, int *idx, float *pdf)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lbvh::sphere<float, 2> s(make_float2(sph[i].x, sph[i].y), sph[i].z);
+    auto r = lbvh::sample_object_in_sphere(bvh, lbvh::sphere_intersect(s), scene2::intersect_sphere(), scene2::measurement_getter(),
+                                           scene2::green_weight(), u[i]);
+    idx[i] = r.first;
+    pdf[i] = r.first >= 0 ? r.second : 0.0f;
+}
+#endif
+
+extern "C"
+{
+    ref2 *ref2_create(const float *xy, int nV, const int *seg, int nS)
+    {
+        std::vector<float2> v(nV);
+        std::vector<int2> idx(nS);
+        for (int i = 0; i < nV; ++i) v[i] = make_float2(xy[2 * i], xy[2 * i + 1]);
+        for (int i = 0; i < nS; ++i) idx[i] = make_int2(seg[2 * i], seg[2 * i + 1]);
+        ref2 *r = new ref2();
+        r->sc = new scene2(v.begin(), v.end(), idx.begin(), idx.end());
+        r->sc->compute_silhouettes();
+        r->sc->build_bvh();
+#if REF_IS_CUDA
+        cudaDeviceSynchronize();
+#endif
+        return r;
+    }
+    void ref2_destroy(ref2 *r)
+    {
+        delete r->sc;
+        delete r;
+    }
+    int ref2_num_objects(ref2 *r) { return (int)r->sc->bvh_dev.num_objects; }
+    int ref2_num_nodes(ref2 *r) { return (int)r->sc->bvh_dev.num_nodes; }
+    /* nodes: 4 x u32 {parent,left,right,object}; aabbs: 4 floats {upper xy, lower xy}; cones: 4 floats {axis xy, half_angle, radius} */
+    void ref2_export_tree(ref2 *r, unsigned *nodes, float *aabbs, float *cones)
+    {
+        const refdev2_t &d = r->sc->bvh_dev;
+        static_assert(sizeof(lbvh::aabb<float, 2>) == 16, "");
+        static_assert(sizeof(lbvh::cone<float, 2>) == 16, "");
+        if (nodes) copy_out(nodes, d.nodes, sizeof(lbvh::detail::node) * d.num_nodes);
+        if (aabbs) copy_out(aabbs, d.aabbs, sizeof(lbvh::aabb<float, 2>) * d.num_nodes);
+        if (cones) copy_out(cones, d.cones, sizeof(lbvh::cone<float, 2>) * d.num_nodes);
+    }
+    /* silhouette_vertex::indices (int4 per vertex) and the owned-vertex pair of every segment (scene.cuh:634-681) */
+    void ref2_export_adjacency(ref2 *r, int *vert4, int *seg_owned2)
+    {
+        scene2 *s = r->sc;
+        for (size_t v = 0; v < s->silhouettes_h.size(); ++v)
+        {
+            int4 id = static_cast<const scene2::silhouette_vertex &>(s->silhouettes_h[v]).indices;
+            vert4[4 * v + 0] = id.x;
+            vert4[4 * v + 1] = id.y;
+            vert4[4 * v + 2] = id.z;
+            vert4[4 * v + 3] = id.w;
+        }
+        for (size_t i = 0; i < s->lines.size(); ++i)
+        {
+            int2 oi = s->lines[i].silhouette_indices;
+            seg_owned2[2 * i + 0] = oi.x;
+            seg_owned2[2 * i + 1] = oi.y;
+        }
+    }
+    double ref2_closest(ref2 *r, const float *q, long n, unsigned *idx, float *dist, int nthreads)
+    {
+        const refdev2_t bvh = r->sc->bvh_dev;
+#if REF_IS_CUDA
+        dbuf<float2> dq((const float2 *)q, n);
+        dbuf<unsigned> di(n);
+        dbuf<float> dd(n);
+        cudaDeviceSynchronize();
+        evtimer t;
+        k2_closest<<<(unsigned)((n + 255) / 256), 256>>>(bvh, dq.p, n, di.p, dd.p);
+        double ms = t.stop();
+        di.to(idx);
+        dd.to(dist);
+        return ms;
+#else
+        double t0 = now_ms();
+        par_for(n, nthreads,
+                [=](long i)
+                {
+                    auto res = lbvh::query_device(bvh, lbvh::nearest(make_float2(q[2 * i], q[2 * i + 1])), scene2::distance_calculator());
+                    idx[i] = res.first;
+                    dist[i] = res.second;
+                });
+        return now_ms() - t0;
+#endif
+    }
+    double ref2_silhouette(ref2 *r, const float *q, long n, int flip, float *dist, int nthreads)
+    {
+        const refdev2_t bvh = r->sc->bvh_dev;
+#if REF_IS_CUDA
+        dbuf<float2> dq((const float2 *)q, n);
+        dbuf<float> dd(n);
+        cudaDeviceSynchronize();
+        evtimer t;
+        k2_silhouette<<<(unsigned)((n + 255) / 256), 256>>>(bvh, dq.p, n, flip != 0, dd.p);
+        double ms = t.stop();
+        dd.to(dist);
+        return ms;
+#else
+        double t0 = now_ms();
+        par_for(n, nthreads,
+                [=](long i)
+                {
+                    dist[i] = lbvh::query_device(bvh, lbvh::nearest_silhouette(make_float2(q[2 * i], q[2 * i + 1]), flip != 0),
+                                                 scene2::silhouette_distance_calculator());
+                });
+        return now_ms() - t0;
+#endif
+    }
+    double ref2_ray(ref2 *r, const float *o, const float *d, const float *tmax, long n, int *found, float *t, float *s, unsigned *prim,
+                    int nthreads)
+    {
+        const refdev2_t bvh = r->sc->bvh_dev;
+#if REF_IS_CUDA
+        dbuf<float2> dorg((const float2 *)o, n), ddir((const float2 *)d, n);
+        dbuf<float> dtm(tmax, n), dt(n), ds(n);
+        dbuf<int> df(n);
+        dbuf<unsigned> dp(n);
+        cudaDeviceSynchronize();
+        evtimer tm;
+        k2_ray<<<(unsigned)((n + 255) / 256), 256>>>(bvh, dorg.p, ddir.p, dtm.p, n, df.p, dt.p, ds.p, dp.p);
+        double ms = tm.stop();
+        df.to(found);
+        dt.to(t);
+        ds.to(s);
+        dp.to(prim);
+        return ms;
+#else
+        double t0 = now_ms();
+        par_for(n, nthreads,
+                [=](long i)
+                {
+                    lbvh::ray<float, 2> ry(make_float2(o[2 * i], o[2 * i + 1]), make_float2(d[2 * i], d[2 * i + 1]));
+                    auto h = lbvh::query_device(bvh, lbvh::ray_intersect(ry, tmax[i]), scene2::intersect_test());
+                    found[i] = thrust::get<0>(h) ? 1 : 0;
+                    t[i] = thrust::get<1>(h);
+                    s[i] = thrust::get<0>(h) ? thrust::get<2>(h) : 0.f;
+                    prim[i] = thrust::get<3>(h);
+                });
+        return now_ms() - t0;
+#endif
+    }
+    /* sph: x,y,radius per query.  pdf is reported as 0 on a miss (Q19) */
+    double ref2_sample(ref2 *r, const float *sph, const float *u, long n, int *idx, float *pdf, int nthreads)
+    {
+        const refdev2_t bvh = r->sc->bvh_dev;
+#if REF_IS_CUDA
+        dbuf<float3> ds((const float3 *)sph, n);
+        dbuf<float> du(u, n), dp(n);
+        dbuf<int> di(n);
+        cudaDeviceSynchronize();
+        evtimer tm;
+        k2_sample<<<(unsigned)((n + 255) / 256), 256>>>(bvh, ds.p, du.p, n, di.p, dp.p);
+        double ms = tm.stop();
+        di.to(idx);
+        dp.to(pdf);
+        return ms;
+#else
+        double t0 = now_ms();
+        par_for(n, nthreads,
+                [=](long i)
+                {
+                    lbvh::sphere<float, 2> s(make_float2(sph[3 * i], sph[3 * i + 1]), sph[3 * i + 2]);
+                    auto res = lbvh::sample_object_in_sphere(bvh, lbvh::sphere_intersect(s), scene2::intersect_sphere(),
+                                                             scene2::measurement_getter(), scene2::green_weight(), u[i]);
+                    idx[i] = res.first;
+                    pdf[i] = res.first >= 0 ? res.second : 0.0f;
+                });
+        return now_ms() - t0;
+#endif
+    }
+}

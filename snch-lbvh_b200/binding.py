@@ -20,6 +20,9 @@ ABI_SYMBOLS = [
     "snch_closest_silhouette_batch", "snch_intersect_batch", "snch_sample_in_sphere_batch", "snch_scene_arena",
     "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter", "snch_lbvh_build", "snch_scene_update_vertices",
     "snch_wost_step_batch", "snch_scene_save", "snch_scene_load",
+    "snch_scene2_create", "snch_scene2_destroy", "snch_scene2_compute_silhouettes", "snch_scene2_build", "snch_scene2_stats",
+    "snch_scene2_device_repr", "snch_scene2_export", "snch_scene2_set_option", "snch_closest_point_batch2",
+    "snch_closest_silhouette_batch2", "snch_intersect_batch2", "snch_sample_in_sphere_batch2",
 ]
 
 
@@ -111,6 +114,18 @@ def lib():
     L.snch_scene_save.argtypes = [vp, C.c_char_p]
     L.snch_scene_load.argtypes = [C.c_char_p, C.c_int, vp, C.POINTER(vp)]
     L.snch_lbvh_build.argtypes = [C.c_int, u32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]
+    L.snch_scene2_create.argtypes = [vp, u32, vp, u32, C.c_int, C.POINTER(vp)]
+    L.snch_scene2_destroy.argtypes = [vp]
+    L.snch_scene2_compute_silhouettes.argtypes = [vp]
+    L.snch_scene2_build.argtypes = [vp, vp]
+    L.snch_scene2_stats.argtypes = [vp, C.POINTER(BuildStats)]
+    L.snch_scene2_device_repr.argtypes = [vp, C.POINTER(BvhDevicePod)]
+    L.snch_scene2_export.argtypes = [vp, C.c_int, vp, u64]
+    L.snch_scene2_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.snch_closest_point_batch2.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.snch_closest_silhouette_batch2.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    L.snch_intersect_batch2.argtypes = [vp, vp, vp, vp, u64, vp, vp, C.c_int, vp]
+    L.snch_sample_in_sphere_batch2.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     for name in ABI_SYMBOLS:
         if name not in ("snch_last_error",):
             getattr(L, name).restype = C.c_int
@@ -371,6 +386,116 @@ class Scene3:
         _check(lib().snch_scene_adopt_arena(arena_tensor.data_ptr(), arena_tensor.numel(), int(device), _stream_ptr(stream),
                                             C.byref(h)))
         return cls._from_handle(h, device)
+
+
+class Scene2:
+    """Mirror of ``lbvh::scene<2>`` (scene.cuh:287-703): polylines — vertices (n, 2) + segment vertex indices (m, 2) — then
+    ``compute_silhouettes()``, ``build_bvh()``; batched queries like :class:`Scene3` (numpy in -> numpy out, torch CUDA in ->
+    torch out).  A ray hit is (t, u = segment parameter, v = 0, prim); sampling takes circles (x, y, radius) and two uniforms."""
+
+    def __init__(self, vertices, indices, device: int = 0):
+        self._L = lib()
+        self.vertices_h = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 2)
+        self.indices_h = np.ascontiguousarray(indices, dtype=np.int32).reshape(-1, 2)
+        self.device = int(device)
+        h = C.c_void_p()
+        _check(self._L.snch_scene2_create(self.vertices_h.ctypes.data, len(self.vertices_h), self.indices_h.ctypes.data,
+                                          len(self.indices_h), self.device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.snch_scene2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute_silhouettes(self):
+        _check(self._L.snch_scene2_compute_silhouettes(self._h))
+        return self
+
+    def build_bvh(self, stream=None):
+        _check(self._L.snch_scene2_build(self._h, _stream_ptr(stream)))
+        return self
+
+    def set_option(self, name: str, value: int):
+        _check(self._L.snch_scene2_set_option(self._h, name.encode(), int(value)))
+        return self
+
+    def stats(self) -> dict:
+        st = BuildStats()
+        _check(self._L.snch_scene2_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k in ("num_objects", "num_nodes", "num_edges", "num_vertices", "morton_collision", "build_ms")}
+
+    def get_bvh_device_ptr(self) -> BvhDevicePod:
+        """Reference-layout device pointers (``bvh_device<float, 2, line_segment>``); raises "BVH is not built yet." (scene.cuh:686)."""
+        pod = BvhDevicePod()
+        _check(self._L.snch_scene2_device_repr(self._h, C.byref(pod)))
+        return pod
+
+    def export(self, kind: ExportKind) -> np.ndarray:
+        n, nv = len(self.indices_h), len(self.vertices_h)
+        nn = 2 * n - 1 if n else 0
+        shape, dt = {
+            ExportKind.NODES: ((nn, 4), np.uint32), ExportKind.AABBS: ((nn, 4), np.float32), ExportKind.CONES: ((nn, 4), np.float32),
+            ExportKind.MORTON_SORTED: ((n,), np.uint32), ExportKind.SORTED_INDEX: ((n,), np.uint32),
+            ExportKind.EDGES: ((nv, 4), np.int32), ExportKind.TRI_OWNED: ((n, 2), np.int32),
+        }[ExportKind(kind)]
+        out = np.zeros(shape, dt)
+        _check(self._L.snch_scene2_export(self._h, int(kind), out.ctypes.data, out.nbytes))
+        return out
+
+    def closest_point(self, points, stream=None):
+        """-> (index uint32, distance float32).  query_device(bvh, nearest(p), scene<2>::distance_calculator())"""
+        q = _Arg(points, np.float32, (2,))
+        idx, ip = _out(q, (q.n,), np.uint32)
+        dist, dp = _out(q, (q.n,), np.float32)
+        _check(self._L.snch_closest_point_batch2(self._h, q.ptr, q.n, ip, dp, _stream_ptr(stream)))
+        return idx, dist
+
+    def closest_silhouette(self, points, flip=None, r_max=None, stream=None):
+        """-> distance float32 (+inf when none).  query_device(bvh, nearest_silhouette(p, flip), silhouette_distance_calculator())"""
+        q = _Arg(points, np.float32, (2,))
+        if isinstance(flip, (bool, np.bool_)):
+            flip = None if not flip else (np.ones(q.n, np.uint8) if not q.torch else _torch_full(q, 1))
+        f = _Arg(flip, np.uint8, None, allow_none=True)
+        r = _Arg(r_max, np.float32, None, allow_none=True)
+        dist, dp = _out(q, (q.n,), np.float32)
+        _check(self._L.snch_closest_silhouette_batch2(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, _stream_ptr(stream)))
+        return dist
+
+    def intersect(self, origins, directions, t_max=None, any_hit=False, stream=None):
+        """-> (found uint8, hits[t,u=s,v=0,prim]).  query_device(bvh, ray_intersect<any_hit>(ray, max_dist), intersect_test())"""
+        o = _Arg(origins, np.float32, (2,))
+        d = _Arg(directions, np.float32, (2,))
+        tm = _Arg(t_max, np.float32, None, allow_none=True)
+        found, fp = _out(o, (o.n,), np.uint8)
+        if any_hit:
+            _check(self._L.snch_intersect_batch2(self._h, o.ptr, d.ptr, tm.ptr, o.n, None, fp, 1, _stream_ptr(stream)))
+            return found, None
+        if o.torch:
+            import torch
+            hits = torch.empty((o.n, 4), dtype=torch.float32, device=o.obj.device)
+            hp = hits.data_ptr()
+        else:
+            hits = np.zeros(o.n, HIT_DTYPE)
+            hp = hits.ctypes.data
+        _check(self._L.snch_intersect_batch2(self._h, o.ptr, d.ptr, tm.ptr, o.n, hp, fp, 0, _stream_ptr(stream)))
+        return found, hits
+
+    def sample_in_sphere(self, circles, rnd, stream=None):
+        """-> (index int32 (-1 = miss), pdf float32, point float32[n,2]).  sample_object_in_sphere + sample_on_object in 2-D"""
+        s = _Arg(circles, np.float32, (3,))
+        r = _Arg(rnd, np.float32, (2,))
+        idx, ip = _out(s, (s.n,), np.int32)
+        pdf, pp = _out(s, (s.n,), np.float32)
+        pt, tp = _out(s, (s.n, 2), np.float32)
+        _check(self._L.snch_sample_in_sphere_batch2(self._h, s.ptr, r.ptr, s.n, ip, pp, tp, _stream_ptr(stream)))
+        return idx, pdf, pt
 
 
 def _stream_ptr(stream):

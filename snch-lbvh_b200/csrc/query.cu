@@ -22,132 +22,13 @@
 //   silhouette: min over the leaves that pass the reference's cone test chain (same predicate)
 //   ray       : smallest t with t < max_dist; prim = any triangle attaining it (Q4)
 //   sample    : identical single-path descent (deterministic given u)
+#include "query_common.cuh"
 #include "scene.h"
 #include "snch_math.cuh"
 #include "sort_scan.cuh"
 
 namespace snch
 {
-
-constexpr int kQueryThreads = 128;
-constexpr int kStackDepth = 64; // >= 62 levels possible with the 62-bit augmented key
-constexpr unsigned kFull = 0xffffffffu;
-constexpr uint32_t kChunk = 64; // consecutive queries a warp draws per atomic
-
-struct NodeBoxes
-{
-    V3 lo0, hi0, lo1, hi1;
-};
-SNCH_DI NodeBoxes unpack_boxes(float4 a, float4 b, float4 c)
-{
-    NodeBoxes n;
-    n.lo0 = V3{a.x, a.y, a.z};
-    n.hi0 = V3{a.w, b.x, b.y};
-    n.lo1 = V3{b.z, b.w, c.x};
-    n.hi1 = V3{c.y, c.z, c.w};
-    return n;
-}
-// One 32-byte sector per instruction (LDG.E.256, sm_100): a divergent warp pays one L1 tag lookup per lane per
-// instruction, so a 64 B / 96 B record costs 2 / 3 lookups instead of 4 / 6 with 128-bit loads.  p must be 32 B aligned.
-SNCH_DI void ld256(const void *p, float4 &lo, float4 &hi)
-{
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-                 : "l"(p));
-}
-// traversal stack entry: node reference + the key it was pushed with, moved with one 64-bit local access
-struct __align__(8) StackEntry
-{
-    uint32_t node;
-    float key;
-};
-SNCH_DI V3 load_point(const float *__restrict__ q, uint64_t i) { return V3{__ldg(q + 3 * i), __ldg(q + 3 * i + 1), __ldg(q + 3 * i + 2)}; }
-
-// ---------------------------------------------------------------------------------------------------------------
-// warp-level work distribution
-// ---------------------------------------------------------------------------------------------------------------
-struct Feeder
-{
-    uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
-    bool exhausted;     // the global counter ran past n
-    uint32_t hop = 0;   // region feed: regions this warp has seen run dry (it draws from region (home + hop) % regions)
-};
-// Region feed ("query.feed" = 1 per CTA, 2 per SM): the ordered batch is cut into `regions` contiguous ranges of `per` slots,
-// each with its own counter; a warp draws its chunks from its home region and moves on to the next region only when one
-// has run dry (counters only grow, so a dry region stays dry and `hop` never goes back).  Warps that share an L1 thus
-// work on neighbouring queries and re-read each other's node records.
-struct RegionFeed
-{
-    unsigned long long *counters; // regions x u64, zeroed per batch (scratch + kScratchCounters)
-    uint32_t regions, per, home;
-};
-constexpr uint32_t kMaxRegions = 2048;
-constexpr uint64_t kScratchCounters = 256, kScratchHeader = kScratchCounters + kMaxRegions * 8; // work counter + query box | region counters
-SNCH_DI uint32_t smid()
-{
-    uint32_t r;
-    asm("mov.u32 %0, %%smid;" : "=r"(r));
-    return r;
-}
-SNCH_DI void region_draw(Feeder &f, const RegionFeed &rf, int lane, uint32_t n)
-{
-    unsigned long long base = ~0ull;
-    uint32_t hop = f.hop;
-    if (lane == 0)
-    {
-        for (; hop < rf.regions; ++hop)
-        {
-            const uint32_t r = (rf.home + hop) % rf.regions;
-            const unsigned long long lo = (unsigned long long)r * rf.per;
-            if (lo >= n) continue;
-            const unsigned long long len = min((unsigned long long)rf.per, (unsigned long long)n - lo);
-            if (*reinterpret_cast<volatile unsigned long long *>(rf.counters + r) >= len) continue;
-            const unsigned long long off = atomicAdd(rf.counters + r, (unsigned long long)kChunk);
-            if (off < len)
-            {
-                base = lo + off;
-                f.end = (uint32_t)min(lo + len, base + kChunk);
-                break;
-            }
-        }
-    }
-    base = __shfl_sync(kFull, base, 0);
-    f.hop = __shfl_sync(kFull, hop, 0);
-    f.end = __shfl_sync(kFull, f.end, 0);
-    if (base == ~0ull)
-    {
-        f.exhausted = true;
-        f.end = f.next;
-    }
-    else f.next = (uint32_t)base;
-}
-// Gives every idle lane (bit set in `idle`) the next query slot of the warp's chunk; draws a new chunk when needed.
-// Returns the slot for this lane or kNone.  Warp-convergent call.
-SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter,
-                             const RegionFeed *rf = nullptr)
-{
-    if (f.next == f.end && !f.exhausted && rf && rf->regions) region_draw(f, *rf, lane, n);
-    else if (f.next == f.end && !f.exhausted)
-    {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)kChunk);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= n) f.exhausted = true;
-        else
-        {
-            f.next = (uint32_t)base;
-            f.end = (uint32_t)min((unsigned long long)n, base + kChunk);
-        }
-    }
-    const uint32_t avail = f.end - f.next;
-    const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-    const uint32_t want = __popc(idle);
-    const uint32_t take = min(avail, want);
-    uint32_t slot = kNone;
-    if (lane_idle && rank < take) slot = f.next + rank;
-    f.next += take;
-    return slot;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // query ordering
@@ -165,7 +46,7 @@ __global__ void k_query_box_init(int *box)
     else if (threadIdx.x < 6) box[threadIdx.x] = f2ord_q(-INFINITY);
 }
 // bounding box of the finite query points (stride = floats per query: 3 for points/origins, 4 for spheres)
-__global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ q, int stride, uint32_t n, int *box)
+__global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ q, int stride, int dims, uint32_t n, int *box)
 {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -173,6 +54,7 @@ __global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ 
 #pragma unroll
         for (int a = 0; a < 3; ++a)
         {
+            if (a >= dims) continue; // 2-D batches: the third axis keeps an empty range and contributes no key bits
             const float x = __ldg(q + (uint64_t)stride * i + a);
             if (fabsf(x) <= FLT_MAX)
             {
@@ -202,7 +84,7 @@ __global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ 
 // 30-bit Morton key of each query point inside the batch's own bounding box (a scheduling hint only: any key is correct)
 // With `radius` (silhouette star radii) the top 4 key bits are the radius octave relative to the batch extent, so the 32
 // queries a warp walks together also have similar search radii (a scheduling hint only: any key is correct).
-__global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q, int stride, uint32_t n, const int *__restrict__ box,
+__global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q, int stride, int dims, uint32_t n, const int *__restrict__ box,
                                                     const float *__restrict__ radius, uint32_t *__restrict__ keys,
                                                     uint32_t *__restrict__ perm)
 {
@@ -212,6 +94,7 @@ __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q,
 #pragma unroll
     for (int a = 0; a < 3; ++a)
     {
+        if (a >= dims) continue;
         const float lo = ord2f_q(box[a]), hi = ord2f_q(box[3 + a]);
         const float x = __ldg(q + (uint64_t)stride * i + a);
         float t = (x - lo) / fmaxf(hi - lo, FLT_MIN) * 1024.0f;
@@ -221,7 +104,7 @@ __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q,
     if (radius)
     {
         const float ext = fmaxf(fmaxf(ord2f_q(box[3]) - ord2f_q(box[0]), ord2f_q(box[4]) - ord2f_q(box[1])),
-                                fmaxf(ord2f_q(box[5]) - ord2f_q(box[2]), FLT_MIN));
+                                fmaxf(dims > 2 ? ord2f_q(box[5]) - ord2f_q(box[2]) : 0.0f, FLT_MIN));
         const float r = __ldg(radius + i);
         const int oct = (int)((__float_as_uint(fmaxf(r, 0.0f)) >> 23) & 0xFFu) - (int)((__float_as_uint(ext) >> 23) & 0xFFu); // floor(log2(r/ext))
         const uint32_t cls = (uint32_t)min(max(oct + 13, 0), 15); // >= 4 x extent (incl. +inf) -> 15; NaN -> 0
@@ -1382,9 +1265,8 @@ uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
 }
 
 // Lays the scratch out and, for batches worth ordering, produces the Morton permutation.  *perm_out = nullptr otherwise.
-static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n,
-                         unsigned char *scratch, cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out,
-                         QueryCounters *qc)
+int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n, unsigned char *scratch,
+                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims)
 {
     SNCH_CUDA(cudaMemsetAsync(scratch, 0, t.feed ? kScratchHeader : 64, st));
     *counter_out = reinterpret_cast<unsigned long long *>(scratch);
@@ -1399,33 +1281,14 @@ static int prepare_batch(const QueryTuning &t, bool order, const float *pts, int
     uint32_t *sscr = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 4 * a);
     const unsigned g = (n + 255) / 256;
     k_query_box_init<<<1, 32, 0, st>>>(box);
-    k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, n, box);
-    k_query_keys<<<g, 256, 0, st>>>(pts, stride, n, box, radius, keys, perm);
+    k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, dims, n, box);
+    k_query_keys<<<g, 256, 0, st>>>(pts, stride, dims, n, box, radius, keys, perm);
     int bits = t.sort_bits < 8 ? 8 : (t.sort_bits > 30 ? 30 : t.sort_bits);
     const int sort_launches = radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
     if (qc) qc->launches += 3 + sort_launches;
     SNCH_CUDA(cudaGetLastError());
     *perm_out = perm;
     return SNCH_OK;
-}
-
-template <typename K> static unsigned persistent_grid(K kernel, const QueryTuning &t, uint32_t n)
-{
-    static thread_local int cached_dev = -1, sms = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != cached_dev)
-    {
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cached_dev = dev;
-    }
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kQueryThreads, 0);
-    if (per_sm < 1) per_sm = 1;
-    if (t.blocks_per_sm > 0 && t.blocks_per_sm < per_sm) per_sm = t.blocks_per_sm;
-    const uint64_t full = (uint64_t)sms * per_sm;
-    const uint64_t need = ((uint64_t)n + kChunk * (kQueryThreads / 32) - 1) / (kChunk * (kQueryThreads / 32));
-    return (unsigned)(need < full ? (need ? need : 1) : full);
 }
 
 // per-lane silhouette traversal: v4 (warp-shared leaf queue, shared-memory stack) unless the knob or the scene size

@@ -1,0 +1,157 @@
+// query_common.cuh — scheduling pieces shared by the batched traversal kernels of query.cu (3-D scenes) and scene2.cu
+// (2-D scenes): persistent-lane work distribution, 256-bit record loads, stack entries, batch ordering.
+#ifndef SNCH_QUERY_COMMON_CUH
+#define SNCH_QUERY_COMMON_CUH
+#include "scene.h"
+#include "snch_math.cuh"
+
+namespace snch
+{
+
+constexpr int kQueryThreads = 128;
+constexpr int kStackDepth = 64; // >= 62 levels possible with the 62-bit augmented key
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kChunk = 64; // consecutive queries a warp draws per atomic
+
+struct NodeBoxes
+{
+    V3 lo0, hi0, lo1, hi1;
+};
+SNCH_DI NodeBoxes unpack_boxes(float4 a, float4 b, float4 c)
+{
+    NodeBoxes n;
+    n.lo0 = V3{a.x, a.y, a.z};
+    n.hi0 = V3{a.w, b.x, b.y};
+    n.lo1 = V3{b.z, b.w, c.x};
+    n.hi1 = V3{c.y, c.z, c.w};
+    return n;
+}
+// One 32-byte sector per instruction (LDG.E.256, sm_100): a divergent warp pays one L1 tag lookup per lane per
+// instruction, so a 64 B / 96 B record costs 2 / 3 lookups instead of 4 / 6 with 128-bit loads.  p must be 32 B aligned.
+SNCH_DI void ld256(const void *p, float4 &lo, float4 &hi)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+// traversal stack entry: node reference + the key it was pushed with, moved with one 64-bit local access
+struct __align__(8) StackEntry
+{
+    uint32_t node;
+    float key;
+};
+SNCH_DI V3 load_point(const float *__restrict__ q, uint64_t i) { return V3{__ldg(q + 3 * i), __ldg(q + 3 * i + 1), __ldg(q + 3 * i + 2)}; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// warp-level work distribution
+// ---------------------------------------------------------------------------------------------------------------
+struct Feeder
+{
+    uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
+    bool exhausted;     // the global counter ran past n
+    uint32_t hop = 0;   // region feed: regions this warp has seen run dry (it draws from region (home + hop) % regions)
+};
+// Region feed ("query.feed" = 1 per CTA, 2 per SM): the ordered batch is cut into `regions` contiguous ranges of `per` slots,
+// each with its own counter; a warp draws its chunks from its home region and moves on to the next region only when one
+// has run dry (counters only grow, so a dry region stays dry and `hop` never goes back).  Warps that share an L1 thus
+// work on neighbouring queries and re-read each other's node records.
+struct RegionFeed
+{
+    unsigned long long *counters; // regions x u64, zeroed per batch (scratch + kScratchCounters)
+    uint32_t regions, per, home;
+};
+constexpr uint32_t kMaxRegions = 2048;
+constexpr uint64_t kScratchCounters = 256, kScratchHeader = kScratchCounters + kMaxRegions * 8; // work counter + query box | region counters
+SNCH_DI uint32_t smid()
+{
+    uint32_t r;
+    asm("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+SNCH_DI void region_draw(Feeder &f, const RegionFeed &rf, int lane, uint32_t n)
+{
+    unsigned long long base = ~0ull;
+    uint32_t hop = f.hop;
+    if (lane == 0)
+    {
+        for (; hop < rf.regions; ++hop)
+        {
+            const uint32_t r = (rf.home + hop) % rf.regions;
+            const unsigned long long lo = (unsigned long long)r * rf.per;
+            if (lo >= n) continue;
+            const unsigned long long len = min((unsigned long long)rf.per, (unsigned long long)n - lo);
+            if (*reinterpret_cast<volatile unsigned long long *>(rf.counters + r) >= len) continue;
+            const unsigned long long off = atomicAdd(rf.counters + r, (unsigned long long)kChunk);
+            if (off < len)
+            {
+                base = lo + off;
+                f.end = (uint32_t)min(lo + len, base + kChunk);
+                break;
+            }
+        }
+    }
+    base = __shfl_sync(kFull, base, 0);
+    f.hop = __shfl_sync(kFull, hop, 0);
+    f.end = __shfl_sync(kFull, f.end, 0);
+    if (base == ~0ull)
+    {
+        f.exhausted = true;
+        f.end = f.next;
+    }
+    else f.next = (uint32_t)base;
+}
+// Gives every idle lane (bit set in `idle`) the next query slot of the warp's chunk; draws a new chunk when needed.
+// Returns the slot for this lane or kNone.  Warp-convergent call.
+SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter,
+                             const RegionFeed *rf = nullptr)
+{
+    if (f.next == f.end && !f.exhausted && rf && rf->regions) region_draw(f, *rf, lane, n);
+    else if (f.next == f.end && !f.exhausted)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)kChunk);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) f.exhausted = true;
+        else
+        {
+            f.next = (uint32_t)base;
+            f.end = (uint32_t)min((unsigned long long)n, base + kChunk);
+        }
+    }
+    const uint32_t avail = f.end - f.next;
+    const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+    const uint32_t want = __popc(idle);
+    const uint32_t take = min(avail, want);
+    uint32_t slot = kNone;
+    if (lane_idle && rank < take) slot = f.next + rank;
+    f.next += take;
+    return slot;
+}
+
+// Lays the per-batch scratch out (query_scratch_bytes) and, for batches worth ordering, produces the Morton permutation of the
+// query points (`dims` = 2 or 3 coordinates at pts[stride * i]).  *perm_out = nullptr otherwise.            query.cu
+int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n, unsigned char *scratch,
+                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims = 3);
+
+// grid of a persistent kernel: SMs x resident CTAs, or fewer when the batch has fewer chunks than that
+template <typename K> static inline unsigned persistent_grid(K kernel, const QueryTuning &t, uint32_t n)
+{
+    static thread_local int cached_dev = -1, sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev)
+    {
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached_dev = dev;
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kQueryThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    if (t.blocks_per_sm > 0 && t.blocks_per_sm < per_sm) per_sm = t.blocks_per_sm;
+    const uint64_t full = (uint64_t)sms * per_sm;
+    const uint64_t need = ((uint64_t)n + kChunk * (kQueryThreads / 32) - 1) / (kChunk * (kQueryThreads / 32));
+    return (unsigned)(need < full ? (need ? need : 1) : full);
+}
+
+} // namespace snch
+#endif // SNCH_QUERY_COMMON_CUH

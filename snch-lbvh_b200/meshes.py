@@ -116,3 +116,62 @@ def star_radius_scale(n: int, seed: int = 4242) -> np.ndarray:
     """s ~ U[0.5, 4): WoSt star radius r_max = s * closest-point distance (config C3)."""
     rng = np.random.default_rng(seed)
     return (0.5 + 3.5 * rng.random(n, dtype=np.float32)).astype(np.float32)
+
+
+# ---- 2-D polylines (lbvh::scene<2>: vertices (n, 2), segments (m, 2)) --------------------------------------------------
+def wavy_circle(n: int = 4096, lobes: int = 7, amp: float = 0.25):
+    """Closed, consistently oriented polyline r(t) = 1 + amp sin(lobes t): every vertex has two adjacent segments."""
+    t = np.linspace(0.0, 2.0 * np.pi, n, endpoint=False)
+    r = 1.0 + amp * np.sin(lobes * t)
+    v = np.stack([r * np.cos(t), r * np.sin(t)], -1).astype(np.float32)
+    s = np.stack([np.arange(n), (np.arange(n) + 1) % n], -1).astype(np.int32)
+    return v, s
+
+
+def open_polyline(n: int = 449):
+    """Open zig-zag with two free ends (boundary silhouette vertices: leaf cones of half-angle pi)."""
+    x = np.linspace(-1.0, 1.0, n + 1)
+    y = 0.3 * np.sin(6.0 * x) + 0.05 * np.where(np.arange(n + 1) % 2 == 0, 1.0, -1.0)
+    v = np.stack([x, y], -1).astype(np.float32)
+    s = np.stack([np.arange(n), np.arange(n) + 1], -1).astype(np.int32)
+    return v, s
+
+
+def polyline_soup(seed: int = 3, loops: int = 5, n: int = 200):
+    """Several closed loops and open strands in one scene, segments shuffled (ownership depends on input order) and a
+    third of them reversed (inconsistent orientation: later segments overwrite a vertex's previous / next slots)."""
+    rng = np.random.default_rng(seed)
+    vs, ss, base = [], [], 0
+    for k in range(loops):
+        c = rng.uniform(-1.0, 1.0, 2)
+        m = n + 17 * k
+        t = np.linspace(0.0, 2.0 * np.pi, m, endpoint=False)
+        r = 0.2 + 0.1 * rng.random() + 0.04 * np.sin((3 + k) * t)
+        vs.append(np.stack([c[0] + r * np.cos(t), c[1] + r * np.sin(t)], -1))
+        idx = np.arange(m)
+        seg = np.stack([idx, (idx + 1) % m], -1)
+        if k % 2 == 1:
+            seg = seg[:-7]  # open strand
+        ss.append(seg + base)
+        base += m
+    v = np.concatenate(vs).astype(np.float32)
+    s = np.concatenate(ss).astype(np.int32)
+    flip = rng.random(len(s)) < 0.33
+    s[flip] = s[flip][:, ::-1]
+    return v, s[rng.permutation(len(s))].copy()
+
+
+def points_in_box2(n: int, lo, hi, scale: float = 1.1, seed: int = 2025) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    lo = np.asarray(lo, np.float64)
+    hi = np.asarray(hi, np.float64)
+    c = 0.5 * (lo + hi)
+    h = 0.5 * (hi - lo) * scale
+    p = rng.random((n, 2), dtype=np.float32).astype(np.float64)
+    return (c - h + 2.0 * h * p).astype(np.float32)
+
+
+def unit_directions2(n: int, seed: int = 77) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    a = rng.random(n) * 2.0 * np.pi
+    return np.stack([np.cos(a), np.sin(a)], -1).astype(np.float32)

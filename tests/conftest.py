@@ -31,3 +31,13 @@ def small_cases(m):
         "grid6": m.open_grid(6),
         "torus24x16": m.bumpy_torus(24, 16),
     }
+
+
+def small_cases2(m):
+    """name -> (verts, segments): 2-D polylines (closed, open with free ends, shuffled / inconsistently oriented soup).
+    A one-segment scene is not here: the reference's traversals read out of bounds on it."""
+    return {
+        "poly_circle": m.wavy_circle(257, 5, 0.2),
+        "poly_open": m.open_polyline(97),
+        "poly_soup": m.polyline_soup(3, 4, 60),
+    }

@@ -1,0 +1,77 @@
+"""2-D scenes (lbvh::scene<2>) without a GPU: the committed golden vectors are what the UNMODIFIED reference headers produce
+on the CPU (oracle/_ref, when present), and the host-side logic of the C-ABI scene (silhouette records, argument checks,
+no fallback) works on a CPU-only box."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import small_cases2
+from oracle import ref_available
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gold(name):
+    return np.load(os.path.join(GOLD, f"{name}.npz"))
+
+
+@pytest.mark.parametrize("name", ["poly_circle", "poly_open", "poly_soup"])
+def test_goldens_are_the_reference(pkg, name):
+    if not ref_available("cpu"):
+        pytest.skip("oracle/_ref/libsnch_ref_cpu.so not built (needs /root/reference)")
+    from oracle import RefScene2
+    g = _gold(name)
+    v, s = small_cases2(pkg.meshes)[name]
+    assert np.array_equal(v, g["verts"]) and np.array_equal(s, g["segs"])  # generators still produce the fixture's inputs
+    r = RefScene2(v, s, "cpu")
+    nodes, aabbs, cones = r.tree()
+    assert np.array_equal(nodes, g["nodes"])
+    assert np.array_equal(aabbs.view(np.uint32), g["aabbs"].view(np.uint32))
+    assert np.array_equal(cones.view(np.uint32), g["cones"].view(np.uint32))
+    v4, owned = r.adjacency()
+    assert np.array_equal(v4, g["vert4"]) and np.array_equal(owned, g["owned"])
+    ci, cd = r.closest(g["q"])
+    assert np.array_equal(cd.view(np.uint32), g["closest_dist"].view(np.uint32)) and np.array_equal(ci, g["closest_idx"])
+    assert np.array_equal(r.silhouette(g["q"], False).view(np.uint32), g["sil_noflip"].view(np.uint32))
+    assert np.array_equal(r.silhouette(g["q"], True).view(np.uint32), g["sil_flip"].view(np.uint32))
+    f, t, s_, p = r.ray(g["q"], g["d"])
+    assert np.array_equal(f, g["ray_found"]) and np.array_equal(t.view(np.uint32), g["ray_t"].view(np.uint32)) and np.array_equal(p, g["ray_prim"])
+    si, sp = r.sample(g["sph"], g["u"])
+    assert np.array_equal(si, g["sample_idx"]) and np.array_equal(sp.view(np.uint32), g["sample_pdf"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["poly_circle", "poly_open", "poly_soup"])
+def test_silhouette_records_match_reference(pkg, name):
+    """compute_silhouettes (scene.cuh:629-656) runs on the host: one {previous, self, next} record per vertex, later segments
+    overwrite earlier ones — identical to the reference's on inconsistently oriented input too."""
+    g = _gold(name)
+    sc = pkg.Scene2(g["verts"], g["segs"]).compute_silhouettes()
+    assert np.array_equal(sc.export(pkg.ExportKind.EDGES), g["vert4"])
+
+
+def test_argument_errors_2d(pkg):
+    v = np.zeros((3, 2), np.float32)
+    with pytest.raises(pkg.SnchError) as e:
+        pkg.Scene2(v, np.array([[0, 3]], np.int32))
+    assert e.value.status == -1 and "out of range" in str(e.value)
+    sc = pkg.Scene2(v, np.array([[0, 1], [1, 2]], np.int32))
+    with pytest.raises(pkg.SnchError) as e:
+        sc.get_bvh_device_ptr()
+    assert e.value.status == -2 and str(e.value) == "BVH is not built yet."  # scene.cuh:686
+    with pytest.raises(pkg.SnchError) as e:
+        sc.closest_point(np.zeros((1, 2), np.float32))
+    assert e.value.status == -2
+    with pytest.raises(pkg.SnchError):
+        sc.set_option("query.no_such_knob", 1)
+
+
+def test_no_cpu_fallback_2d(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    v, s = pkg.meshes.wavy_circle(64)
+    sc = pkg.Scene2(v, s).compute_silhouettes()
+    with pytest.raises(pkg.SnchError) as e:
+        sc.build_bvh()
+    assert e.value.status == -3 and "no CPU fallback" in str(e.value)
