@@ -13,7 +13,8 @@
 //     std::map, and the fused sm_100a build pipeline.  All device data lives in ONE arena owned by the library handle;
 //     vertices_d / silhouettes_d are non-owning views into it and bvh_dev points at its reference-layout arrays.  The same
 //     handle serves the batched query entry points (closest_points(), closest_silhouettes(), intersect(), sample_in_spheres()).
-//   * scene<2> evaluates its getters in this header and builds through lbvh::bvh -> snch_lbvh_build (dim = 2).
+//   * scene<2> evaluates its getters in this header and builds through lbvh::bvh -> snch_lbvh_build (dim = 2); its batched
+//     entry points run on the library's 2-D scene (snch_scene2_* in include/snch_b200.h), created on first use.
 // Float operation order inside the functors follows the reference so results agree to rounding (DESIGN.md "Parity rules").
 #ifndef SNCH_LBVH_B200_SCENE_CUH
 #define SNCH_LBVH_B200_SCENE_CUH
@@ -453,11 +454,40 @@ public:
         }
         p_bvh = std::make_unique<bvh_type>(lines.begin(), lines.end(), true);
         bvh_dev = p_bvh->get_device_repr();
+        batched_.reset(); // the batched entry points rebuild their records from the new geometry on next use
     }
     const lbvh::bvh_device<float, 2, line_segment> &get_bvh_device_ptr() const
     {
         if (!p_bvh) throw std::runtime_error("BVH is not built yet.");
         return bvh_dev;
+    }
+
+    // ---- batched queries (one launch per call; device OR host pointers, see include/snch_b200.h "2-D scenes") ----------------
+    // Each is the batched form of the per-thread call named next to it and returns the same values per query.  They run on
+    // the library's own 2-D scene (fused two-child records, persistent kernels), created from this scene's vertices and
+    // segments the first time one of them is called after build_bvh().
+    // query_device(bvh_dev, nearest(p), distance_calculator())
+    void closest_points(const float2 *points, std::size_t n, unsigned int *out_index, float *out_distance, cudaStream_t stream = nullptr) const
+    {
+        detail::check_status(snch_closest_point_batch2(batched(stream), &points->x, n, out_index, out_distance, stream));
+    }
+    // query_device(bvh_dev, nearest_silhouette(p, flip), silhouette_distance_calculator()); r_max optional search radii
+    void closest_silhouettes(const float2 *points, const unsigned char *flip, const float *r_max, std::size_t n, float *out_distance,
+                             cudaStream_t stream = nullptr) const
+    {
+        detail::check_status(snch_closest_silhouette_batch2(batched(stream), &points->x, flip, r_max, n, out_distance, stream));
+    }
+    // query_device(bvh_dev, ray_intersect<any_hit>(ray(o, d), t_max), intersect_test()); snch_hit = {t, s, 0, segment}
+    void intersect(const float2 *origins, const float2 *directions, const float *t_max, std::size_t n, snch_hit *out_hits, unsigned char *out_found,
+                   bool any_hit = false, cudaStream_t stream = nullptr) const
+    {
+        detail::check_status(snch_intersect_batch2(batched(stream), &origins->x, &directions->x, t_max, n, out_hits, out_found, any_hit ? 1 : 0, stream));
+    }
+    // sample_object_in_sphere(...) followed by sample_on_object(...); circles = (x, y, radius), rnd = (u, u1) per query
+    void sample_in_spheres(const float3 *circles, const float2 *rnd, std::size_t n, int *out_index, float *out_pdf, float2 *out_point,
+                           cudaStream_t stream = nullptr) const
+    {
+        detail::check_status(snch_sample_in_sphere_batch2(batched(stream), &circles->x, &rnd->x, n, out_index, out_pdf, out_point ? &out_point->x : nullptr, stream));
     }
 
 public:
@@ -471,8 +501,27 @@ public:
     lbvh::bvh_device<float, 2, line_segment> bvh_dev;
 
 private:
+    struct handle2_deleter
+    {
+        void operator()(snch_scene2 *s) const noexcept { snch_scene2_destroy(s); }
+    };
+    const snch_scene2 *batched(cudaStream_t stream) const
+    {
+        if (!p_bvh) throw std::runtime_error("BVH is not built yet.");
+        if (!batched_)
+        {
+            snch_scene2 *h = nullptr;
+            detail::check_status(snch_scene2_create(vertices_h.size() ? &vertices_h[0].x : nullptr, static_cast<std::uint32_t>(vertices_h.size()),
+                                                    indices_h.size() ? &indices_h[0].x : nullptr, static_cast<std::uint32_t>(indices_h.size()), 0, &h));
+            batched_.reset(h);
+            detail::check_status(snch_scene2_compute_silhouettes(h));
+            detail::check_status(snch_scene2_build(h, stream));
+        }
+        return batched_.get();
+    }
     detail::device_buffer<float2> vertices_store_;
     detail::device_buffer<silhouette_vertex> silhouettes_store_;
+    mutable std::unique_ptr<snch_scene2, handle2_deleter> batched_;
 };
 
 // =========================================================================================================================

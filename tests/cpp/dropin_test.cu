@@ -333,6 +333,25 @@ int main(int argc, char **argv)
         std::printf("CHECK sample2d_hits %zu\n", sampled);
         const auto &nodes2 = s2.p_bvh->nodes_host();
         std::printf("CHECK nodes2d %zu\n", nodes2.size());
+        // batched 2-D entry points of the same scene (device pointers) vs the per-thread calls above
+        float *bd, *bs;
+        snch_hit *bh;
+        unsigned char *bf;
+        CUDA_OK(cudaMalloc(&bd, n2 * 4));
+        CUDA_OK(cudaMalloc(&bs, n2 * 4));
+        CUDA_OK(cudaMalloc(&bh, n2 * sizeof(snch_hit)));
+        CUDA_OK(cudaMalloc(&bf, n2));
+        s2.closest_points(dq2, n2, oc, bd);
+        s2.closest_silhouettes(dq2, nullptr, nullptr, n2, bs);
+        s2.intersect(dq2, dd2, nullptr, n2, bh, bf);
+        CUDA_OK(cudaDeviceSynchronize());
+        std::vector<snch_hit> hh(n2);
+        CUDA_OK(cudaMemcpy(hh.data(), bh, n2 * sizeof(snch_hit), cudaMemcpyDeviceToHost));
+        std::vector<float> bt(n2);
+        for (int i = 0; i < n2; ++i) bt[i] = hh[i].t;
+        std::printf("CHECK closest2d_vs_batched_worst_rel %.3e\n", worst_rel(host(o[0], n2), host(bd, n2)));
+        std::printf("CHECK silhouette2d_vs_batched_mismatch_frac %.3e\n", mismatch_frac(host(o[1], n2), host(bs, n2), 1e-5));
+        std::printf("CHECK ray2d_vs_batched_mismatch_frac %.3e\n", mismatch_frac(host(o[2], n2), bt, 1e-5));
     }
     std::printf("DROPIN_OK\n");
     return 0;

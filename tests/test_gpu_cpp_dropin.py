@@ -51,3 +51,6 @@ def test_cpp_dropin_api(meshes, tmp_path, mesh):
     assert c["closest2d_vs_brute_worst_rel"] <= 1e-5 and c["ray2d_vs_brute_mismatch_frac"] <= 1e-3
     assert c["silhouette2d_vs_brute_mismatch_frac"] <= 2e-2  # cone pruning is only approximately conservative in the reference too
     assert c["sample2d_hits"] > 0
+    # batched 2-D entry points (snch_*_batch2) == the per-thread header traversals of the same scene
+    assert c["closest2d_vs_batched_worst_rel"] <= 1e-5
+    assert c["silhouette2d_vs_batched_mismatch_frac"] <= 1e-3 and c["ray2d_vs_batched_mismatch_frac"] <= 1e-3
