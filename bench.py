@@ -188,6 +188,8 @@ def other_config(cfg, pkg, m, dev, stream):
     """BASELINE.json configs C4 / C5 at their per-GPU share of the 8-GPU batch (one rank's shard: the tree is replicated,
     so a rank's throughput does not depend on the other ranks).  Device-resident, CUDA events on `stream`."""
     import torch
+    if cfg == "2d":
+        return scene2_config(pkg, m, dev, stream)
     nu, per_gpu = {"c4": (1416, (1 << 24) // 8), "c5": (2240, (1 << 26) // 8)}[cfg]
     v, f = m.bumpy_torus(nu, nu)
     t0 = time.perf_counter()
@@ -226,6 +228,66 @@ def other_config(cfg, pkg, m, dev, stream):
     return out
 
 
+def scene2_config(pkg, m, dev, stream):
+    """2-D path (lbvh::scene<2>, SURVEY 8(f) rank 3): a 1 048 576-segment closed polyline, 4 194 304 queries, device-resident,
+    CUDA events on `stream`; the reference's own CUDA 2-D path (unmodified headers, one thread per query) beside it."""
+    import torch
+    v, s = m.wavy_circle(1 << 20, 37, 0.2)
+    n = 1 << 22
+    t0 = time.perf_counter()
+    sc = pkg.Scene2(v, s, device=dev).compute_silhouettes().build_bvh(stream=stream)
+    out = {"segments": len(s), "queries": n, "scene_setup_wall_ms": (time.perf_counter() - t0) * 1e3, "build_ms": sc.stats()["build_ms"]}
+    q_h = m.points_in_box2(n, v.min(0), v.max(0), 1.1, seed=41)
+    d_h = m.unit_directions2(n, seed=42)
+    q, d = torch.from_numpy(q_h).to(f"cuda:{dev}"), torch.from_numpy(d_h).to(f"cuda:{dev}")
+
+    def timed(fn, reps=5):
+        fn()
+        stream.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        stream.synchronize()
+        return a.elapsed_time(b) / reps
+
+    with torch.cuda.stream(stream):
+        _, dist = sc.closest_point(q, stream=stream)
+        rmax = (dist * 2.0).contiguous()
+        out["closest_mqps"] = n / timed(lambda: sc.closest_point(q, stream=stream)) / 1e3
+        out["silhouette_unbounded_mqps"] = n / timed(lambda: sc.closest_silhouette(q, stream=stream)) / 1e3
+        out["silhouette_star_radius_mqps"] = n / timed(lambda: sc.closest_silhouette(q, r_max=rmax, stream=stream)) / 1e3
+        out["ray_mqps"] = n / timed(lambda: sc.intersect(q, d, stream=stream)) / 1e3
+        circ = torch.cat([q, rmax[:, None]], dim=1).contiguous()
+        rnd = torch.from_numpy(m.uniforms(n, 2, seed=43)).to(f"cuda:{dev}")
+        out["sample_in_circle_mqps"] = n / timed(lambda: sc.sample_in_sphere(circ, rnd, stream=stream)) / 1e3
+        builds = []
+        for _ in range(3):
+            sc.build_bvh(stream=stream)
+            builds.append(sc.stats()["build_ms"])
+        out["build_ms"] = min(builds)
+    try:
+        from oracle import RefScene2, ref_available
+        if ref_available("cuda"):
+            ns = 1 << 20
+            t0 = time.perf_counter()
+            ref = RefScene2(v, s, "cuda")
+            rc = {"scene_setup_wall_ms": (time.perf_counter() - t0) * 1e3, "sample": f"first {ns} of the queries"}
+            for name, fn in (("closest_mqps", lambda: ref.L.ref2_closest(ref.h, q_h[:ns], ns, np.zeros(ns, np.uint32), np.zeros(ns, np.float32), 1)),
+                             ("silhouette_unbounded_mqps", lambda: ref.L.ref2_silhouette(ref.h, q_h[:ns], ns, 0, np.zeros(ns, np.float32), 1)),
+                             ("ray_mqps", lambda: ref.L.ref2_ray(ref.h, q_h[:ns], d_h[:ns], np.full(ns, np.inf, np.float32), ns, np.zeros(ns, np.int32),
+                                                                 np.zeros(ns, np.float32), np.zeros(ns, np.float32), np.zeros(ns, np.uint32), 1))):
+                fn()
+                rc[name] = ns / fn() / 1e3  # the wrappers return the traversal kernel's milliseconds (CUDA events)
+            out["reference_cuda"] = rc
+    except Exception as ex:
+        out["reference_cuda_error"] = repr(ex)
+    del sc
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 def main():
     """Everything but the result line is kept off stdout (NCCL prints its version banner there, the reference prints its
@@ -244,7 +306,7 @@ def _run():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--queries", type=int, default=N_QUERIES, help="queries per GPU per step (default: the C3 batch)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (closest/ray/build/reference CUDA)")
-    ap.add_argument("--also", default="", help="comma list of further BASELINE.json configs to time into `extra` on rank 0: "
+    ap.add_argument("--also", default="", help="comma list of further configs to time into `extra` on rank 0 (c4, c5 of BASELINE.json; 2d = the scene<2> path): "
                     "c4 (16M rays / 8 GPUs on a 4M-triangle mesh), c5 (wavefront WoSt step, 64M walkers / 8 GPUs on a 10M-triangle mesh)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

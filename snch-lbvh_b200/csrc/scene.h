@@ -16,8 +16,10 @@ struct QueryTuning
     int sort_bits = 24;     // Morton key bits the ordering sorts on (top bits of the 30-bit code)
     int sort_rays = 0;      // also order ray batches by origin (off: random directions decorrelate the paths anyway)
     int packet = 1;         // warp-cooperative traversal of ordered batches: bit 0 closest point, bit 1 silhouette
-    int cone_filter = 2;    // silhouette normal-cone test: 0 = the reference's libm chain, 1 = guard-banded sine-space filter on
-                            // correctly rounded sqrt/rcp, 2 = the same filter on MUFU approximations (decisions identical)
+    int cone_filter = 3;    // silhouette normal-cone test: 0 = the reference's libm chain, 1 = guard-banded sine-space filter on
+                            // correctly rounded sqrt/rcp, 2 = the same filter on MUFU approximations, 3 = 2 with the exact chain out of
+                            // line (decisions identical in all modes; 3 measured 52.3 vs 54.6 ms on C3: a 1768- instead of
+                            // 3648-instruction kernel)
     int sil_kernel = 1;     // silhouette per-lane kernel: 1 = warp-shared leaf queue + shared-memory stack (v4), 0 = per-lane parks (v3)
     int sil_nodes = 0;      // v4 kernel walks 1 = the 64 B compact records when the scene was built with "build.compact_nodes" (48-bit cone
                             // codes, exact cones fetched when undecided), 0 = the 96 B records.  Bit-identical results; measured SLOWER on
