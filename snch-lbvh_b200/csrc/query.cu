@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ 
 // With `radius` (silhouette star radii) the top 4 key bits are the radius octave relative to the batch extent, so the 32
 // queries a warp walks together also have similar search radii (a scheduling hint only: any key is correct).
 __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q, int stride, int dims, uint32_t n, const int *__restrict__ box,
-                                                    const float *__restrict__ radius, uint32_t *__restrict__ keys,
+                                                    const float *__restrict__ radius, int radius_desc, uint32_t *__restrict__ keys,
                                                     uint32_t *__restrict__ perm)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,9 +106,14 @@ __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q,
         const float ext = fmaxf(fmaxf(ord2f_q(box[3]) - ord2f_q(box[0]), ord2f_q(box[4]) - ord2f_q(box[1])),
                                 fmaxf(dims > 2 ? ord2f_q(box[5]) - ord2f_q(box[2]) : 0.0f, FLT_MIN));
         const float r = __ldg(radius + i);
-        const int oct = (int)((__float_as_uint(fmaxf(r, 0.0f)) >> 23) & 0xFFu) - (int)((__float_as_uint(ext) >> 23) & 0xFFu); // floor(log2(r/ext))
-        const uint32_t cls = (uint32_t)min(max(oct + 13, 0), 15); // >= 4 x extent (incl. +inf) -> 15; NaN -> 0
-        code = (cls << 26) | (code >> 4);
+        // radius class = floor(2^e * log2(r / extent)) read off the float bit patterns (exponent + top e mantissa bits)
+        const int e = radius_desc > 1 ? radius_desc - 1 : 0; // extra class bits beyond the octave
+        const int oct = (int)((__float_as_uint(fmaxf(r, 0.0f)) >> (23 - e)) & (0xFFu << e | ((1u << e) - 1u))) -
+                        (int)((__float_as_uint(ext) >> (23 - e)) & (0xFFu << e | ((1u << e) - 1u)));
+        const int top = (16 << e) - 1;
+        uint32_t cls = (uint32_t)min(max(oct + (13 << e), 0), top); // >= 4 x extent (incl. +inf) -> top; NaN -> 0
+        if (radius_desc) cls = (uint32_t)top - cls; // largest search radii (the most expensive walks) first: the kernel's tail is then made of cheap queries
+        code = (cls << (26 - e)) | (code >> (4 + e));
     }
     keys[i] = code;
     perm[i] = i;
@@ -1266,7 +1271,7 @@ uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
 
 // Lays the scratch out and, for batches worth ordering, produces the Morton permutation.  *perm_out = nullptr otherwise.
 int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n, unsigned char *scratch,
-                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims)
+                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims, int radius_desc)
 {
     SNCH_CUDA(cudaMemsetAsync(scratch, 0, t.feed ? kScratchHeader : 64, st));
     *counter_out = reinterpret_cast<unsigned long long *>(scratch);
@@ -1282,7 +1287,7 @@ int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride
     const unsigned g = (n + 255) / 256;
     k_query_box_init<<<1, 32, 0, st>>>(box);
     k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, dims, n, box);
-    k_query_keys<<<g, 256, 0, st>>>(pts, stride, dims, n, box, radius, keys, perm);
+    k_query_keys<<<g, 256, 0, st>>>(pts, stride, dims, n, box, radius, radius_desc, keys, perm);
     int bits = t.sort_bits < 8 ? 8 : (t.sort_bits > 30 ? 30 : t.sort_bits);
     const int sort_launches = radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
     if (qc) qc->launches += 3 + sort_launches;
@@ -1362,7 +1367,8 @@ int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, 
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, true, q, 3, (t.packet & 2) ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
+    const int rc = prepare_batch(t, true, q, 3, ((t.packet & 2) || t.sort_radius) ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3,
+                                 (!(t.packet & 2) && t.sort_radius >= 2) ? t.sort_radius - 1 : 0);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);
     if (perm && (t.packet & 2))

@@ -131,7 +131,8 @@ SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane,
 // Lays the per-batch scratch out (query_scratch_bytes) and, for batches worth ordering, produces the Morton permutation of the
 // query points (`dims` = 2 or 3 coordinates at pts[stride * i]).  *perm_out = nullptr otherwise.            query.cu
 int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n, unsigned char *scratch,
-                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims = 3);
+                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims = 3,
+                  int radius_desc = 0);
 
 // grid of a persistent kernel: SMs x resident CTAs, or fewer when the batch has fewer chunks than that
 template <typename K> static inline unsigned persistent_grid(K kernel, const QueryTuning &t, uint32_t n)

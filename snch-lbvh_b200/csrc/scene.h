@@ -14,6 +14,9 @@ struct QueryTuning
 {
     int sort_min_n = 16384; // batches at least this large are visited in Morton order of the query points (0 = never)
     int sort_bits = 24;     // Morton key bits the ordering sorts on (top bits of the 30-bit code)
+    int sort_radius = 2;    // bounded silhouette batches (per-lane kernels): 1 = order by search-radius octave first, then Morton code;
+                            // 2 = the same with the largest radii first (longest walks start first, the tail is made of cheap queries);
+                            // 3, 4 = largest first with 2 / 4 classes per octave
     int sort_rays = 0;      // also order ray batches by origin (off: random directions decorrelate the paths anyway)
     int packet = 1;         // warp-cooperative traversal of ordered batches: bit 0 closest point, bit 1 silhouette
     int cone_filter = 3;    // silhouette normal-cone test: 0 = the reference's libm chain, 1 = guard-banded sine-space filter on
