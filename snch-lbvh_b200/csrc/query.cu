@@ -670,12 +670,19 @@ constexpr int kSStack = 12;
 constexpr int kLeafQueue = 128;  // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
 constexpr int kLeafFlushAt = 32;
 constexpr uint32_t kCoopMaxPayload = 1u << 27; // (first_edge << 2 | count) must leave 5 bits for the owner lane
+constexpr uint32_t kCoopHintFlag = 1u << 26;   // kSeed: bit 26 marks a hint entry, payloads keep 26 bits
+//   * kSeed: a lane remembers the leaf that answered its previous query (its neighbour in the ordered batch) and queues that
+//     leaf as a HINT when it takes a new query.  A hint distance only tightens the pruning bound; the answer is still the
+//     minimum over edges the walk itself reaches, and if the walk ends without confirming the hint (no reached edge within
+//     it — the reference's cone chain does not lead to that leaf) the query is walked again from the answer found so far
+//     without a hint.  So the result is the unseeded one; measured: 301 -> ~222 node visits per answered query if the hint
+//     were perfect (tools/dbg notes in DESIGN.md).
 //   * kCompact: the walk reads the 64 B CNode (boxes + split + 48-bit cone codes: 2 sectors) instead of the 96 B SNode.
 //     profiles/r01j: the kernel is bound by the L1 data pipe (88% of peak), which serves a divergent warp one 32 B sector per
 //     cycle, and 3 of every ~4 sectors are node records.  The exact cones are fetched only for the tests the codes leave
 //     undecided (cone_test_compact); a leaf child carries its sorted position and its edge payload comes from edge_off[].
 __device__ unsigned long long g_sil_stats[8]; // "query.sil_stats" instrumentation (kStats instantiation only)
-template <int kFilter, bool kCompact, bool kStats>
+template <int kFilter, bool kCompact, bool kStats, bool kSeed>
 __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter,
@@ -685,18 +692,28 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     __shared__ uint32_t s_queue[kQueryThreads / 32][kLeafQueue];
     __shared__ uint32_t s_qcount[kQueryThreads / 32];
     __shared__ uint32_t s_result[kQueryThreads];
+    __shared__ uint32_t s_hint[kSeed ? kQueryThreads : 1], s_seed[kSeed ? kQueryThreads : 1];
+    constexpr uint32_t kPayloadMask = (kSeed ? kCoopHintFlag : kCoopMaxPayload) - 1u;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t *queue = s_queue[wid];
     Feeder fd{0u, 0u, false};
-    const RegionFeed rf{counter + kScratchCounters / 8, feed_mode ? feed_regions : 0u, feed_per,
-                        feed_mode == 1 ? blockIdx.x % (feed_regions ? feed_regions : 1u) : smid() % (feed_regions ? feed_regions : 1u)};
+    const RegionFeed rf{counter + kScratchCounters / 8, (feed_mode & 255) ? feed_regions : 0u, feed_per,
+                        (feed_mode & 255) == 1 ? blockIdx.x % (feed_regions ? feed_regions : 1u) : smid() % (feed_regions ? feed_regions : 1u)};
     StackEntry lstk[kStackDepth - kSStack];
     int sp = 0;
     V3 p = V3{0.f, 0.f, 0.f};
     bool flip = false, found = false, busy = false, pend = false;
     float best = INFINITY, best2 = INFINITY;
+    float ans = INFINITY;    // kSeed: smallest distance the walk itself has reached (best = min(ans, hint) is only the pruning bound)
+    uint32_t seed = kNone;   // kSeed: queue payload of the leaf that answered this lane's previous query
+    bool hinted = false;     // kSeed: a hint has lowered `best` below what the walk itself has reached
     uint32_t slot = kNone, node = kNone;
     s_result[threadIdx.x] = kNone;
+    if (kSeed)
+    {
+        s_hint[threadIdx.x] = kNone;
+        s_seed[threadIdx.x] = kNone;
+    }
     if (lane == 0) s_qcount[wid] = 0;
     __syncwarp();
     for (;;)
@@ -715,7 +732,9 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 const float ox = __shfl_sync(kFull, p.x, owner), oy = __shfl_sync(kFull, p.y, owner), oz = __shfl_sync(kFull, p.z, owner);
                 float ob = __shfl_sync(kFull, best, owner);
                 const bool oflip = __shfl_sync(kFull, (int)flip, owner) != 0;
-                uint32_t payload = ent & (kCoopMaxPayload - 1u);
+                const uint32_t raw = ent & kPayloadMask;
+                const bool is_hint = kSeed && (ent & kCoopHintFlag) != 0;
+                uint32_t payload = raw;
                 if (kCompact) payload = mine ? __ldg(sv.edge_off + payload) : 0u; // queue entries carry the sorted leaf position
                 const uint32_t first = payload >> 2, cnt = payload & 3u;
                 const V3 op = V3{ox, oy, oz};
@@ -739,7 +758,16 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                         hit = true;
                     }
                 }
-                if (hit) atomicMin(&s_result[(wid << 5) + owner], __float_as_uint(ob)); // distances are >= +0: uint order = float order
+                if (hit)
+                { // distances are >= +0: uint order = float order
+                    const uint32_t nb = __float_as_uint(ob);
+                    if (is_hint) atomicMin(&s_hint[(wid << 5) + owner], nb);
+                    else
+                    {
+                        const uint32_t old = atomicMin(&s_result[(wid << 5) + owner], nb);
+                        if (kSeed && nb <= old) s_seed[(wid << 5) + owner] = raw; // (racy between two improving lanes: any of them is a usable seed)
+                    }
+                }
                 __syncwarp();
             }
             const uint32_t rb = s_result[threadIdx.x];
@@ -752,7 +780,27 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                     best2 = v * v;
                     found = true;
                 }
+                if (kSeed && v <= ans)
+                {
+                    ans = v;
+                    seed = s_seed[threadIdx.x];
+                }
                 s_result[threadIdx.x] = kNone;
+            }
+            if (kSeed)
+            {
+                const uint32_t hb = s_hint[threadIdx.x];
+                if (hb != kNone)
+                {
+                    const float v = __uint_as_float(hb);
+                    if (node != kNone && v < best)
+                    { // a hint that arrives after the walk has ended changes nothing: that walk used only confirmed bounds
+                        best = v;
+                        best2 = v * v;
+                        hinted = true;
+                    }
+                    s_hint[threadIdx.x] = kNone;
+                }
             }
             pend = false;
             if (lane == 0) s_qcount[wid] = 0;
@@ -761,8 +809,19 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         // ---- 2. finished walks hand in their answer; idle lanes take the next query
         if (busy && node == kNone)
         {
-            out_dist[slot] = found ? best : INFINITY;
-            busy = false;
+            if (kSeed && hinted && ans > best)
+            { // the hint was never confirmed by an edge the walk reached: walk again, bounded by what it did reach
+                best = found ? ans : (rmax ? __ldg(rmax + slot) : INFINITY);
+                best2 = best * best;
+                hinted = false;
+                sp = 0;
+                node = 0;
+            }
+            else
+            {
+                out_dist[slot] = found ? (kSeed ? ans : best) : INFINITY;
+                busy = false;
+            }
         }
         const unsigned idle = __ballot_sync(kFull, !busy);
         if (idle)
@@ -779,6 +838,17 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 busy = true;
                 sp = 0;
                 node = 0;
+                if (kSeed)
+                {
+                    ans = INFINITY;
+                    hinted = false;
+                    if (seed != kNone)
+                    {
+                        const uint32_t pos = atomicAdd(&s_qcount[wid], 1u);
+                        queue[pos] = ((uint32_t)lane << 27) | kCoopHintFlag | seed;
+                        pend = true;
+                    }
+                }
             }
             if (fd.exhausted && __all_sync(kFull, !busy)) break;
         }
@@ -825,8 +895,8 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 { // undecided by the codes: the exact cones of this node
                     ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
                     ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
-                    if (t0 == 2) t0 = (d.w >= 0.0f) && cone_test<2>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-                    if (t1 == 2) t1 = (f.x >= 0.0f) && cone_test<2>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+                    if (t0 == 2) t0 = (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+                    if (t1 == 2) t1 = (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
                 }
                 h0 = t0 != 0;
                 h1 = t1 != 0;
@@ -859,7 +929,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 if (r & kLeafFlag)
                 {
                     const uint32_t pos = atomicAdd(&s_qcount[wid], 1u);
-                    queue[pos] = ((uint32_t)lane << 27) | (r & (kCoopMaxPayload - 1u));
+                    queue[pos] = ((uint32_t)lane << 27) | (r & kPayloadMask);
                     pend = true;
                 }
                 else if (next == kNone) next = r;
@@ -1304,23 +1374,29 @@ static void launch_silhouette_lanes_f(const SceneView &v, const QueryTuning &t, 
 {
     const bool coop = t.sil_kernel != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopMaxPayload;
     // region feed: per CTA (1) or per SM (2); `per` is a whole number of chunks so regions never share a chunk
-    const unsigned grid = persistent_grid(k_silhouette_coop<kFilter, false, false>, t, n);
+    const unsigned grid = persistent_grid(k_silhouette_coop<kFilter, false, false, false>, t, n);
     int sms = 1;
     {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    uint32_t regions = t.feed == 1 ? grid : (t.feed == 2 ? (uint32_t)sms : 0u);
+    uint32_t regions = (t.feed & 255) == 1 ? grid : ((t.feed & 255) == 2 ? (uint32_t)sms : 0u);
     if (regions > kMaxRegions) regions = kMaxRegions;
-    const int fm = regions ? t.feed : 0;
+    const int fm = (regions ? (t.feed & 255) : 0) | (t.feed & ~255);
     const uint32_t per = regions ? (uint32_t)((((uint64_t)n + regions - 1) / regions + kChunk - 1) / kChunk * kChunk) : 0u;
-    if (coop && kFilter == 2 && t.sil_nodes != 0 && v.cnode && t.sil_stats)
-        k_silhouette_coop<2, true, true><<<persistent_grid(k_silhouette_coop<2, true, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
-    else if (coop && kFilter == 2 && t.sil_nodes != 0 && v.cnode)
-        k_silhouette_coop<2, true, false><<<persistent_grid(k_silhouette_coop<2, true, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
+    constexpr int kCF = kFilter >= 2 ? kFilter : 2; // the compact walk exists for the MUFU filter modes only
+    const bool seeded = t.sil_seed != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopHintFlag && (!v.cnode || v.n_tris < kCoopHintFlag);
+    if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode && t.sil_stats)
+        k_silhouette_coop<kCF, true, true, false><<<persistent_grid(k_silhouette_coop<kCF, true, true, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
+    else if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode && seeded)
+        k_silhouette_coop<kCF, true, false, true><<<persistent_grid(k_silhouette_coop<kCF, true, false, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
+    else if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode)
+        k_silhouette_coop<kCF, true, false, false><<<persistent_grid(k_silhouette_coop<kCF, true, false, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
+    else if (coop && seeded)
+        k_silhouette_coop<kFilter, false, false, true><<<persistent_grid(k_silhouette_coop<kFilter, false, false, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
     else if (coop)
-        k_silhouette_coop<kFilter, false, false><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
+        k_silhouette_coop<kFilter, false, false, false><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
     else k_silhouette<kFilter><<<persistent_grid(k_silhouette<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
 }
 static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,

@@ -30,6 +30,8 @@ struct QueryTuning
     int sil_stats = 0;      // instrumented instantiation of the compact kernel: counters "query.sil_stats.0..7" (slow; analysis only)
     int feed = 0;           // v4 silhouette kernel work distribution: 0 = one global chunk counter, 1 = a contiguous region of the ordered
                             // batch per CTA, 2 = per SM (warps sharing an L1 walk neighbouring queries; dry regions are stolen from)
+    int sil_seed = 1;       // v4 silhouette kernel: queue the leaf that answered the lane's previous query as a pruning hint (results unchanged:
+                            // an unconfirmed hint makes the query walk again without one)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
