@@ -443,7 +443,7 @@ def _run():
         kernel_ms = trav_ms / max(trav_launches, 1)  # the traversal kernel alone (CUDA events on its stream, inside the timed region)
         achieved = b_q * n / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "snch::k_silhouette_coop<2>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / statistics.mean(step_ms),
+                    "kernel": "snch::k_silhouette_coop<3, 0, 0, 1>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / statistics.mean(step_ms),
                     "algorithmic_bytes_per_query": b_q, "must_visit_internal": V, "must_visit_leaves": Lv,
                     "peak_source": peak_src,
                     "note": "divergent gather over SNode 96 MB + LEdge 96 MB; the kernel is issue/L1-bound, not DRAM-bound: traffic << algorithmic "
