@@ -450,7 +450,8 @@ def _run():
                             "bytes because records are re-read from L1/L2 (hit rates in profiles/)"}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            roofline["traffic"] = json.load(open(tp)).get("k_silhouette_bytes_per_launch")
+            tj = json.load(open(tp))
+            roofline["traffic"] = tj.get("k_silhouette_coop_bytes_per_launch", tj.get("k_silhouette_bytes_per_launch"))
 
     extra = {"build_ms": stats["build_ms"], "adjacency_ms": stats["adjacency_ms"], "arena_bytes": stats["arena_bytes"],
              "replicate_ms": replicate_ms if world > 1 else 0.0, "scene_setup_wall_ms": (t1 - t0) * 1e3,
