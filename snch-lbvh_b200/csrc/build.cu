@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(128) k_refit(BuildCtx c)
 // parent's range leaves the interval ("escapes": the roots of the maximal in-CTA subtrees) are appended to a list that
 // k_refit_top finishes with the global flags and fences of the v1 climb.  Every merge is the same pure function of the same
 // two children as in v1, so all products are bit-identical (tests/test_gpu_build.py).
-constexpr int kRefitLeaves = 256;
+constexpr int kRefitLeaves = 128;
 struct RefitShared
 {
     float f[11][2 * kRefitLeaves]; // lo.xyz hi.xyz axis.xyz half_angle radius, by local id: leaves [0,B), internal B + (i - b0)
@@ -581,7 +581,7 @@ SNCH_DI void sh_get(const RefitShared &sh, uint32_t id, Box &b, Cone &cn)
     cn.half_angle = sh.f[9][id];
     cn.radius = sh.f[10][id];
 }
-__global__ void __launch_bounds__(kRefitLeaves, 4) k_refit_coop(BuildCtx c)
+__global__ void __launch_bounds__(kRefitLeaves, 8) k_refit_coop(BuildCtx c)
 {
     __shared__ RefitShared sh;
     constexpr uint32_t B = kRefitLeaves;
@@ -931,7 +931,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
         k_refit_coop<<<ctas, kRefitLeaves, 0, stream>>>(c);
         if (nT > 1)
         {
-            k_refit_top<<<ctas < 8 ? 1 : ctas / 8, 128, 0, stream>>>(c); // 16 threads per CTA of the pass above (~12 escapes each); grid-stride beyond
+            k_refit_top<<<ctas < 8 ? 1 : ctas / 8, 128, 0, stream>>>(c); // one thread per escape of the pass above (~12 per CTA); grid-stride beyond
             launches += 1;
         }
     }
