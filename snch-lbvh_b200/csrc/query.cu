@@ -308,13 +308,17 @@ __global__ void __launch_bounds__(kQueryThreads)
                 float4 t0, t1, t2, t3;
                 ld256(tp, t0, t1);
                 ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
-                float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
-                dist *= dist; // the reference squares the distance it got back (query.cuh:284-285)
-                if (w && dist < best2)
-                {
-                    best2 = dist;
-                    best = __float_as_uint(t0.w);
-                    best_leaf = k;
+                if (w)
+                { // only the lanes that need this triangle: the Voronoi-region branches of the test then split the warp over the
+                  // regions of THOSE lanes, not over the regions of all 32 query points
+                    float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+                    dist *= dist; // the reference squares the distance it got back (query.cuh:284-285)
+                    if (dist < best2)
+                    {
+                        best2 = dist;
+                        best = __float_as_uint(t0.w);
+                        best_leaf = k;
+                    }
                 }
             }
             const bool w0 = in && !(r0 & kLeafFlag) && m0 < best2;
