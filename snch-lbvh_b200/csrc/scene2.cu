@@ -593,6 +593,8 @@ struct snch_scene2
     int collision = 0;
     float build_ms = 0.0f;
     snch::QueryTuning tuning;
+    cudaMemPool_t pool = nullptr; // per-call scratch and staging: stream-ordered, freed blocks stay cached (no driver allocation per call)
+    std::mutex mu;
     void free_device()
     {
         for (void *p : {(void *)verts, (void *)sil, (void *)lines, (void *)nodes, (void *)aabbs, (void *)cones, (void *)sorted_idx, (void *)morton,
@@ -635,9 +637,25 @@ template <typename T> int dev_alloc(T **p, uint64_t count)
 
 // Host or device buffers of one batch: host arrays are staged through stream-ordered device allocations and copied back
 // before the call returns (the call then synchronises `st`); device arrays are used in place.
+int ensure_pool2(snch_scene2 *s)
+{
+    std::lock_guard<std::mutex> lock(s->mu);
+    if (s->pool) return SNCH_OK;
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof props);
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = s->device;
+    SNCH_CUDA(cudaMemPoolCreate(&s->pool, &props));
+    uint64_t keep = ~0ull;
+    SNCH_CUDA(cudaMemPoolSetAttribute(s->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return SNCH_OK;
+}
 struct Stage2
 {
     cudaStream_t st;
+    cudaMemPool_t pool;
     bool host = false, device = false;
     int status = SNCH_OK;
     struct Out
@@ -647,7 +665,7 @@ struct Stage2
     };
     std::vector<void *> owned;
     std::vector<Out> outs;
-    explicit Stage2(cudaStream_t s) : st(s) {}
+    Stage2(cudaStream_t s, cudaMemPool_t p) : st(s), pool(p) {}
     void note(Kind2 k)
     {
         if (k == K2_HOST) host = true;
@@ -659,7 +677,7 @@ struct Stage2
         note(k);
         if (k != K2_HOST || status != SNCH_OK) return p;
         void *d = nullptr;
-        if (cudaMallocAsync(&d, bytes ? bytes : 16, st) != cudaSuccess)
+        if (cudaMallocFromPoolAsync(&d, bytes ? bytes : 16, pool, st) != cudaSuccess)
         {
             cudaGetLastError();
             set_error("out of device memory for the staged query batch");
@@ -676,7 +694,7 @@ struct Stage2
         note(k);
         if (k != K2_HOST || status != SNCH_OK) return p;
         void *d = nullptr;
-        if (cudaMallocAsync(&d, bytes ? bytes : 16, st) != cudaSuccess)
+        if (cudaMallocFromPoolAsync(&d, bytes ? bytes : 16, pool, st) != cudaSuccess)
         {
             cudaGetLastError();
             set_error("out of device memory for the staged query batch");
@@ -706,9 +724,9 @@ struct Scratch2
 {
     cudaStream_t st;
     unsigned char *p = nullptr;
-    Scratch2(cudaStream_t s, uint64_t bytes) : st(s)
+    Scratch2(cudaStream_t s, cudaMemPool_t pool, uint64_t bytes) : st(s)
     {
-        if (cudaMallocAsync((void **)&p, bytes ? bytes : 256, st) != cudaSuccess)
+        if (cudaMallocFromPoolAsync((void **)&p, bytes ? bytes : 256, pool, st) != cudaSuccess)
         {
             cudaGetLastError();
             p = nullptr;
@@ -736,7 +754,8 @@ int check_ready(const snch_scene2 *s, uint64_t n, const char *what)
         set_error(std::string(what) + ": at most 2^32 - 2^20 queries per call");
         return SNCH_ERR_INVALID;
     }
-    return SNCH_OK;
+    DeviceGuard g(s->device);
+    return ensure_pool2(const_cast<snch_scene2 *>(s)); // the pool is a cache, not scene state
 }
 } // namespace
 } // namespace snch
@@ -779,6 +798,11 @@ extern "C" int snch_scene2_destroy(snch_scene2 *s)
     {
         DeviceGuard g(s->device);
         s->free_device();
+        if (s->pool)
+        {
+            cudaDeviceSynchronize();
+            cudaMemPoolDestroy(s->pool);
+        }
     }
     delete s;
     return SNCH_OK;
@@ -1001,7 +1025,7 @@ extern "C" int snch_closest_point_batch2(const snch_scene2 *s, const float *poin
     }
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    Stage2 sg(st);
+    Stage2 sg(st, s->pool);
     const float *q = sg.in(points_xy, n * 8);
     uint32_t *idx = sg.out(out_index, n * 4);
     float *dist = sg.out(out_distance, n * 4);
@@ -1014,7 +1038,7 @@ extern "C" int snch_closest_point_batch2(const snch_scene2 *s, const float *poin
     if (s->n_segs == 0) k2_fill_empty<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, idx, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
     {
-        Scratch2 scr(st, query_scratch_bytes(n, s->tuning));
+        Scratch2 scr(st, s->pool, query_scratch_bytes(n, s->tuning));
         if (!scr.p)
         {
             set_error("out of device memory for the per-call query scratch");
@@ -1041,7 +1065,7 @@ extern "C" int snch_closest_silhouette_batch2(const snch_scene2 *s, const float 
     }
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    Stage2 sg(st);
+    Stage2 sg(st, s->pool);
     const float *q = sg.in(points_xy, n * 8);
     const uint8_t *fl = sg.in(flip, n);
     const float *rm = sg.in(r_max, n * 4);
@@ -1055,7 +1079,7 @@ extern "C" int snch_closest_silhouette_batch2(const snch_scene2 *s, const float 
     if (s->n_segs == 0) k2_fill_empty<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, nullptr, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
     {
-        Scratch2 scr(st, query_scratch_bytes(n, s->tuning));
+        Scratch2 scr(st, s->pool, query_scratch_bytes(n, s->tuning));
         if (!scr.p)
         {
             set_error("out of device memory for the per-call query scratch");
@@ -1083,7 +1107,7 @@ extern "C" int snch_intersect_batch2(const snch_scene2 *s, const float *origins_
     }
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    Stage2 sg(st);
+    Stage2 sg(st, s->pool);
     const float *o = sg.in(origins_xy, n * 8);
     const float *d = sg.in(dirs_xy, n * 8);
     const float *tm = sg.in(t_max, n * 4);
@@ -1098,7 +1122,7 @@ extern "C" int snch_intersect_batch2(const snch_scene2 *s, const float *origins_
     if (s->n_segs == 0) k2_fill_empty<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, nullptr, nullptr, hits, found, nullptr, nullptr, nullptr);
     else
     {
-        Scratch2 scr(st, query_scratch_bytes(n, s->tuning));
+        Scratch2 scr(st, s->pool, s->tuning.sort_rays != 0 ? query_scratch_bytes(n, s->tuning) : query_scratch_bytes(0, s->tuning)); // unordered: header only
         if (!scr.p)
         {
             set_error("out of device memory for the per-call query scratch");
@@ -1130,7 +1154,7 @@ extern "C" int snch_sample_in_sphere_batch2(const snch_scene2 *s, const float *c
     }
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
-    Stage2 sg(st);
+    Stage2 sg(st, s->pool);
     const float *sp = sg.in(circles_xyr, n * 12);
     const float *rn = sg.in(rnd2, n * 8);
     int32_t *idx = sg.out(out_index, n * 4);
