@@ -244,6 +244,101 @@ __global__ void __launch_bounds__(kQueryThreads)
 // against it, and __ballot_sync decides which children any lane still needs.  The traversal stack is per warp (node +
 // lane mask, in shared memory); per-lane state is just the running best.  Lanes only ever skip work they could not use
 // (mindist >= their best / their cone test failed), so each lane's result is exactly what its own traversal returns.
+// SOLO WALK.  When only one lane of a packet still needs a subtree, walking it node by node keeps 31 lanes idle — and a query
+// that is (nearly) equidistant to a large part of the mesh (the centre of a sphere, the axis of a torus) needs tens of
+// thousands of nodes: 5.2 ms for ONE such query in the 64K-query config C1, whatever the size of the GPU.  The warp then walks
+// that subtree for that one query together: a shared stack of (node, key) entries, up to 32 popped per step, every lane opens
+// one node — both child boxes, leaf children tested at once — the survivors are pushed with warp-aggregated offsets and the
+// running best is the warp minimum.  The result is the minimum over the same triangles with the same distance function, so
+// the distance is the one the sequential walk returns (the index is an argmin, as everywhere: ties, Q3).
+constexpr int kSoloStack = 512;  // entries per warp; above kSoloStack - 128 the walk pops one entry per step (growth <= tree depth)
+SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, int owner, int lane, V3 p_lane, float &best2_lane, uint32_t &best_lane,
+                          uint32_t &best_leaf_lane)
+{
+    const V3 p = V3{__shfl_sync(kFull, p_lane.x, owner), __shfl_sync(kFull, p_lane.y, owner), __shfl_sync(kFull, p_lane.z, owner)};
+    float b2 = __shfl_sync(kFull, best2_lane, owner);
+    uint32_t bi = __shfl_sync(kFull, best_lane, owner), bl = __shfl_sync(kFull, best_leaf_lane, owner);
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) st[0] = StackEntry{root, 0.0f};
+    int sp = 1;
+    __syncwarp();
+    while (sp > 0)
+    {
+        const int take = sp > kSoloStack - 128 ? 1 : (sp < 32 ? sp : 32);
+        sp -= take;
+        StackEntry e = StackEntry{kNone, INFINITY};
+        if (lane < take) e = st[sp + lane];
+        __syncwarp(); // every popped entry is read before this step's pushes reuse the slots
+        uint32_t cand = 0xFFFFFFFFu, cand_i = kNone, cand_leaf = kNone; // squared distance as ordered bits (>= +0)
+        uint32_t pr0 = kNone, pr1 = kNone;
+        float pk0 = 0.0f, pk1 = 0.0f;
+        if (e.node != kNone && e.key < b2)
+        {
+            float4 a, b, c, d;
+            ld256(sv.bnode + e.node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.bnode + e.node) + 32, c, d);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
+            const bool far1 = m0 < m1; // the farther child is pushed first, so the nearer one is popped first
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const bool one = (ch == 0) == far1; // iteration 0: the farther child, iteration 1: the nearer child
+                const float m = one ? m1 : m0;
+                const uint32_t r = one ? r1 : r0;
+                if (!(m < b2)) continue;
+                if (r & kLeafFlag)
+                {
+                    const uint32_t k = r & ~kLeafFlag;
+                    const LTri *tp = sv.ltri + k;
+                    float4 t0, t1, t2, t3;
+                    ld256(tp, t0, t1);
+                    ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                    float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+                    dist *= dist;
+                    if (dist < b2 && __float_as_uint(dist) < cand)
+                    {
+                        cand = __float_as_uint(dist);
+                        cand_i = __float_as_uint(t0.w);
+                        cand_leaf = k;
+                    }
+                }
+                else if (pr0 == kNone)
+                {
+                    pr0 = r;
+                    pk0 = m;
+                }
+                else
+                {
+                    pr1 = r;
+                    pk1 = m;
+                }
+            }
+        }
+        const unsigned c1 = __ballot_sync(kFull, pr0 != kNone), c2 = __ballot_sync(kFull, pr1 != kNone);
+        const int off = sp + __popc(c1 & lt) + __popc(c2 & lt);
+        if (pr0 != kNone) st[off] = StackEntry{pr0, pk0};
+        if (pr1 != kNone) st[off + 1] = StackEntry{pr1, pk1};
+        sp += __popc(c1) + __popc(c2);
+        const uint32_t mn = __reduce_min_sync(kFull, cand);
+        if (mn != 0xFFFFFFFFu)
+        { // some lane improved the bound (cand < b2 by construction)
+            const int wl = __ffs(__ballot_sync(kFull, cand == mn)) - 1;
+            b2 = __uint_as_float(mn);
+            bi = __shfl_sync(kFull, cand_i, wl);
+            bl = __shfl_sync(kFull, cand_leaf, wl);
+        }
+        __syncwarp();
+    }
+    if (lane == owner)
+    {
+        best2_lane = b2;
+        best_lane = bi;
+        best_leaf_lane = bl;
+    }
+}
+
 struct PacketStack
 {
     uint2 e[kStackDepth];
@@ -254,8 +349,10 @@ __global__ void __launch_bounds__(kQueryThreads)
                      float *__restrict__ out_dist, unsigned long long *counter, int use_seed)
 {
     __shared__ PacketStack s_stack[kQueryThreads / 32];
+    __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStack];
     const int lane = threadIdx.x & 31;
     uint2 *stk = s_stack[threadIdx.x >> 5].e;
+    StackEntry *solo = s_solo[threadIdx.x >> 5];
     uint32_t best_leaf = kNone;
     for (;;)
     {
@@ -289,6 +386,16 @@ __global__ void __launch_bounds__(kQueryThreads)
         int sp = 0;
         for (;;)
         {
+            if (use_seed < 4 && (mask & (mask - 1u)) == 0u)
+            { // one lane left on this subtree: the warp walks it for that lane (solo_closest)
+                solo_closest(sv, solo, node, __ffs(mask) - 1, lane, p, best2, best, best_leaf);
+                if (sp == 0) break;
+                --sp;
+                const uint2 e = stk[sp];
+                node = e.x;
+                mask = e.y;
+                continue;
+            }
             float4 a, b, c, d;
             ld256(sv.bnode + node, a, b);
             ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
@@ -351,6 +458,56 @@ __global__ void __launch_bounds__(kQueryThreads)
         {
             out_idx[slot] = best;
             out_dist[slot] = sqrtf(best2);
+        }
+    }
+}
+
+// One query per WARP, walked with solo_closest from the root.  For batches too small to fill the machine with packets the
+// run time is the critical path of the most expensive query (config C1, 64K queries on a sphere: 5.2 ms for the points near
+// the centre, to which every triangle is equally near); 32 lanes on one query shorten exactly that path.
+__global__ void __launch_bounds__(kQueryThreads)
+    k_closest_wide(SceneView sv, const float *__restrict__ q, const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ out_idx,
+                   float *__restrict__ out_dist, unsigned long long *counter, int use_seed)
+{
+    __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStack];
+    const int lane = threadIdx.x & 31;
+    StackEntry *solo = s_solo[threadIdx.x >> 5];
+    uint32_t best_leaf = kNone;
+    constexpr unsigned long long kRun = 4; // consecutive (neighbouring) queries per draw
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, kRun);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        for (unsigned long long s = base; s < base + kRun && s < n; ++s)
+        {
+            const uint32_t slot = perm ? __ldg(perm + s) : (uint32_t)s;
+            const V3 p = load_point(q, slot); // every lane holds the query
+            float best2 = INFINITY;
+            uint32_t best = kNone;
+            if (use_seed && best_leaf != kNone)
+            {
+                const LTri *tp = sv.ltri + best_leaf;
+                float4 t0, t1, t2, t3;
+                ld256(tp, t0, t1);
+                ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
+                dist *= dist;
+                if (dist < INFINITY)
+                {
+                    best2 = dist;
+                    best = __float_as_uint(t0.w);
+                }
+                else best_leaf = kNone;
+            }
+            solo_closest(sv, solo, 0u, 0, lane, p, best2, best, best_leaf);
+            best_leaf = __shfl_sync(kFull, best_leaf, 0);
+            if (lane == 0)
+            {
+                out_idx[slot] = best;
+                out_dist[slot] = sqrtf(best2);
+            }
         }
     }
 }
@@ -1427,7 +1584,10 @@ int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uin
     const int rc = prepare_batch(t, true, q, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);
-    if (perm && (t.packet & 1))
+    if (n < (uint64_t)t.wide_max_n)
+        k_closest_wide<<<persistent_grid(k_closest_wide, t, (uint32_t)(n < (1u << 26) ? n * 16 : n)), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx,
+                                                                                                                        dist, counter, t.seed);
+    else if (perm && (t.packet & 1))
         k_closest_packet<<<persistent_grid(k_closest_packet, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist,
                                                                                                    counter, t.seed);
     else
@@ -1551,7 +1711,10 @@ int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers
     if (rc != SNCH_OK) return rc;
     {
         TraversalTimer tt(qc, st);
-        if (perm && (t.packet & 1))
+        if (m < (uint32_t)t.wide_max_n)
+            k_closest_wide<<<persistent_grid(k_closest_wide, t, m < (1u << 26) ? m * 16 : m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index,
+                                                                                                                  d_closest, counter, t.seed);
+        else if (perm && (t.packet & 1))
             k_closest_packet<<<persistent_grid(k_closest_packet, t, m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index, d_closest,
                                                                                                counter, t.seed);
         else

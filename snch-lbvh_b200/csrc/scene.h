@@ -32,6 +32,8 @@ struct QueryTuning
                             // batch per CTA, 2 = per SM (warps sharing an L1 walk neighbouring queries; dry regions are stolen from)
     int sil_seed = 1;       // v4 silhouette kernel: queue the leaf that answered the lane's previous query as a pruning hint (results unchanged:
                             // an unconfirmed hint makes the query walk again without one)
+    int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical
+                            // path of pathological queries in batches too small to fill the machine; 0 = never)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
