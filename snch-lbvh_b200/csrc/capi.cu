@@ -828,6 +828,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.sort_radius") t.sort_radius = (int)value;
     else if (k == "query.sil_seed") t.sil_seed = (int)value;
     else if (k == "query.wide_max_n") t.wide_max_n = (int)value;
+    else if (k == "query.wide_max_n_sil") t.wide_max_n_sil = (int)value;
     else if (k == "query.sil_nodes") t.sil_nodes = (int)value;
     else if (k == "query.sil_stats") t.sil_stats = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;

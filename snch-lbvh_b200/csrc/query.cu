@@ -1121,6 +1121,127 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     }
 }
 
+// The same cooperative walk for the silhouette query: every lane opens one node of ONE query (both child boxes, the
+// reference's per-child cone test, the edges of leaf children), survivors are pushed with warp-aggregated offsets, the bound
+// is the warp minimum.  The answer is the minimum over the silhouette edges of the leaves the reference's predicate chain
+// reaches, which does not depend on the order of the walk.  Used for batches too small to fill the machine with per-lane
+// walks (k_silhouette_wide).
+template <int kFilter>
+SNCH_DI float solo_silhouette(const SceneView &sv, StackEntry *st, int lane, V3 p, bool flip, float best)
+{
+    float best2 = best * best;
+    bool found = false;
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) st[0] = StackEntry{0u, 0.0f};
+    int sp = 1;
+    __syncwarp();
+    while (sp > 0)
+    {
+        const int take = sp > kSoloStack - 128 ? 1 : (sp < 32 ? sp : 32);
+        sp -= take;
+        StackEntry en = StackEntry{kNone, INFINITY};
+        if (lane < take) en = st[sp + lane];
+        __syncwarp();
+        uint32_t cand = 0xFFFFFFFFu; // distance as ordered bits (>= +0)
+        uint32_t pr0 = kNone, pr1 = kNone;
+        float pk0 = 0.0f, pk1 = 0.0f;
+        if (en.node != kNone && en.key <= best2)
+        {
+            float4 a, b, c, d, e, f;
+            ld256(sv.snode + en.node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.snode + en.node) + 32, c, d);
+            ld256(reinterpret_cast<const char *>(sv.snode + en.node) + 64, e, f);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
+            const bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+            const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+            const bool far1 = m0 < m1; // the farther child is pushed first, so the nearer one is popped first
+            float ob = best, ob2 = best2;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+            {
+                const bool one = (ch == 0) == far1;
+                if (!(one ? h1 : h0)) continue;
+                const float m = one ? m1 : m0;
+                const uint32_t r = one ? r1 : r0;
+                if (r & kLeafFlag)
+                {
+                    const uint32_t payload = r & ~kLeafFlag, first = payload >> 2, cnt = payload & 3u;
+                    for (uint32_t k = 0; k < cnt; ++k)
+                    { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
+                        float4 e0, e1, e2, e3;
+                        ld256(sv.ledge + first + k, e0, e1);
+                        ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
+                        const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
+                        V3 cp;
+                        const float dist = point_segment_distance(pa, pb, p, &cp);
+                        if (dist * dist > ob2) continue;
+                        bool is_sil = isnan(e1.z); // boundary edge
+                        if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
+                        if (is_sil && dist <= ob)
+                        {
+                            ob = dist;
+                            ob2 = dist * dist;
+                            cand = __float_as_uint(dist);
+                        }
+                    }
+                }
+                else if (pr0 == kNone)
+                {
+                    pr0 = r;
+                    pk0 = m;
+                }
+                else
+                {
+                    pr1 = r;
+                    pk1 = m;
+                }
+            }
+        }
+        const unsigned c1 = __ballot_sync(kFull, pr0 != kNone), c2 = __ballot_sync(kFull, pr1 != kNone);
+        const int off = sp + __popc(c1 & lt) + __popc(c2 & lt);
+        if (pr0 != kNone) st[off] = StackEntry{pr0, pk0};
+        if (pr1 != kNone) st[off + 1] = StackEntry{pr1, pk1};
+        sp += __popc(c1) + __popc(c2);
+        const uint32_t mn = __reduce_min_sync(kFull, cand);
+        if (mn != 0xFFFFFFFFu)
+        { // cand <= best by construction
+            best = __uint_as_float(mn);
+            best2 = best * best;
+            found = true;
+        }
+        __syncwarp();
+    }
+    return found ? best : INFINITY;
+}
+template <int kFilter>
+__global__ void __launch_bounds__(kQueryThreads)
+    k_silhouette_wide(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
+                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+{
+    __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStack];
+    const int lane = threadIdx.x & 31;
+    StackEntry *solo = s_solo[threadIdx.x >> 5];
+    constexpr unsigned long long kRun = 4;
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, kRun);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        for (unsigned long long s = base; s < base + kRun && s < n; ++s)
+        {
+            const uint32_t slot = perm ? __ldg(perm + s) : (uint32_t)s;
+            const V3 p = load_point(q, slot);
+            const bool flip = flipv ? (__ldg(flipv + slot) != 0) : false;
+            const float r = rmax ? __ldg(rmax + slot) : INFINITY;
+            const float ans = solo_silhouette<kFilter>(sv, solo, lane, p, flip, r);
+            if (lane == 0) out_dist[slot] = ans;
+        }
+    }
+}
+
 template <int kFilter>
 __global__ void __launch_bounds__(kQueryThreads)
     k_silhouette_packet(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
@@ -1546,6 +1667,12 @@ static void launch_silhouette_lanes_f(const SceneView &v, const QueryTuning &t, 
     if (regions > kMaxRegions) regions = kMaxRegions;
     const int fm = (regions ? (t.feed & 255) : 0) | (t.feed & ~255);
     const uint32_t per = regions ? (uint32_t)((((uint64_t)n + regions - 1) / regions + kChunk - 1) / kChunk * kChunk) : 0u;
+    if (n < (uint32_t)t.wide_max_n_sil)
+    {
+        k_silhouette_wide<kFilter><<<persistent_grid(k_silhouette_wide<kFilter>, t, n < (1u << 26) ? n * 16 : n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm,
+                                                                                                                                    n, dist, counter);
+        return;
+    }
     constexpr int kCF = kFilter >= 2 ? kFilter : 2; // the compact walk exists for the MUFU filter modes only
     const bool seeded = t.sil_seed != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopHintFlag && (!v.cnode || v.n_tris < kCoopHintFlag);
     if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode && t.sil_stats)

@@ -34,6 +34,7 @@ struct QueryTuning
                             // an unconfirmed hint makes the query walk again without one)
     int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical
                             // path of pathological queries in batches too small to fill the machine; 0 = never)
+    int wide_max_n_sil = 262144; // silhouette: the same for k_silhouette_wide (measured crossover 0.25-0.5M queries)
     int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.

@@ -188,7 +188,7 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
     d = meshes.unit_directions(n, seed=49)
     flip = (np.arange(n) % 3 == 0).astype(np.uint8)
     rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(n)).astype(np.float32)
-    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 2, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.sil_nodes": 0, "query.host_chunk": 1 << 23, "query.feed": 0, "query.sort_radius": 0, "query.sil_seed": 1, "query.wide_max_n": 0}
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 2, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.sil_nodes": 0, "query.host_chunk": 1 << 23, "query.feed": 0, "query.sort_radius": 0, "query.sil_seed": 1, "query.wide_max_n": 0, "query.wide_max_n_sil": 0}
 
     def run():
         idx, dist = sc.closest_point(q)
@@ -203,7 +203,7 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
         sel = np.nonzero(flip[:6000] == fl)[0]
         check_silhouette(base["sil"][sel], orc.silhouette(q[sel], bool(fl), nthreads=8), 2e-3)
     for kv in ({"query.packet": 0}, {"query.packet": 3}, {"query.packet": 2, "query.cone_filter": 0}, {"query.packet": 0, "query.cone_filter": 0}, {"query.sort_min_n": 0}, {"query.cone_filter": 0}, {"query.cone_filter": 1}, {"query.sil_kernel": 0}, {"query.sil_kernel": 0, "query.cone_filter": 1}, {"query.sil_kernel": 0, "query.cone_filter": 0},
-               {"query.sil_kernel": 1, "query.sort_min_n": 0}, {"query.cone_filter": 3}, {"query.wide_max_n": 1 << 30}, {"query.wide_max_n": 1 << 30, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.seed": 0}, {"query.seed": 5}, {"query.sil_seed": 0}, {"query.sil_seed": 0, "query.sort_min_n": 0}, {"query.sil_seed": 0, "query.sil_nodes": 1}, {"query.cone_filter": 3, "query.sil_nodes": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.feed": 1}, {"query.feed": 2}, {"query.feed": 2, "query.cone_filter": 3, "query.sort_min_n": 0}, {"query.sil_nodes": 1}, {"query.sil_nodes": 1, "query.sort_min_n": 0}, {"query.seed": 0}, {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
+               {"query.sil_kernel": 1, "query.sort_min_n": 0}, {"query.cone_filter": 3}, {"query.wide_max_n": 1 << 30}, {"query.wide_max_n_sil": 1 << 30}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 0}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 1, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.seed": 0}, {"query.seed": 5}, {"query.sil_seed": 0}, {"query.sil_seed": 0, "query.sort_min_n": 0}, {"query.sil_seed": 0, "query.sil_nodes": 1}, {"query.cone_filter": 3, "query.sil_nodes": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.feed": 1}, {"query.feed": 2}, {"query.feed": 2, "query.cone_filter": 3, "query.sort_min_n": 0}, {"query.sil_nodes": 1}, {"query.sil_nodes": 1, "query.sort_min_n": 0}, {"query.seed": 0}, {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
                {"query.host_chunk": 7001}, {"query.host_chunk": 0}, {"query.host_chunk": 500, "query.sort_min_n": 0},  # host-pointer pipeline
                {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0}):
         for k, val in {**defaults, **kv}.items():
