@@ -244,13 +244,16 @@ __global__ void __launch_bounds__(kQueryThreads)
 // against it, and __ballot_sync decides which children any lane still needs.  The traversal stack is per warp (node +
 // lane mask, in shared memory); per-lane state is just the running best.  Lanes only ever skip work they could not use
 // (mindist >= their best / their cone test failed), so each lane's result is exactly what its own traversal returns.
-// SOLO WALK.  When only one lane of a packet still needs a subtree, walking it node by node keeps 31 lanes idle — and a query
-// that is (nearly) equidistant to a large part of the mesh (the centre of a sphere, the axis of a torus) needs tens of
-// thousands of nodes: 5.2 ms for ONE such query in the 64K-query config C1, whatever the size of the GPU.  The warp then walks
-// that subtree for that one query together: a shared stack of (node, key) entries, up to 32 popped per step, every lane opens
-// one node — both child boxes, leaf children tested at once — the survivors are pushed with warp-aggregated offsets and the
-// running best is the warp minimum.  The result is the minimum over the same triangles with the same distance function, so
-// the distance is the one the sequential walk returns (the index is an argmin, as everywhere: ties, Q3).
+// COOPERATIVE WALK of one query by a whole warp.  A query that is (nearly) equidistant to a large part of the mesh (the centre
+// of a sphere, the axis of a torus) needs tens of thousands of nodes; walked by one lane, or by a packet it shares with 31
+// neighbours that need the same nodes, that is a 5 ms critical path — the whole run time of a batch too small to fill the
+// machine (config C1: 64K queries), whatever the size of the GPU.  Here the warp keeps a shared stack of (node, key) entries, pops
+// up to 32 per step, every lane opens one node — both child boxes, leaf children tested at once — the survivors are pushed with
+// warp-aggregated offsets and the running best is the warp minimum.  The result is the minimum over the same triangles with
+// the same distance function, so the distance is the one the sequential walk returns (the index is an argmin, as everywhere:
+// ties, Q3).  Tried inside the packet kernel too (for subtrees only one lane still needs, and as a second pass for packets
+// over a step budget): 51 -> 59 ms on the 16.7M-query batch (registers 48 -> 56, one resident CTA fewer), so large batches keep
+// the plain packets.
 constexpr int kSoloStack = 512;  // entries per warp; above kSoloStack - 128 the walk pops one entry per step (growth <= tree depth)
 SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, int owner, int lane, V3 p_lane, float &best2_lane, uint32_t &best_lane,
                           uint32_t &best_leaf_lane)
@@ -349,10 +352,8 @@ __global__ void __launch_bounds__(kQueryThreads)
                      float *__restrict__ out_dist, unsigned long long *counter, int use_seed)
 {
     __shared__ PacketStack s_stack[kQueryThreads / 32];
-    __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStack];
     const int lane = threadIdx.x & 31;
     uint2 *stk = s_stack[threadIdx.x >> 5].e;
-    StackEntry *solo = s_solo[threadIdx.x >> 5];
     uint32_t best_leaf = kNone;
     for (;;)
     {
@@ -386,16 +387,6 @@ __global__ void __launch_bounds__(kQueryThreads)
         int sp = 0;
         for (;;)
         {
-            if (use_seed < 4 && (mask & (mask - 1u)) == 0u)
-            { // one lane left on this subtree: the warp walks it for that lane (solo_closest)
-                solo_closest(sv, solo, node, __ffs(mask) - 1, lane, p, best2, best, best_leaf);
-                if (sp == 0) break;
-                --sp;
-                const uint2 e = stk[sp];
-                node = e.x;
-                mask = e.y;
-                continue;
-            }
             float4 a, b, c, d;
             ld256(sv.bnode + node, a, b);
             ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
