@@ -190,6 +190,8 @@ def other_config(cfg, pkg, m, dev, stream):
     import torch
     if cfg == "2d":
         return scene2_config(pkg, m, dev, stream)
+    if cfg == "c1":
+        return c1_config(pkg, m, dev, stream)
     nu, per_gpu = {"c4": (1416, (1 << 24) // 8), "c5": (2240, (1 << 26) // 8)}[cfg]
     v, f = m.bumpy_torus(nu, nu)
     t0 = time.perf_counter()
@@ -225,6 +227,53 @@ def other_config(cfg, pkg, m, dev, stream):
                        ms_per_step=ms, walker_steps_mqps=per_gpu / ms / 1e3, queries_mqps=4 * per_gpu / ms / 1e3)
     del sc
     torch.cuda.empty_cache()
+    return out
+
+
+def c1_config(pkg, m, dev, stream):
+    """BASELINE.json config C1: 65 536 closest-point / silhouette / ray queries uniform in [-1.5, 1.5]^3 on the 20 480-triangle
+    icosphere, device-resident (CUDA events on `stream`, mean of 20), with the reference's CUDA path on the same queries.  A
+    batch this small does not fill the machine: its run time is the critical path of its most expensive query (the points
+    near the centre of the sphere see every triangle at the same distance), which is what the one-query-per-warp kernels cut."""
+    import torch
+    v, f = m.icosphere(5)
+    sc = pkg.Scene3(v, f, device=dev).compute_silhouettes().build_bvh(stream=stream)
+    n = 65536
+    q_h = np.random.default_rng(1234).uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    d_h = m.unit_directions(n, seed=3)
+    q, d = torch.from_numpy(q_h).to(f"cuda:{dev}"), torch.from_numpy(d_h).to(f"cuda:{dev}")
+
+    def timed(fn, reps=20):
+        fn()
+        stream.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        stream.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {"triangles": len(f), "queries": n}
+    with torch.cuda.stream(stream):
+        out["closest_ms"] = timed(lambda: sc.closest_point(q, stream=stream))
+        out["silhouette_ms"] = timed(lambda: sc.closest_silhouette(q, stream=stream))
+        out["ray_ms"] = timed(lambda: sc.intersect(q, d, stream=stream))
+    for k in ("closest", "silhouette", "ray"):
+        out[f"{k}_mqps"] = n / out[f"{k}_ms"] / 1e3
+    try:
+        from oracle import RefScene, ref_available
+        if ref_available("cuda"):
+            ref = RefScene(v, f, "cuda")
+            rc = {}
+            for name, fn in (("closest_ms", lambda: ref.closest(q_h)), ("silhouette_ms", lambda: ref.silhouette(q_h)), ("ray_ms", lambda: ref.ray(q_h, d_h))):
+                fn()
+                fn()
+                rc[name] = ref.last_ms  # the traversal kernel alone (CUDA events inside the wrapper)
+            out["reference_cuda"] = rc
+    except Exception as ex:
+        out["reference_cuda_error"] = repr(ex)
+    del sc
     return out
 
 
@@ -313,7 +362,7 @@ def _run():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--queries", type=int, default=N_QUERIES, help="queries per GPU per step (default: the C3 batch)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (closest/ray/build/reference CUDA)")
-    ap.add_argument("--also", default="", help="comma list of further configs to time into `extra` on rank 0 (c4, c5 of BASELINE.json; 2d = the scene<2> path): "
+    ap.add_argument("--also", default="", help="comma list of further configs to time into `extra` on rank 0 (c1, c4, c5 of BASELINE.json; 2d = the scene<2> path): "
                     "c4 (16M rays / 8 GPUs on a 4M-triangle mesh), c5 (wavefront WoSt step, 64M walkers / 8 GPUs on a 10M-triangle mesh)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
