@@ -261,6 +261,18 @@ def c1_config(pkg, m, dev, stream):
         out["ray_ms"] = timed(lambda: sc.intersect(q, d, stream=stream))
     for k in ("closest", "silhouette", "ray"):
         out[f"{k}_mqps"] = n / out[f"{k}_ms"] / 1e3
+    # the traversal kernels alone (the library's own CUDA events around them): what the reference's numbers below measure
+    sc.set_option("query.time_kernels", 1)
+    with torch.cuda.stream(stream):
+        for k, fn in (("closest", lambda: sc.closest_point(q, stream=stream)), ("silhouette", lambda: sc.closest_silhouette(q, stream=stream)),
+                      ("ray", lambda: sc.intersect(q, d, stream=stream))):
+            fn()
+            sc.counter("query.traversal_ms", reset=True)
+            for _ in range(10):
+                fn()
+            out[f"{k}_kernel_ms"] = sc.counter("query.traversal_ms", reset=True) / 10
+    sc.set_option("query.time_kernels", 0)
+    out["note"] = "x_ms = whole call (ordering + kernels + per-call host overhead, back to back); x_kernel_ms = traversal kernel alone"
     try:
         from oracle import RefScene, ref_available
         if ref_available("cuda"):

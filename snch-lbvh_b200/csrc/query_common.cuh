@@ -12,6 +12,9 @@ constexpr int kQueryThreads = 128;
 constexpr int kStackDepth = 64; // >= 62 levels possible with the 62-bit augmented key
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kChunk = 64; // consecutive queries a warp draws per atomic
+// batches under 1M queries draw 32 at a time: twice the warps, one query per lane — such a batch is latency-bound (C1: 64K rays)
+SNCH_DI uint32_t chunk_for(uint32_t n) { return n < (1u << 20) ? 32u : kChunk; }
+static inline uint32_t chunk_for_host(uint64_t n) { return n < (1u << 20) ? 32u : kChunk; }
 
 struct NodeBoxes
 {
@@ -109,13 +112,13 @@ SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane,
     else if (f.next == f.end && !f.exhausted)
     {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)kChunk);
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)chunk_for(n));
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) f.exhausted = true;
         else
         {
             f.next = (uint32_t)base;
-            f.end = (uint32_t)min((unsigned long long)n, base + kChunk);
+            f.end = (uint32_t)min((unsigned long long)n, base + chunk_for(n));
         }
     }
     const uint32_t avail = f.end - f.next;
@@ -150,7 +153,8 @@ template <typename K> static inline unsigned persistent_grid(K kernel, const Que
     if (per_sm < 1) per_sm = 1;
     if (t.blocks_per_sm > 0 && t.blocks_per_sm < per_sm) per_sm = t.blocks_per_sm;
     const uint64_t full = (uint64_t)sms * per_sm;
-    const uint64_t need = ((uint64_t)n + kChunk * (kQueryThreads / 32) - 1) / (kChunk * (kQueryThreads / 32));
+    const uint64_t per_cta = (uint64_t)chunk_for_host(n) * (kQueryThreads / 32);
+    const uint64_t need = ((uint64_t)n + per_cta - 1) / per_cta;
     return (unsigned)(need < full ? (need ? need : 1) : full);
 }
 
