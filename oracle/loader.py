@@ -39,8 +39,8 @@ def oracle_lib():
     if _oracle_lib is not None:
         return _oracle_lib
     path = os.path.join(HERE, "liboracle.so")
-    src = os.path.join(HERE, "snch_oracle.c")
-    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, "snch_oracle.c"), os.path.join(HERE, "snch_oracle2.c")]
+    if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(x) for x in srcs):
         build_oracle(with_ref=False)
     L = C.CDLL(path)
     vp = C.c_void_p
@@ -71,6 +71,19 @@ def oracle_lib():
     L.orc_morton3.restype = C.c_uint32
     L.orc_expand_bits.argtypes = [C.c_uint32]
     L.orc_expand_bits.restype = C.c_uint32
+    # 2-D (snch_oracle2.c)
+    L.orc_scene2_create.restype = vp
+    L.orc_scene2_create.argtypes = [_f32p, C.c_int, _i32p, C.c_int]
+    L.orc_scene2_destroy.argtypes = [vp]
+    for name in ("orc2_num_nodes", "orc2_collision"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = C.c_int
+    L.orc2_export_tree.argtypes = [vp, _u32p, _f32p, _f32p, _u8p]
+    L.orc2_export_adjacency.argtypes = [vp, _i32p, _i32p]
+    L.orc2_closest.argtypes = [vp, _f32p, C.c_long, _u32p, _f32p]
+    L.orc2_silhouette.argtypes = [vp, _f32p, C.c_long, C.c_int, C.c_void_p, _f32p]
+    L.orc2_ray.argtypes = [vp, _f32p, _f32p, C.c_void_p, C.c_long, _i32p, _f32p, _f32p, _u32p]
+    L.orc2_sample.argtypes = [vp, _f32p, _f32p, C.c_long, _i32p, _f32p]
     _oracle_lib = L
     return L
 
@@ -208,6 +221,68 @@ class OracleScene:
         else:
             raise ValueError(kind)
         return a.value, b.value
+
+
+class OracleScene2:
+    """Plain-C restatement of lbvh::scene<2> (oracle/snch_oracle2.c): polylines, segments / silhouette vertices."""
+
+    def __init__(self, verts, segs):
+        self.L = oracle_lib()
+        self.verts = _f32(verts).reshape(-1, 2)
+        self.segs = _i32(segs).reshape(-1, 2)
+        self.h = self.L.orc_scene2_create(self.verts, len(self.verts), self.segs, len(self.segs))
+        self.n = len(self.segs)
+        self.num_nodes = self.L.orc2_num_nodes(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.orc_scene2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def tree(self):
+        """nodes (nn, 4) u32, aabbs (nn, 4) {upper xy, lower xy}, cones (nn, 4) {axis xy, half_angle, radius}, q1 taint (nn,) u8"""
+        nn = self.num_nodes
+        nodes, aabbs, cones, q1 = np.zeros((nn, 4), np.uint32), np.zeros((nn, 4), np.float32), np.zeros((nn, 4), np.float32), np.zeros(nn, np.uint8)
+        self.L.orc2_export_tree(self.h, nodes, aabbs, cones, q1)
+        return nodes, aabbs, cones, q1
+
+    def adjacency(self):
+        v4, owned = np.zeros((len(self.verts), 4), np.int32), np.zeros((self.n, 2), np.int32)
+        self.L.orc2_export_adjacency(self.h, v4, owned)
+        return v4, owned
+
+    def closest(self, q):
+        q = _f32(q).reshape(-1, 2)
+        idx, dist = np.zeros(len(q), np.uint32), np.zeros(len(q), np.float32)
+        self.L.orc2_closest(self.h, q, len(q), idx, dist)
+        return idx, dist
+
+    def silhouette(self, q, flip=False, r_max=None):
+        q = _f32(q).reshape(-1, 2)
+        dist = np.zeros(len(q), np.float32)
+        r = None if r_max is None else _f32(np.broadcast_to(r_max, (len(q),)))
+        self.L.orc2_silhouette(self.h, q, len(q), int(flip), None if r is None else r.ctypes.data, dist)
+        return dist
+
+    def ray(self, org, dirs, tmax=None):
+        org, dirs = _f32(org).reshape(-1, 2), _f32(dirs).reshape(-1, 2)
+        n = len(org)
+        tm = None if tmax is None else _f32(np.broadcast_to(tmax, (n,)))
+        found, t, s, prim = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+        self.L.orc2_ray(self.h, org, dirs, None if tm is None else tm.ctypes.data, n, found, t, s, prim)
+        return found, t, s, prim
+
+    def sample(self, sph, u):
+        sph, u = _f32(sph).reshape(-1, 3), _f32(u).reshape(-1)
+        idx, pdf = np.zeros(len(sph), np.int32), np.zeros(len(sph), np.float32)
+        self.L.orc2_sample(self.h, sph, u, len(sph), idx, pdf)
+        return idx, pdf
 
 
 def ref_available(kind: str = "cpu") -> bool:
