@@ -181,9 +181,22 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *   "query.sort_rays"   also order ray batches by origin (default 0)
  *   "query.packet"      bit mask: ordered batches walked by whole warps (one node fetch per warp, ballots pick the children)
  *                       instead of one traversal per lane.  bit 0 closest point, bit 1 silhouette (default 1)
- *   "query.cone_filter" silhouette: guard-banded sine-space evaluation of the normal-cone test (default 1; 0 = always cone.cuh:168-212 verbatim)
+ *   "query.cone_filter" silhouette normal-cone test: 0 = cone.cuh:168-212 verbatim; 1 = guard-banded sine-space evaluation on correctly
+ *                       rounded sqrt / rcp; 2 = the same on MUFU approximations; 3 = 2 with the verbatim chain out of line (default 3)
  *   "query.seed"        closest point: bound each query by the triangle that answered the lane's previous query (default 1)
+ *   "query.sil_kernel"  per-lane silhouette kernel: 1 = warp-shared leaf queue + shared-memory stack (default), 0 = per-lane parks
+ *   "query.sil_seed"    silhouette: queue the leaf that answered the lane's previous query as a pruning hint (default 1)
+ *   "query.sil_nodes"   silhouette: walk the 64 B compact records of a scene built with "build.compact_nodes" (default 0: slower)
+ *   "query.sort_radius" bounded silhouette batches: 0 = Morton order only, 1 = search-radius octave then Morton, 2 = the same with
+ *                       the largest radii first (default 2: the longest walks start first)
+ *   "query.wide_max_n"  closest point: batches smaller than this are walked one query per warp (default 2097152; 0 = never)
+ *   "query.wide_max_n_sil"  the same for silhouette batches (default 262144)
+ *   "query.feed"        silhouette work distribution: 0 = one global chunk counter (default), 1 / 2 = a contiguous region per CTA / SM
+ *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
+ *   "build.compact_nodes" also emit the 64 B compact silhouette records (default 0); "build.refit_kernel" 1 = CTA-cooperative refit
+ *                       (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort (default), 0 = three-kernel passes;
+ *                       "adjacency.device" 1 = GPU silhouette adjacency (default when a device is present), 0 = host passes
  * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel).
  *   "query.time_kernels" bracket every traversal kernel with CUDA events on the launching stream (default 0; see snch_scene_counter) */
 int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
