@@ -250,7 +250,7 @@ int snch_scene2_build(snch_scene2 *s, snch_stream stream);
 int snch_scene2_stats(const snch_scene2 *s, snch_build_stats *out);
 int snch_scene2_device_repr(const snch_scene2 *s, snch_bvh_device_pod *out);
 int snch_scene2_export(const snch_scene2 *s, int kind, void *host_dst, uint64_t bytes);
-int snch_scene2_set_option(snch_scene2 *s, const char *name, int64_t value); /* "query.sort_min_n", "query.sort_bits", "query.sort_rays", "query.blocks_per_sm" */
+int snch_scene2_set_option(snch_scene2 *s, const char *name, int64_t value); /* "query.sort_min_n", "query.sort_bits", "query.sort_rays", "query.blocks_per_sm", "query.wide_max_n" (batches below it walk one query per warp; default 131072) */
 int snch_closest_point_batch2(const snch_scene2 *s, const float *points_xy, uint64_t n, uint32_t *out_index, float *out_distance,
                               snch_stream stream);
 int snch_closest_silhouette_batch2(const snch_scene2 *s, const float *points_xy, const uint8_t *flip, const float *r_max, uint64_t n,

@@ -360,6 +360,241 @@ __global__ void __launch_bounds__(kQueryThreads)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One query per WARP (small batches): the cooperative walk of query.cu (solo_closest / solo_silhouette) on the 2-D records.
+// A batch that does not fill the machine runs as long as its most expensive query — the centre of a closed curve sees every
+// segment at the same distance — and 32 lanes on one query shorten exactly that path.  Same predicates, same distance
+// functions, same results.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWide2Stack = 512; // entries per warp; above kWide2Stack - 128 one entry is popped per step (growth <= tree depth)
+__global__ void __launch_bounds__(kQueryThreads)
+    k2_closest_wide(View2 v, const float *__restrict__ q, const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ out_idx,
+                    float *__restrict__ out_dist, unsigned long long *counter)
+{
+    __shared__ StackEntry s_st[kQueryThreads / 32][kWide2Stack];
+    const int lane = threadIdx.x & 31;
+    StackEntry *st = s_st[threadIdx.x >> 5];
+    const unsigned lt = (1u << lane) - 1u;
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 4ull);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        for (unsigned long long s = base; s < base + 4ull && s < n; ++s)
+        {
+            const uint32_t slot = perm ? __ldg(perm + s) : (uint32_t)s;
+            const float2 p = load_point2(q, slot);
+            float b2 = INFINITY;
+            uint32_t bi = kNone;
+            int sp = 0;
+            if (v.n == 1)
+            {
+                float4 a, b;
+                ld256(v.l2, a, b);
+                const float d = dist_point_segment(make_float2(a.x, a.y), make_float2(a.z, a.w), p);
+                b2 = d * d;
+                bi = __float_as_uint(b.x);
+            }
+            else
+            {
+                if (lane == 0) st[0] = StackEntry{0u, 0.0f};
+                sp = 1;
+            }
+            __syncwarp();
+            while (sp > 0)
+            {
+                const int take = sp > kWide2Stack - 128 ? 1 : (sp < 32 ? sp : 32);
+                sp -= take;
+                StackEntry e = StackEntry{kNone, INFINITY};
+                if (lane < take) e = st[sp + lane];
+                __syncwarp();
+                uint32_t cand = 0xFFFFFFFFu, cand_i = kNone, pr0 = kNone, pr1 = kNone;
+                float pk0 = 0.0f, pk1 = 0.0f;
+                if (e.node != kNone && (e.key < b2 || bi == kNone))
+                {
+                    const Pair2 pr = load_pair(v.n2, e.node);
+                    const float m0 = lbvh::mindist(pr.b0, p), m1 = lbvh::mindist(pr.b1, p);
+                    const bool far1 = m0 < m1; // the farther child is pushed first, so the nearer one is popped first
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch)
+                    {
+                        const bool one = (ch == 0) == far1;
+                        const float m = one ? m1 : m0;
+                        const uint32_t r = one ? pr.r1 : pr.r0;
+                        if (!(m < b2 || bi == kNone)) continue;
+                        if (r & kLeaf2)
+                        {
+                            float4 a, b;
+                            ld256(v.l2 + (r & kRefIndex2), a, b);
+                            float d = dist_point_segment(make_float2(a.x, a.y), make_float2(a.z, a.w), p);
+                            d *= d;
+                            if ((d < b2 || bi == kNone) && __float_as_uint(d) < cand)
+                            {
+                                cand = __float_as_uint(d);
+                                cand_i = __float_as_uint(b.x);
+                            }
+                        }
+                        else if (pr0 == kNone)
+                        {
+                            pr0 = r;
+                            pk0 = m;
+                        }
+                        else
+                        {
+                            pr1 = r;
+                            pk1 = m;
+                        }
+                    }
+                }
+                const unsigned c1 = __ballot_sync(kFull, pr0 != kNone), c2 = __ballot_sync(kFull, pr1 != kNone);
+                const int off = sp + __popc(c1 & lt) + __popc(c2 & lt);
+                if (pr0 != kNone) st[off] = StackEntry{pr0, pk0};
+                if (pr1 != kNone) st[off + 1] = StackEntry{pr1, pk1};
+                sp += __popc(c1) + __popc(c2);
+                const uint32_t mn = __reduce_min_sync(kFull, cand);
+                if (mn != 0xFFFFFFFFu)
+                {
+                    const int wl = __ffs(__ballot_sync(kFull, cand == mn)) - 1;
+                    b2 = __uint_as_float(mn);
+                    bi = __shfl_sync(kFull, cand_i, wl);
+                }
+                __syncwarp();
+            }
+            if (lane == 0)
+            {
+                if (out_idx) out_idx[slot] = bi;
+                out_dist[slot] = sqrtf(b2);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(kQueryThreads)
+    k2_silhouette_wide(View2 v, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
+                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+{
+    __shared__ StackEntry s_st[kQueryThreads / 32][kWide2Stack];
+    const int lane = threadIdx.x & 31;
+    StackEntry *st = s_st[threadIdx.x >> 5];
+    const unsigned lt = (1u << lane) - 1u;
+    for (;;)
+    {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, 4ull);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= n) break;
+        for (unsigned long long s = base; s < base + 4ull && s < n; ++s)
+        {
+            const uint32_t slot = perm ? __ldg(perm + s) : (uint32_t)s;
+            const float2 p = load_point2(q, slot);
+            const bool flip = flipv ? (__ldg(flipv + slot) != 0) : false;
+            float best = rmax ? __ldg(rmax + slot) : INFINITY;
+            bool found = false;
+            // silhouette_distance_calculator over the owned vertices of leaf k (scene.cuh:518-541, 345-378), bound = `bound`
+            auto test_leaf = [&](uint32_t k, uint32_t cnt, float bound, uint32_t &cand)
+            {
+                float max_r2 = bound * bound;
+                for (uint32_t j = 0; j < cnt; ++j)
+                {
+                    float4 a, b;
+                    ld256(reinterpret_cast<const char *>(v.l2 + k) + 32 + 32 * j, a, b);
+                    const float2 view_dir = make_float2(p.x - a.x, p.y - a.y);
+                    const float d = lbvh::length(view_dir);
+                    if (0.0f >= max_r2 || d * d > max_r2) continue;
+                    bool is_sil = __float_as_uint(b.z) != 3u;
+                    if (!is_sil) is_sil = lbvh::is_silhouette_vertex(make_float2(a.z, a.w), make_float2(b.x, b.y), view_dir, d, flip);
+                    if (is_sil && d * d <= max_r2 && d <= bound)
+                    {
+                        max_r2 = d * d;
+                        bound = d;
+                        cand = __float_as_uint(d);
+                    }
+                }
+            };
+            int sp = 0;
+            if (v.n == 1)
+            {
+                const Box2 rb = v.aabbs[0];
+                const Cone2 rc = v.cones[0];
+                const float m = lbvh::mindist(rb, p);
+                const float c4[4] = {rc.axis.x, rc.axis.y, rc.half_angle, rc.radius};
+                uint32_t cand = 0xFFFFFFFFu;
+                if (m <= best * best && may_hold_silhouette2(c4, p, rb, m)) test_leaf(0, v.l2[0].owned, best, cand);
+                if (cand != 0xFFFFFFFFu)
+                {
+                    best = __uint_as_float(cand);
+                    found = true;
+                }
+            }
+            else
+            {
+                if (lane == 0) st[0] = StackEntry{0u, 0.0f};
+                sp = 1;
+            }
+            __syncwarp();
+            while (sp > 0)
+            {
+                const int take = sp > kWide2Stack - 128 ? 1 : (sp < 32 ? sp : 32);
+                sp -= take;
+                StackEntry e = StackEntry{kNone, INFINITY};
+                if (lane < take) e = st[sp + lane];
+                __syncwarp();
+                uint32_t cand = 0xFFFFFFFFu, pr0 = kNone, pr1 = kNone;
+                float pk0 = 0.0f, pk1 = 0.0f;
+                const float best2 = best * best;
+                if (e.node != kNone && e.key <= best2)
+                {
+                    const Pair2 pr = load_pair(v.n2, e.node);
+                    float4 ce, cf;
+                    ld256(reinterpret_cast<const char *>(v.n2 + e.node) + 64, ce, cf);
+                    const float c0[4] = {ce.x, ce.y, ce.z, ce.w}, c1[4] = {cf.x, cf.y, cf.z, cf.w};
+                    const float m0 = lbvh::mindist(pr.b0, p), m1 = lbvh::mindist(pr.b1, p);
+                    const bool h0 = (m0 <= best2) && may_hold_silhouette2(c0, p, pr.b0, m0);
+                    const bool h1 = (m1 <= best2) && may_hold_silhouette2(c1, p, pr.b1, m1);
+                    const bool far1 = m0 < m1;
+                    float bound = best;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch)
+                    {
+                        const bool one = (ch == 0) == far1;
+                        if (!(one ? h1 : h0)) continue;
+                        const float m = one ? m1 : m0;
+                        const uint32_t r = one ? pr.r1 : pr.r0;
+                        if (r & kLeaf2)
+                        {
+                            test_leaf(r & kRefIndex2, (r >> 29) & 3u, bound, cand);
+                            if (cand != 0xFFFFFFFFu) bound = __uint_as_float(cand);
+                        }
+                        else if (pr0 == kNone)
+                        {
+                            pr0 = r;
+                            pk0 = m;
+                        }
+                        else
+                        {
+                            pr1 = r;
+                            pk1 = m;
+                        }
+                    }
+                }
+                const unsigned c1m = __ballot_sync(kFull, pr0 != kNone), c2m = __ballot_sync(kFull, pr1 != kNone);
+                const int off = sp + __popc(c1m & lt) + __popc(c2m & lt);
+                if (pr0 != kNone) st[off] = StackEntry{pr0, pk0};
+                if (pr1 != kNone) st[off + 1] = StackEntry{pr1, pk1};
+                sp += __popc(c1m) + __popc(c2m);
+                const uint32_t mn = __reduce_min_sync(kFull, cand);
+                if (mn != 0xFFFFFFFFu)
+                {
+                    best = __uint_as_float(mn);
+                    found = true;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) out_dist[slot] = found ? best : INFINITY;
+        }
+    }
+}
+
 // ray vs segments                                                                         query.cuh:79-169
 SNCH_DI bool ray_segment(float2 p0, float2 p1, float2 org, float2 dir, float *t, float *s) // scene.cuh:543-577
 {
@@ -783,6 +1018,7 @@ extern "C" int snch_scene2_create(const float *xy, uint32_t n_verts, const int32
     snch_scene2 *s = new (std::nothrow) snch_scene2();
     if (!s) return SNCH_ERR_OOM;
     s->device = device;
+    s->tuning.wide_max_n_sil = 131072; // "query.wide_max_n" of a 2-D scene
     s->n_verts = n_verts;
     s->n_segs = n_segs;
     s->verts_h.resize(n_verts);
@@ -1004,6 +1240,7 @@ extern "C" int snch_scene2_set_option(snch_scene2 *s, const char *name, int64_t 
     else if (k == "query.sort_bits") s->tuning.sort_bits = (int)value;
     else if (k == "query.sort_rays") s->tuning.sort_rays = (int)value;
     else if (k == "query.blocks_per_sm") s->tuning.blocks_per_sm = (int)value;
+    else if (k == "query.wide_max_n") s->tuning.wide_max_n_sil = (int)value;
     else
     {
         set_error("snch_scene2_set_option: unknown option '" + k + "'");
@@ -1048,7 +1285,11 @@ extern "C" int snch_closest_point_batch2(const snch_scene2 *s, const float *poin
         const uint32_t *perm;
         rc = prepare_batch(s->tuning, true, q, 2, nullptr, (uint32_t)n, scr.p, st, &counter, &perm, nullptr, 2);
         if (rc != SNCH_OK) return rc;
-        k2_closest<<<persistent_grid(k2_closest, s->tuning, (uint32_t)n), kQueryThreads, 0, st>>>(s->view(), q, perm, (uint32_t)n, idx, dist, counter);
+        if (n < (uint64_t)s->tuning.wide_max_n_sil) // 2-D scenes share one threshold (measured crossover 0.1-0.3M queries)
+            k2_closest_wide<<<persistent_grid(k2_closest_wide, s->tuning, (uint32_t)(n * 16)), kQueryThreads, 0, st>>>(s->view(), q, perm, (uint32_t)n, idx,
+                                                                                                                 dist, counter);
+        else
+            k2_closest<<<persistent_grid(k2_closest, s->tuning, (uint32_t)n), kQueryThreads, 0, st>>>(s->view(), q, perm, (uint32_t)n, idx, dist, counter);
     }
     return sg.finish();
 }
@@ -1089,8 +1330,12 @@ extern "C" int snch_closest_silhouette_batch2(const snch_scene2 *s, const float 
         const uint32_t *perm;
         rc = prepare_batch(s->tuning, true, q, 2, nullptr, (uint32_t)n, scr.p, st, &counter, &perm, nullptr, 2);
         if (rc != SNCH_OK) return rc;
-        k2_silhouette<<<persistent_grid(k2_silhouette, s->tuning, (uint32_t)n), kQueryThreads, 0, st>>>(s->view(), q, fl, rm, perm, (uint32_t)n, dist,
-                                                                                                       counter);
+        if (n < (uint64_t)s->tuning.wide_max_n_sil)
+            k2_silhouette_wide<<<persistent_grid(k2_silhouette_wide, s->tuning, (uint32_t)(n * 16)), kQueryThreads, 0, st>>>(s->view(), q, fl, rm, perm,
+                                                                                                                       (uint32_t)n, dist, counter);
+        else
+            k2_silhouette<<<persistent_grid(k2_silhouette, s->tuning, (uint32_t)n), kQueryThreads, 0, st>>>(s->view(), q, fl, rm, perm, (uint32_t)n, dist,
+                                                                                                           counter);
     }
     return sg.finish();
 }
