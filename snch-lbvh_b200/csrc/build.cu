@@ -377,7 +377,10 @@ SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
         lt[0] = make_float4(pa.x, pa.y, pa.z, __uint_as_float(obj));
         lt[1] = make_float4(pb.x, pb.y, pb.z, 0.0f);
         lt[2] = make_float4(pc.x, pc.y, pc.z, 0.0f);
-        lt[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // unit normal and the reach of the triangle from its first vertex: the cheap lower bound of tri_lower_bound2() (query.cu)
+        const V3 ab = pb - pa, ac = pc - pa;
+        const V3 nn = normalize(cross(ab, ac)); // NaN for a degenerate triangle: the bound then never rejects
+        lt[3] = make_float4(nn.x, nn.y, nn.z, fmaxf(len(ab), len(ac)) * 1.000001f);
     }
     // ---- leaf normal cone from the owned silhouette edges, and their traversal records
     const V3 bc = box_centroid(box);

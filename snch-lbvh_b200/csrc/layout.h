@@ -81,7 +81,7 @@ struct __align__(32) LTri // 64 B (two sectors, two 256-bit loads), Morton (leaf
     float4 v0; // xyz, w = object index bits
     float4 v1;
     float4 v2;
-    float4 pad;
+    float4 plane; // unit normal xyz (NaN if degenerate), w = max(|v1 - v0|, |v2 - v0|) rounded up: the cheap distance lower bound
 };
 struct __align__(32) LEdge // 64 B, grouped by owning leaf in Morton order
 {

@@ -244,6 +244,40 @@ __global__ void __launch_bounds__(kQueryThreads)
 // against it, and __ballot_sync decides which children any lane still needs.  The traversal stack is per warp (node +
 // lane mask, in shared memory); per-lane state is just the running best.  Lanes only ever skip work they could not use
 // (mindist >= their best / their cone test failed), so each lane's result is exactly what its own traversal returns.
+SNCH_DI float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+SNCH_DI float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// Can the triangle with first vertex pa, unit normal n and reach ra (no point of it is farther than ra from pa) be nearer to x
+// than `bestd` = sqrt(best2)?  Lower bound of its distance: the distance to its plane, combined with how far the projection
+// of x lies beyond that reach.  For the triangles an exact search has to LOOK at — those whose box comes within the current
+// best, a band whose population grows with sqrt(N) for a query far from a fine surface — this is tight to second order where
+// the box is tight to first order, so most of them are rejected for ~25 instructions instead of the ~120 of the reference's
+// point-triangle distance.
+// Sound in float, so results stay bit-identical: (i) the bound's own roundings (|n| = 1 +- 2e-7, the dot products, the
+// approximate square roots) are covered by the 4e-6 s / 2e-6 s terms, s = |x - pa|^2; (ii) the reference's distance function
+// rounds its closest point in ABSOLUTE terms (~4e-7 of the coordinate magnitude M <= |x|_inf + |x - pa|), so the distance it
+// would return may undercut the true one by that much: the triangle is rejected only if the bound exceeds
+// (bestd + 2e-6 M)^2 (1 + 4e-6), i.e. only if that returned distance could not have passed `dist^2 < best2`.  NaN (degenerate
+// triangle, infinite best) never rejects.
+SNCH_DI bool tri_cannot_improve(V3 pa, V3 n, float ra, V3 x, float xmax, float bestd)
+{
+    const V3 w = x - pa;
+    const float s = dot(w, w), pd = dot(n, w), pd2 = pd * pd;
+    const float lat = fmaxf(sqrt_approx(fmaxf(s - pd2 - 4e-6f * s, 0.0f)) - ra, 0.0f);
+    const float lb2 = pd2 + lat * lat - 2e-6f * s;
+    const float t = bestd + 2e-6f * (xmax + sqrt_approx(s));
+    return lb2 > t * t * 1.000004f;
+}
+
 // COOPERATIVE WALK of one query by a whole warp.  A query that is (nearly) equidistant to a large part of the mesh (the centre
 // of a sphere, the axis of a torus) needs tens of thousands of nodes; walked by one lane, or by a packet it shares with 31
 // neighbours that need the same nodes, that is a 5 ms critical path — the whole run time of a batch too small to fill the
@@ -262,6 +296,7 @@ SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, in
     float b2 = __shfl_sync(kFull, best2_lane, owner);
     uint32_t bi = __shfl_sync(kFull, best_lane, owner), bl = __shfl_sync(kFull, best_leaf_lane, owner);
     const unsigned lt = (1u << lane) - 1u;
+    const float pmax = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z));
     if (lane == 0) st[0] = StackEntry{root, 0.0f};
     int sp = 1;
     __syncwarp();
@@ -273,6 +308,7 @@ SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, in
         if (lane < take) e = st[sp + lane];
         __syncwarp(); // every popped entry is read before this step's pushes reuse the slots
         uint32_t cand = 0xFFFFFFFFu, cand_i = kNone, cand_leaf = kNone; // squared distance as ordered bits (>= +0)
+        const float bd = sqrt_approx(b2) * 1.000001f;
         uint32_t pr0 = kNone, pr1 = kNone;
         float pk0 = 0.0f, pk1 = 0.0f;
         if (e.node != kNone && e.key < b2)
@@ -298,6 +334,7 @@ SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, in
                     float4 t0, t1, t2, t3;
                     ld256(tp, t0, t1);
                     ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                    if (tri_cannot_improve(V3{t0.x, t0.y, t0.z}, V3{t3.x, t3.y, t3.z}, t3.w, p, pmax, bd)) continue;
                     float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
                     dist *= dist;
                     if (dist < b2 && __float_as_uint(dist) < cand)
@@ -355,6 +392,8 @@ __global__ void __launch_bounds__(kQueryThreads)
     const int lane = threadIdx.x & 31;
     uint2 *stk = s_stack[threadIdx.x >> 5].e;
     uint32_t best_leaf = kNone;
+    const bool use_lb = !(use_seed & 2); // "query.seed" bit 1 switches the cheap lower bound off (A/B, knob tests)
+    use_seed &= 1;
     for (;;)
     {
         unsigned long long base = 0;
@@ -365,6 +404,7 @@ __global__ void __launch_bounds__(kQueryThreads)
         const bool valid = s < n;
         const uint32_t slot = valid ? __ldg(perm + s) : 0u;
         const V3 p = valid ? load_point(q, slot) : V3{0.f, 0.f, 0.f};
+        const float pmax = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z));
         float best2 = INFINITY;
         uint32_t best = kNone;
         if (use_seed && valid && best_leaf != kNone)
@@ -406,7 +446,7 @@ __global__ void __launch_bounds__(kQueryThreads)
                 float4 t0, t1, t2, t3;
                 ld256(tp, t0, t1);
                 ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
-                if (w)
+                if (w && !(use_lb && tri_cannot_improve(V3{t0.x, t0.y, t0.z}, V3{t3.x, t3.y, t3.z}, t3.w, p, pmax, sqrt_approx(best2) * 1.000001f)))
                 { // only the lanes that need this triangle: the Voronoi-region branches of the test then split the warp over the
                   // regions of THOSE lanes, not over the regions of all 32 query points
                     float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
@@ -514,18 +554,6 @@ __global__ void __launch_bounds__(kQueryThreads)
 // every branch decision the reference takes on exact float values — it defers to cone_overlap(), the reference's own
 // operation sequence.  Decisions are therefore the reference's; only their cost changes.
 constexpr float kConeBand = 2e-5f;
-SNCH_DI float rsqrt_approx(float x)
-{
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-SNCH_DI float sqrt_approx(float x)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 // kMode 0: the reference's libm chain.  1: sine-space filter on correctly rounded sqrt/rcp.  2: the same filter on the
 // MUFU approximations (rel. error <= 2^-22, i.e. <= 5e-7 on every quantity compared against the 2e-5 band); the two
 // exact-value branch decisions of the reference (l > radius, s <= 0) and the ill-conditioned corner (view cone within

@@ -203,7 +203,7 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
         sel = np.nonzero(flip[:6000] == fl)[0]
         check_silhouette(base["sil"][sel], orc.silhouette(q[sel], bool(fl), nthreads=8), 2e-3)
     for kv in ({"query.packet": 0}, {"query.packet": 3}, {"query.packet": 2, "query.cone_filter": 0}, {"query.packet": 0, "query.cone_filter": 0}, {"query.sort_min_n": 0}, {"query.cone_filter": 0}, {"query.cone_filter": 1}, {"query.sil_kernel": 0}, {"query.sil_kernel": 0, "query.cone_filter": 1}, {"query.sil_kernel": 0, "query.cone_filter": 0},
-               {"query.sil_kernel": 1, "query.sort_min_n": 0}, {"query.cone_filter": 3}, {"query.wide_max_n": 1 << 30}, {"query.wide_max_n_sil": 1 << 30}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 0}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 1, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.seed": 0}, {"query.sil_seed": 0}, {"query.sil_seed": 0, "query.sort_min_n": 0}, {"query.sil_seed": 0, "query.sil_nodes": 1}, {"query.cone_filter": 3, "query.sil_nodes": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.feed": 1}, {"query.feed": 2}, {"query.feed": 2, "query.cone_filter": 3, "query.sort_min_n": 0}, {"query.sil_nodes": 1}, {"query.sil_nodes": 1, "query.sort_min_n": 0}, {"query.seed": 0}, {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
+               {"query.sil_kernel": 1, "query.sort_min_n": 0}, {"query.cone_filter": 3}, {"query.seed": 3}, {"query.seed": 2, "query.sort_min_n": 16384}, {"query.wide_max_n": 1 << 30}, {"query.wide_max_n_sil": 1 << 30}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 0}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 1, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.seed": 0}, {"query.sil_seed": 0}, {"query.sil_seed": 0, "query.sort_min_n": 0}, {"query.sil_seed": 0, "query.sil_nodes": 1}, {"query.cone_filter": 3, "query.sil_nodes": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.feed": 1}, {"query.feed": 2}, {"query.feed": 2, "query.cone_filter": 3, "query.sort_min_n": 0}, {"query.sil_nodes": 1}, {"query.sil_nodes": 1, "query.sort_min_n": 0}, {"query.seed": 0}, {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
                {"query.host_chunk": 7001}, {"query.host_chunk": 0}, {"query.host_chunk": 500, "query.sort_min_n": 0},  # host-pointer pipeline
                {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0}):
         for k, val in {**defaults, **kv}.items():

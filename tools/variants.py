@@ -53,7 +53,7 @@ def main():
         return best, out
 
     defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 3, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.feed": 0, "query.sort_radius": 2, "query.sil_seed": 1, "query.sil_nodes": 0, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144}
-    settings = [("default", {}), ("compact", {"query.sil_nodes": 1}), ("compact_unseeded", {"query.sil_nodes": 1, "query.sil_seed": 0}), ("sil_unseeded", {"query.sil_seed": 0}), ("radius_asc", {"query.sort_radius": 1}), ("radius_desc", {"query.sort_radius": 2}), ("radius_desc5", {"query.sort_radius": 3}), ("radius_desc6", {"query.sort_radius": 4}), ("radius_desc_bits30", {"query.sort_radius": 2, "query.sort_bits": 30}), ("sil_ool", {"query.cone_filter": 3}), ("feed_cta", {"query.feed": 1}), ("feed_sm", {"query.feed": 2}), ("ool_feed_cta", {"query.cone_filter": 3, "query.feed": 1}), ("ool_feed_sm", {"query.cone_filter": 3, "query.feed": 2}), ("sil_v3", {"query.sil_kernel": 0}), ("sil_v3_filter1", {"query.sil_kernel": 0, "query.cone_filter": 1}), ("sil_v4_filter1", {"query.cone_filter": 1}), ("sil_v4_bps7", {"query.blocks_per_sm": 7}), ("sil_v4_bps6", {"query.blocks_per_sm": 6}), ("no_packet", {"query.packet": 0}), ("packet_both", {"query.packet": 3}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
+    settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("compact", {"query.sil_nodes": 1}), ("compact_unseeded", {"query.sil_nodes": 1, "query.sil_seed": 0}), ("sil_unseeded", {"query.sil_seed": 0}), ("radius_asc", {"query.sort_radius": 1}), ("radius_desc", {"query.sort_radius": 2}), ("radius_desc5", {"query.sort_radius": 3}), ("radius_desc6", {"query.sort_radius": 4}), ("radius_desc_bits30", {"query.sort_radius": 2, "query.sort_bits": 30}), ("sil_ool", {"query.cone_filter": 3}), ("feed_cta", {"query.feed": 1}), ("feed_sm", {"query.feed": 2}), ("ool_feed_cta", {"query.cone_filter": 3, "query.feed": 1}), ("ool_feed_sm", {"query.cone_filter": 3, "query.feed": 2}), ("sil_v3", {"query.sil_kernel": 0}), ("sil_v3_filter1", {"query.sil_kernel": 0, "query.cone_filter": 1}), ("sil_v4_filter1", {"query.cone_filter": 1}), ("sil_v4_bps7", {"query.blocks_per_sm": 7}), ("sil_v4_bps6", {"query.blocks_per_sm": 6}), ("no_packet", {"query.packet": 0}), ("packet_both", {"query.packet": 3}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
                 ("no_seed", {"query.seed": 0}), ("sort_bits_30", {"query.sort_bits": 30}), ("sort_bits_18", {"query.sort_bits": 18}),
                 ("no_sort_no_filter_no_seed", {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0})]
     if args.sets != "all":
