@@ -216,3 +216,41 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
         assert rel_close(orc.point_triangle_distance(q, idx1), base["dist"]).all(), kv
     with pytest.raises(pkg.SnchError):
         sc.set_option("query.no_such_knob", 1)
+
+
+@pytest.mark.parametrize("case", ["offset", "stretched", "near_surface", "tiny"])
+def test_triangle_lower_bound_never_changes_a_distance(pkg, meshes, case):
+    """The plane-and-reach rejection in front of the point-triangle distance (query.cu tri_cannot_improve) must be invisible:
+    bit-identical distances with it on ("query.seed" 1) and off (3), in the packet and the one-query-per-warp kernels, on
+    geometry chosen to stress its rounding margins — coordinates far from the origin (absolute rounding of the reference's
+    closest point grows with the coordinate magnitude), sliver triangles (ill-conditioned normals), queries a few ulps off
+    the surface, and a mesh scaled to 1e-3."""
+    import torch
+    v, f = meshes.bumpy_torus(160, 120)
+    rng = np.random.default_rng(17)
+    n = 400000
+    lo, hi = meshes.mesh_bounds(v)
+    q = meshes.points_in_box(n, lo, hi, 1.2, seed=18)
+    if case == "offset":
+        shift = np.array([1000.0, -2000.0, 500.0], np.float32)
+        v, q = (v + shift).astype(np.float32), (q + shift).astype(np.float32)
+    elif case == "stretched":
+        scale = np.array([300.0, 1.0, 0.01], np.float32)
+        v, q = (v * scale).astype(np.float32), (q * scale).astype(np.float32)
+    elif case == "near_surface":
+        tri = v[f[rng.integers(0, len(f), n)]]
+        w = rng.dirichlet([1.0, 1.0, 1.0], n).astype(np.float32)
+        q = (np.einsum("nk,nkd->nd", w, tri) + rng.normal(0.0, 2e-6, (n, 3))).astype(np.float32)
+    elif case == "tiny":
+        v, q = (v * 1e-3).astype(np.float32), (q * 1e-3).astype(np.float32)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    qd = torch.from_numpy(q).cuda()
+    out = {}
+    for wide in (0, 1 << 30):
+        for seed in (1, 3):
+            sc.set_option("query.wide_max_n", wide).set_option("query.seed", seed)
+            idx, dist = sc.closest_point(qd)
+            out[(wide, seed)] = dist.clone()
+    ref = out[(0, 3)]
+    for k, d in out.items():
+        assert torch.equal(d.view(torch.int32), ref.view(torch.int32)), (case, k)
