@@ -189,7 +189,8 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *   "query.sil_nodes"   silhouette: walk the 64 B compact records of a scene built with "build.compact_nodes" (default 0: slower)
  *   "query.sort_radius" bounded silhouette batches: 0 = Morton order only, 1 = search-radius octave then Morton, 2 = the same with
  *                       the largest radii first (default 2: the longest walks start first)
- *   "query.wide_max_n"  closest point: batches smaller than this are walked one query per warp (default 2097152; 0 = never)
+ *   "query.wide_max_n"  closest point: batches smaller than this — or with fewer than 2 queries per triangle — are walked one query
+ *                       per warp (default 2097152; 0 = never)
  *   "query.wide_max_n_sil"  the same for silhouette batches (default 262144)
  *   "query.feed"        silhouette work distribution: 0 = one global chunk counter (default), 1 / 2 = a contiguous region per CTA / SM
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
