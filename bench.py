@@ -426,7 +426,7 @@ def _run():
         L = pkg.lib()
 
         def step_device():
-            st = L.snch_closest_silhouette_batch(scene._h, q_d.data_ptr(), None, rmax_d.data_ptr(), n, out_d.data_ptr(), stream.cuda_stream)
+            st = L.snch_closest_silhouette_batch(scene._h, q_d.data_ptr(), None, rmax_d.data_ptr(), n, out_d.data_ptr(), None, None, stream.cuda_stream)
             assert st == 0, L.snch_last_error()
 
         def barrier():
@@ -468,7 +468,7 @@ def _run():
         o_p = torch.empty(n, dtype=torch.float32).pin_memory()
 
         def step_host():
-            st = L.snch_closest_silhouette_batch(scene._h, q_p.data_ptr(), None, r_p.data_ptr(), n, o_p.data_ptr(), stream.cuda_stream)
+            st = L.snch_closest_silhouette_batch(scene._h, q_p.data_ptr(), None, r_p.data_ptr(), n, o_p.data_ptr(), None, None, stream.cuda_stream)
             assert st == 0, L.snch_last_error()
 
         for _ in range(2):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SNCH_B200_ABI_VERSION 1
+#define SNCH_B200_ABI_VERSION 2
 
 typedef struct snch_scene snch_scene; /* opaque; owns one device arena on one GPU */
 typedef void *snch_stream;            /* a cudaStream_t (NULL = legacy default stream) */
@@ -124,9 +124,14 @@ int snch_closest_point_batch(const snch_scene *s, const float *points_xyz, uint6
 
 /* query_device(bvh, nearest_silhouette(p, flip), scene<3>::silhouette_distance_calculator()) -> distance   query.cuh:325-423
  * r_max (NULL = unbounded, the reference behaviour): search radius per query; result is +inf when no silhouette point
- * lies within it — identical to filtering the unbounded answer.  flip: one byte per query, or NULL = false. */
+ * lies within it — identical to filtering the unbounded answer.  flip: one byte per query, or NULL = false.
+ * Optional outputs (NULL = not wanted; asking for neither costs nothing) — what the reference computes and drops:
+ *   out_edge      index in scene<3>::silhouettes of an edge attaining the distance ("TODO: identify nearest index",
+ *                 query.cuh:386,411); 0xFFFFFFFF when the distance is +inf.  On exact ties any attaining edge.
+ *   out_point_xyz the closest point ON that edge — `closest_pos` of silhouette_edge::find_closest_silhouette_point
+ *                 (scene.cuh:796-799), which the reference discards at :817-821; (0,0,0) when the distance is +inf. */
 int snch_closest_silhouette_batch(const snch_scene *s, const float *points_xyz, const uint8_t *flip, const float *r_max, uint64_t n,
-                                  float *out_distance, snch_stream stream);
+                                  float *out_distance, uint32_t *out_edge, float *out_point_xyz, snch_stream stream);
 
 /* query_device(bvh, ray_intersect<TestOnly>(ray, max_dist), scene<3>::intersect_test())                     query.cuh:79-169
  * -> tuple<found, t, uv, prim idx>.  any_hit != 0 is TestOnly: only `found` is meaningful. */
@@ -172,32 +177,34 @@ typedef struct snch_wost_io
     int32_t *sample_index;
     float *sample_pdf;
     float *sample_point_xyz;
+    uint32_t *silhouette_edge;    /* as out_edge / out_point_xyz of snch_closest_silhouette_batch */
+    float *silhouette_point_xyz;
 } snch_wost_io;
 int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n, snch_stream stream);
 
 /* Scheduling knobs of the batched kernels; results never depend on them (tests/test_gpu_queries.py sweeps them).
  *   "query.sort_min_n"  batches at least this large are visited in Morton order of the query points (default 16384; 0 = never)
  *   "query.sort_bits"   key bits of that ordering (8..30, default 24)
- *   "query.sort_rays"   also order ray batches by origin (default 0)
- *   "query.packet"      bit mask: ordered batches walked by whole warps (one node fetch per warp, ballots pick the children)
- *                       instead of one traversal per lane.  bit 0 closest point, bit 1 silhouette (default 1)
- *   "query.cone_filter" silhouette normal-cone test: 0 = cone.cuh:168-212 verbatim; 1 = guard-banded sine-space evaluation on correctly
- *                       rounded sqrt / rcp; 2 = the same on MUFU approximations; 3 = 2 with the verbatim chain out of line (default 3)
- *   "query.seed"        closest point: bound each query by the triangle that answered the lane's previous query (default 1)
- *   "query.sil_kernel"  per-lane silhouette kernel: 1 = warp-shared leaf queue + shared-memory stack (default), 0 = per-lane parks
+ *   "query.sort_rays"   ray batches: 0 = caller's order, 1 = Morton order of the origins (default), 2 = direction octant, then origin
+ *   "query.cone_filter" silhouette normal-cone test: 0 = cone.cuh:168-212 verbatim; 1 = guard-banded sine-space evaluation on MUFU
+ *                       approximations, the verbatim chain out of line for everything inside the band (default)
+ *   "query.seed"        closest point: bit 0 = bound each query by the triangle that answered the lane's previous query (default 1);
+ *                       bit 1 = switch the per-triangle lower bound off
  *   "query.sil_seed"    silhouette: queue the leaf that answered the lane's previous query as a pruning hint (default 1)
- *   "query.sil_nodes"   silhouette: walk the 64 B compact records of a scene built with "build.compact_nodes" (default 0: slower)
+ *   "query.sil_tail"    silhouette: when a batch has been handed out, a warp with at most this many walking lanes passes them to a
+ *                       one-query-per-warp finishing launch (default 4; 0 = never)
  *   "query.sort_radius" bounded silhouette batches: 0 = Morton order only, 1 = search-radius octave then Morton, 2 = the same with
  *                       the largest radii first (default 2: the longest walks start first)
  *   "query.wide_max_n"  closest point: batches smaller than this — or with fewer than 2 queries per triangle — are walked one query
  *                       per warp (default 2097152; 0 = never)
  *   "query.wide_max_n_sil"  the same for silhouette batches (default 262144)
- *   "query.feed"        silhouette work distribution: 0 = one global chunk counter (default), 1 / 2 = a contiguous region per CTA / SM
+ *   "query.ray_kernel"  1 = reference-order ray walk with parked leaves (default), 0 = leaves tested where they are met
+ *   "query.ray_flush" / "query.ray_refill"  parked / idle lanes of a warp that trigger the triangle tests / the next draw (8 / 4)
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
- *   "build.compact_nodes" also emit the 64 B compact silhouette records (default 0); "build.refit_kernel" 1 = CTA-cooperative refit
- *                       (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort (default), 0 = three-kernel passes;
- *                       "adjacency.device" 1 = GPU silhouette adjacency (default when a device is present), 0 = host passes
+ *   "build.refit_kernel" 1 = CTA-cooperative refit (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort
+ *                       (default), 0 = three-kernel passes; "adjacency.device" 1 = GPU silhouette adjacency (default when a device
+ *                       is present), 0 = host passes
  * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel).
  *   "query.time_kernels" bracket every traversal kernel with CUDA events on the launching stream (default 0; see snch_scene_counter) */
 int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
@@ -211,6 +218,8 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
  *   "query.traversal_ms"        device time of the traversal kernels alone; needs "query.time_kernels" = 1 (synchronises the last one)
  *   "build.launches"            kernels of the last snch_scene_build */
 int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset);
+/* name of the traversal kernel the last *_batch call on this scene launched (static string; what bench.py puts in roofline.kernel) */
+const char *snch_scene_last_kernel(const snch_scene *s);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Generic builder.  Replaces lbvh::bvh<Real,dim,Object,AABBGetter,ConeGetter,MortonCalc>::construct()   bvh.cuh:380-613
@@ -254,8 +263,11 @@ int snch_scene2_export(const snch_scene2 *s, int kind, void *host_dst, uint64_t 
 int snch_scene2_set_option(snch_scene2 *s, const char *name, int64_t value); /* "query.sort_min_n", "query.sort_bits", "query.sort_rays", "query.blocks_per_sm", "query.wide_max_n" (batches below it walk one query per warp; default 131072) */
 int snch_closest_point_batch2(const snch_scene2 *s, const float *points_xy, uint64_t n, uint32_t *out_index, float *out_distance,
                               snch_stream stream);
+/* out_vertex / out_point_xy (optional, NULL = not wanted): index in scene<2>::silhouettes (= the vertex index) of a silhouette
+ * vertex attaining the distance and that vertex's position — `p` of silhouette_vertex::find_closest_silhouette_point
+ * (scene.cuh:354-356); 0xFFFFFFFF / (0,0) when the distance is +inf */
 int snch_closest_silhouette_batch2(const snch_scene2 *s, const float *points_xy, const uint8_t *flip, const float *r_max, uint64_t n,
-                                   float *out_distance, snch_stream stream);
+                                   float *out_distance, uint32_t *out_vertex, float *out_point_xy, snch_stream stream);
 int snch_intersect_batch2(const snch_scene2 *s, const float *origins_xy, const float *dirs_xy, const float *t_max, uint64_t n,
                           snch_hit *out_hits, uint8_t *out_found, int any_hit, snch_stream stream);
 int snch_sample_in_sphere_batch2(const snch_scene2 *s, const float *circles_xyr, const float *rnd2, uint64_t n, int32_t *out_index,

@@ -472,10 +472,12 @@ public:
         detail::check_status(snch_closest_point_batch2(batched(stream), &points->x, n, out_index, out_distance, stream));
     }
     // query_device(bvh_dev, nearest_silhouette(p, flip), silhouette_distance_calculator()); r_max optional search radii
+    // out_vertex / out_point (optional): index in silhouettes_d of a silhouette vertex attaining the distance, and its position
     void closest_silhouettes(const float2 *points, const unsigned char *flip, const float *r_max, std::size_t n, float *out_distance,
-                             cudaStream_t stream = nullptr) const
+                             cudaStream_t stream = nullptr, unsigned int *out_vertex = nullptr, float2 *out_point = nullptr) const
     {
-        detail::check_status(snch_closest_silhouette_batch2(batched(stream), &points->x, flip, r_max, n, out_distance, stream));
+        detail::check_status(snch_closest_silhouette_batch2(batched(stream), &points->x, flip, r_max, n, out_distance, out_vertex,
+                                                            out_point ? &out_point->x : nullptr, stream));
     }
     // query_device(bvh_dev, ray_intersect<any_hit>(ray(o, d), t_max), intersect_test()); snch_hit = {t, s, 0, segment}
     void intersect(const float2 *origins, const float2 *directions, const float *t_max, std::size_t n, snch_hit *out_hits, unsigned char *out_found,
@@ -830,10 +832,12 @@ public:
         detail::check_status(snch_closest_point_batch(built(), &points->x, n, out_index, out_distance, stream));
     }
     // query_device(bvh_dev, nearest_silhouette(p, flip), silhouette_distance_calculator()); r_max optional search radii
+    // out_edge / out_point (optional): index in silhouettes_d of an edge attaining the distance and the closest point on it —
+    // the values silhouette_edge::find_closest_silhouette_point computes and the reference drops
     void closest_silhouettes(const float3 *points, const unsigned char *flip, const float *r_max, std::size_t n, float *out_distance,
-                             cudaStream_t stream = nullptr) const
+                             cudaStream_t stream = nullptr, unsigned int *out_edge = nullptr, float3 *out_point = nullptr) const
     {
-        detail::check_status(snch_closest_silhouette_batch(built(), &points->x, flip, r_max, n, out_distance, stream));
+        detail::check_status(snch_closest_silhouette_batch(built(), &points->x, flip, r_max, n, out_distance, out_edge, out_point ? &out_point->x : nullptr, stream));
     }
     // query_device(bvh_dev, ray_intersect<any_hit>(ray(o, d), t_max), intersect_test())
     void intersect(const float3 *origins, const float3 *directions, const float *t_max, std::size_t n, snch_hit *out_hits, unsigned char *out_found,

@@ -57,6 +57,8 @@ def oracle_lib():
     L.orc_export_ranges.argtypes = [vp, _u32p]
     L.orc_closest.argtypes = [vp, _f32p, C.c_long, _u32p, _f32p, C.c_int]
     L.orc_silhouette.argtypes = [vp, _f32p, C.c_long, C.c_int, C.c_void_p, _f32p, C.c_int]
+    L.orc_silhouette_ex.argtypes = [vp, _f32p, C.c_long, C.c_int, C.c_void_p, _f32p, _i32p, _f32p, C.c_int]
+    L.orc_point_edge_distance.argtypes = [vp, _f32p, _i32p, C.c_long, _f32p, _f32p]
     L.orc_ray.argtypes = [vp, _f32p, _f32p, _f32p, C.c_long, C.c_int, _i32p, _f32p, _f32p, _u32p, C.c_int]
     L.orc_sample.argtypes = [vp, _f32p, _f32p, C.c_long, _i32p, _f32p, C.c_int]
     L.orc_sample_on_object.argtypes = [vp, _i32p, _f32p, _f32p, C.c_long, _f32p]
@@ -82,6 +84,7 @@ def oracle_lib():
     L.orc2_export_adjacency.argtypes = [vp, _i32p, _i32p]
     L.orc2_closest.argtypes = [vp, _f32p, C.c_long, _u32p, _f32p]
     L.orc2_silhouette.argtypes = [vp, _f32p, C.c_long, C.c_int, C.c_void_p, _f32p]
+    L.orc2_silhouette_ex.argtypes = [vp, _f32p, C.c_long, C.c_int, C.c_void_p, _f32p, _i32p, _f32p]
     L.orc2_ray.argtypes = [vp, _f32p, _f32p, C.c_void_p, C.c_long, _i32p, _f32p, _f32p, _u32p]
     L.orc2_sample.argtypes = [vp, _f32p, _f32p, C.c_long, _i32p, _f32p]
     _oracle_lib = L
@@ -167,6 +170,29 @@ class OracleScene:
             assert len(rm) == len(q)
         self.L.orc_silhouette(self.h, q, len(q), int(flip), rm.ctypes.data if rm is not None else None, dist, nthreads)
         return dist
+
+    def silhouette_ex(self, q, flip=False, r_max=None, nthreads=1):
+        """-> (distance, edge id int32 (-1 = none), closest point on that edge): the reference's walk plus the two values it
+        computes and drops (scene.cuh:796-799, query.cuh:386,411)."""
+        q = _f32(q).reshape(-1, 3)
+        dist = np.zeros(len(q), np.float32)
+        edge = np.zeros(len(q), np.int32)
+        point = np.zeros((len(q), 3), np.float32)
+        rm = None
+        if r_max is not None:
+            rm = _f32(r_max)
+            assert len(rm) == len(q)
+        self.L.orc_silhouette_ex(self.h, q, len(q), int(flip), rm.ctypes.data if rm is not None else None, dist, edge, point, nthreads)
+        return dist, edge, point
+
+    def point_edge_distance(self, q, edge):
+        """distance from q[i] to silhouette edge edge[i] and the closest point on it (scene.cuh:230-255)"""
+        q = _f32(q).reshape(-1, 3)
+        e = _i32(edge)
+        d = np.zeros(len(q), np.float32)
+        pt = np.zeros((len(q), 3), np.float32)
+        self.L.orc_point_edge_distance(self.h, q, e, len(q), d, pt)
+        return d, pt
 
     def ray(self, org, dirs, tmax=None, any_hit=False, nthreads=1, brute=False):
         org = _f32(org).reshape(-1, 3)
@@ -269,6 +295,14 @@ class OracleScene2:
         r = None if r_max is None else _f32(np.broadcast_to(r_max, (len(q),)))
         self.L.orc2_silhouette(self.h, q, len(q), int(flip), None if r is None else r.ctypes.data, dist)
         return dist
+
+    def silhouette_ex(self, q, flip=False, r_max=None):
+        """-> (distance, silhouette vertex id int32 (-1 = none), its position)"""
+        q = _f32(q).reshape(-1, 2)
+        dist, vid, pt = np.zeros(len(q), np.float32), np.zeros(len(q), np.int32), np.zeros((len(q), 2), np.float32)
+        r = None if r_max is None else _f32(np.broadcast_to(r_max, (len(q),)))
+        self.L.orc2_silhouette_ex(self.h, q, len(q), int(flip), None if r is None else r.ctypes.data, dist, vid, pt)
+        return dist, vid, pt
 
     def ray(self, org, dirs, tmax=None):
         org, dirs = _f32(org).reshape(-1, 2), _f32(dirs).reshape(-1, 2)

@@ -316,7 +316,8 @@ static int is_silhouette_edge(f3 pa, f3 pb, f3 n0, f3 n1, f3 view, float d, int 
     return dot0 * dot1 < 0.0f;
 }
 /* scene.cuh:788-824 */
-static int edge_closest_silhouette(const orc_scene *s, const int *e, f3 origin, float max_r2, float *distance, int flip, float min_r2)
+/* `point` (optional): closest_pos, the value the reference computes at :796-799 and does not return */
+static int edge_closest_silhouette(const orc_scene *s, const int *e, f3 origin, float max_r2, float *distance, int flip, float min_r2, f3 *point)
 {
     if (min_r2 >= max_r2) return 0;
     const f3 pa = s->verts[e[1]], pb = s->verts[e[2]];
@@ -329,21 +330,25 @@ static int edge_closest_silhouette(const orc_scene *s, const int *e, f3 origin, 
         const f3 n0 = edge_face_normal(s, e, 0, 1), n1 = edge_face_normal(s, e, 1, 1);
         is_sil = is_silhouette_edge(pa, pb, n0, n1, sub3(origin, cp), d, flip);
     }
-    if (is_sil && d * d <= max_r2) { *distance = d; return 1; }
+    if (is_sil && d * d <= max_r2) { *distance = d; if (point) *point = cp; return 1; }
     return 0;
 }
 /* scene.cuh:978-1003 — silhouette_distance_calculator over the <=3 owned edges of one triangle */
-static int tri_closest_silhouette(const orc_scene *s, int tri, f3 origin, float max_r2, float *distance, int flip, float min_r2)
+/* `edge` / `point` (optional): id of the owned edge that set *distance and the closest point on it ("TODO: identify nearest
+ * index", query.cuh:386,411) */
+static int tri_closest_silhouette(const orc_scene *s, int tri, f3 origin, float max_r2, float *distance, int flip, float min_r2, int *edge,
+                                  f3 *point)
 {
     float detached = max_r2;
     int ret = 0;
     for (int i = 0; i < 3; ++i)
     {
         const int ei = s->tri_owned[3 * tri + i];
-        if (ei != -1 && edge_closest_silhouette(s, s->edges + 4 * ei, origin, detached, distance, flip, min_r2))
+        if (ei != -1 && edge_closest_silhouette(s, s->edges + 4 * ei, origin, detached, distance, flip, min_r2, point))
         {
             ret = 1;
             detached = *distance * *distance;
+            if (edge) *edge = ei;
         }
     }
     return ret;
@@ -869,16 +874,27 @@ static void closest_one(const orc_scene *s, f3 p, uint32_t *idx, float *dist)
 }
 
 /* query.cuh:325-423 */
-static float silhouette_one(const orc_scene *s, f3 p, int flip, float r_max)
+/* edge_out / point_out (optional): the silhouette edge that attains the returned distance and the closest point on it; -1 and
+ * (0,0,0) when nothing is found.  The walk and the distance are the reference's; these are the two values it drops. */
+static float silhouette_one_ex(const orc_scene *s, f3 p, int flip, float r_max, int *edge_out, f3 *point_out)
 {
+    int best_edge = -1;
+    f3 best_pt = mk3(0.0f, 0.0f, 0.0f);
+    if (edge_out) *edge_out = -1;
+    if (point_out) *point_out = best_pt;
     if (s->nT == 0) return INFINITY;
     float best = r_max; /* +inf in the reference (query.cuh:343) */
     int found_any = 0;
     if (s->nT == 1)
     { /* Q6 */
         float d = INFINITY;
-        if (cone_valid(&s->cones[0]) && tri_closest_silhouette(s, (int)s->nodes[0].object, p, best * best, &d, flip, 0.0f) && d <= best)
+        if (cone_valid(&s->cones[0]) && tri_closest_silhouette(s, (int)s->nodes[0].object, p, best * best, &d, flip, 0.0f, &best_edge, &best_pt) &&
+            d <= best)
+        {
+            if (edge_out) *edge_out = best_edge;
+            if (point_out) *point_out = best_pt;
             return d;
+        }
         return INFINITY;
     }
     stack_entry st[STACK_CAP];
@@ -903,14 +919,22 @@ static float silhouette_one(const orc_scene *s, f3 p, int flip, float r_max)
             if (obj != LEAF_NONE)
             {
                 float d = INFINITY;
-                const int found = tri_closest_silhouette(s, (int)obj, p, best * best, &d, flip, 0.0f);
-                if (found && d <= best) { best = d; found_any = 1; }
+                int e_at = -1;
+                f3 p_at = mk3(0.0f, 0.0f, 0.0f);
+                const int found = tri_closest_silhouette(s, (int)obj, p, best * best, &d, flip, 0.0f, &e_at, &p_at);
+                if (found && d <= best) { best = d; found_any = 1; best_edge = e_at; best_pt = p_at; }
             }
             else { st[sp].node = ch[c]; st[sp].key = md[c]; ++sp; }
         }
     } while (sp > 0);
+    if (found_any)
+    {
+        if (edge_out) *edge_out = best_edge;
+        if (point_out) *point_out = best_pt;
+    }
     return found_any ? best : INFINITY;
 }
+static float silhouette_one(const orc_scene *s, f3 p, int flip, float r_max) { return silhouette_one_ex(s, p, flip, r_max, NULL, NULL); }
 
 /* query.cuh:79-169 */
 static void ray_one(const orc_scene *s, f3 org, f3 dir, float max_dist, int any_hit, int *found, float *t, float *uv, uint32_t *prim)
@@ -1011,8 +1035,14 @@ static void *job_run(void *arg)
             closest_one(s, mk3(j->a[3 * i], j->a[3 * i + 1], j->a[3 * i + 2]), &j->oidx[i], &j->of0[i]);
             break;
         case K_SIL:
-            j->of0[i] = silhouette_one(s, mk3(j->a[3 * i], j->a[3 * i + 1], j->a[3 * i + 2]), j->flip, j->b ? j->b[i] : INFINITY);
+        {
+            int e_at;
+            f3 p_at;
+            j->of0[i] = silhouette_one_ex(s, mk3(j->a[3 * i], j->a[3 * i + 1], j->a[3 * i + 2]), j->flip, j->b ? j->b[i] : INFINITY, &e_at, &p_at);
+            if (j->oint) j->oint[i] = e_at;
+            if (j->of1) { j->of1[3 * i] = p_at.x; j->of1[3 * i + 1] = p_at.y; j->of1[3 * i + 2] = p_at.z; }
             break;
+        }
         case K_RAY:
             ray_one(s, mk3(j->a[3 * i], j->a[3 * i + 1], j->a[3 * i + 2]), mk3(j->b[3 * i], j->b[3 * i + 1], j->b[3 * i + 2]), j->c[i],
                     j->any_hit, &j->ofound[i], &j->of0[i], &j->of1[2 * i], &j->oidx[i]);
@@ -1083,6 +1113,24 @@ void orc_silhouette(const orc_scene *s, const float *q, long n, int flip, const 
     job_t j = {0};
     j.s = s; j.kind = K_SIL; j.a = q; j.b = r_max; j.flip = flip; j.of0 = dist;
     run_jobs(j, n, nthreads);
+}
+/* + edge[n] (silhouette edge id, -1 = none) and point[3n] (closest point on that edge) */
+void orc_silhouette_ex(const orc_scene *s, const float *q, long n, int flip, const float *r_max, float *dist, int *edge, float *point, int nthreads)
+{
+    job_t j = {0};
+    j.s = s; j.kind = K_SIL; j.a = q; j.b = r_max; j.flip = flip; j.of0 = dist; j.oint = edge; j.of1 = point;
+    run_jobs(j, n, nthreads);
+}
+/* distance from q[i] to silhouette edge edge[i] (closest_point_segment, scene.cuh:230-255) and the closest point on it */
+void orc_point_edge_distance(const orc_scene *s, const float *q, const int *edge, long n, float *dist, float *point)
+{
+    for (long i = 0; i < n; ++i)
+    {
+        const int *e = s->edges + 4 * edge[i];
+        f3 cp;
+        dist[i] = closest_point_segment(s->verts[e[1]], s->verts[e[2]], mk3(q[3 * i], q[3 * i + 1], q[3 * i + 2]), &cp);
+        point[3 * i] = cp.x; point[3 * i + 1] = cp.y; point[3 * i + 2] = cp.z;
+    }
 }
 void orc_ray(const orc_scene *s, const float *org, const float *dir, const float *tmax, long n, int any_hit, int *found, float *t,
              float *uv, uint32_t *prim, int nthreads)

@@ -37,6 +37,10 @@ void orc_closest(const orc_scene *s, const float *q, long n, uint32_t *idx, floa
 /* r_max may be NULL (reference behaviour: unbounded).  With r_max the search starts from best = r_max and
  * returns +inf when nothing is found inside. */
 void orc_silhouette(const orc_scene *s, const float *q, long n, int flip, const float *r_max, float *dist, int nthreads);
+/* the same walk, also returning the silhouette edge that attains the distance (-1 = none) and the closest point on it (the two
+ * values the reference computes and drops: scene.cuh:796-799, query.cuh:386,411) */
+void orc_silhouette_ex(const orc_scene *s, const float *q, long n, int flip, const float *r_max, float *dist, int *edge, float *point, int nthreads);
+void orc_point_edge_distance(const orc_scene *s, const float *q, const int *edge, long n, float *dist, float *point);
 void orc_ray(const orc_scene *s, const float *org, const float *dir, const float *tmax, long n, int any_hit, int *found,
              float *t, float *uv, uint32_t *prim, int nthreads);
 void orc_sample(const orc_scene *s, const float *sph4, const float *u, long n, int *idx, float *pdf, int nthreads);

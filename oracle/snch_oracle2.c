@@ -209,7 +209,8 @@ static int vert_closest_silhouette(const orc_scene2 *s, const int *v4, f2 origin
     }
     return 0;
 }
-static int seg_closest_silhouette(const orc_scene2 *s, int seg, f2 origin, float max_r2, float *distance, int flip, float min_r2)
+/* `vertex` (optional): the owned silhouette vertex that set *distance ("TODO: identify nearest index", query.cuh:386,411) */
+static int seg_closest_silhouette(const orc_scene2 *s, int seg, f2 origin, float max_r2, float *distance, int flip, float min_r2, int *vertex)
 {
     int ret = 0;
     for (int i = 0; i < 2; ++i)
@@ -220,6 +221,7 @@ static int seg_closest_silhouette(const orc_scene2 *s, int seg, f2 origin, float
         {
             ret = 1;
             max_r2 = *distance * *distance;
+            if (vertex) *vertex = v;
         }
     }
     return ret;
@@ -578,22 +580,30 @@ void orc2_closest(const orc_scene2 *s, const float *q, long n, uint32_t *idx, fl
     }
 }
 /* query.cuh:325-423; r_max may be NULL (the reference's unbounded search) */
-void orc2_silhouette(const orc_scene2 *s, const float *q, long n, int flip, const float *r_max, float *dist)
+/* vertex / point (optional): the silhouette vertex that attains dist[i] (-1 = none) and its position (silhouette_vertex::
+ * find_closest_silhouette_point's `p`, scene.cuh:354-356) */
+void orc2_silhouette_ex(const orc_scene2 *s, const float *q, long n, int flip, const float *r_max, float *dist, int *vertex, float *point)
 {
     for (long i = 0; i < n; ++i)
     {
         const f2 p = mk2(q[2 * i], q[2 * i + 1]);
         float best = r_max ? r_max[i] : INFINITY;
-        int found_any = 0;
+        int found_any = 0, best_v = -1;
         dist[i] = INFINITY;
+        if (vertex) vertex[i] = -1;
+        if (point) point[2 * i] = point[2 * i + 1] = 0.0f;
         if (s->nS == 0) continue;
         if (s->nS == 1)
         { /* Q6 */
             float d = INFINITY;
             const float m = box_mindist(s->aabbs[0], p);
             if (m <= best * best && cone_valid(&s->cones[0]) && cone_overlap(&s->cones[0], p, s->aabbs[0], m) &&
-                seg_closest_silhouette(s, 0, p, best * best, &d, flip, 0.0f) && d <= best)
+                seg_closest_silhouette(s, 0, p, best * best, &d, flip, 0.0f, &best_v) && d <= best)
+            {
                 dist[i] = d;
+                if (vertex) vertex[i] = best_v;
+                if (point) { const f2 vp = s->verts[s->vert4[4 * best_v + 1]]; point[2 * i] = vp.x; point[2 * i + 1] = vp.y; }
+            }
             continue;
         }
         stack_entry st[STACK_CAP];
@@ -618,13 +628,23 @@ void orc2_silhouette(const orc_scene2 *s, const float *q, long n, int flip, cons
                 if (obj != NONE)
                 {
                     float d = INFINITY;
-                    if (seg_closest_silhouette(s, (int)obj, p, best * best, &d, flip, 0.0f) && d <= best) { best = d; found_any = 1; }
+                    int v_at = -1;
+                    if (seg_closest_silhouette(s, (int)obj, p, best * best, &d, flip, 0.0f, &v_at) && d <= best) { best = d; found_any = 1; best_v = v_at; }
                 }
                 else { st[sp].node = ch[c]; st[sp].key = md[c]; ++sp; }
             }
         } while (sp > 0);
-        if (found_any) dist[i] = best;
+        if (found_any)
+        {
+            dist[i] = best;
+            if (vertex) vertex[i] = best_v;
+            if (point) { const f2 vp = s->verts[s->vert4[4 * best_v + 1]]; point[2 * i] = vp.x; point[2 * i + 1] = vp.y; }
+        }
     }
+}
+void orc2_silhouette(const orc_scene2 *s, const float *q, long n, int flip, const float *r_max, float *dist)
+{
+    orc2_silhouette_ex(s, q, n, flip, r_max, dist, NULL, NULL);
 }
 /* query.cuh:79-169 */
 void orc2_ray(const orc_scene2 *s, const float *org, const float *dir, const float *tmax, long n, int *found, float *t, float *sp_out, uint32_t *prim)

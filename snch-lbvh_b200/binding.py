@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "snch_scene_build", "snch_scene_stats", "snch_scene_device_repr", "snch_scene_export", "snch_closest_point_batch",
     "snch_closest_silhouette_batch", "snch_intersect_batch", "snch_sample_in_sphere_batch", "snch_scene_arena",
     "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter", "snch_lbvh_build", "snch_scene_update_vertices",
-    "snch_wost_step_batch", "snch_scene_save", "snch_scene_load",
+    "snch_wost_step_batch", "snch_scene_save", "snch_scene_load", "snch_scene_last_kernel",
     "snch_scene2_create", "snch_scene2_destroy", "snch_scene2_compute_silhouettes", "snch_scene2_build", "snch_scene2_stats",
     "snch_scene2_device_repr", "snch_scene2_export", "snch_scene2_set_option", "snch_closest_point_batch2",
     "snch_closest_silhouette_batch2", "snch_intersect_batch2", "snch_sample_in_sphere_batch2",
@@ -54,7 +54,8 @@ class WostIO(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("points_xyz", C.c_void_p), ("flip", C.c_void_p),
                 ("dirs_xyz", C.c_void_p), ("rnd_uvw", C.c_void_p), ("closest_index", C.c_void_p), ("closest_distance", C.c_void_p),
                 ("silhouette_distance", C.c_void_p), ("star_radius", C.c_void_p), ("hits", C.c_void_p), ("found", C.c_void_p),
-                ("sample_index", C.c_void_p), ("sample_pdf", C.c_void_p), ("sample_point_xyz", C.c_void_p)]
+                ("sample_index", C.c_void_p), ("sample_pdf", C.c_void_p), ("sample_point_xyz", C.c_void_p),
+                ("silhouette_edge", C.c_void_p), ("silhouette_point_xyz", C.c_void_p)]
 
 
 class BuildStats(C.Structure):
@@ -102,7 +103,7 @@ def lib():
     L.snch_scene_device_repr.argtypes = [vp, C.POINTER(BvhDevicePod)]
     L.snch_scene_export.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.snch_closest_point_batch.argtypes = [vp, vp, u64, vp, vp, vp]
-    L.snch_closest_silhouette_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    L.snch_closest_silhouette_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]
     L.snch_intersect_batch.argtypes = [vp, vp, vp, vp, u64, vp, vp, C.c_int, vp]
     L.snch_sample_in_sphere_batch.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     L.snch_scene_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
@@ -123,12 +124,14 @@ def lib():
     L.snch_scene2_export.argtypes = [vp, C.c_int, vp, u64]
     L.snch_scene2_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.snch_closest_point_batch2.argtypes = [vp, vp, u64, vp, vp, vp]
-    L.snch_closest_silhouette_batch2.argtypes = [vp, vp, vp, vp, u64, vp, vp]
+    L.snch_closest_silhouette_batch2.argtypes = [vp, vp, vp, vp, u64, vp, vp, vp, vp]
     L.snch_intersect_batch2.argtypes = [vp, vp, vp, vp, u64, vp, vp, C.c_int, vp]
     L.snch_sample_in_sphere_batch2.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
+    L.snch_scene_last_kernel.argtypes = [vp]
     for name in ABI_SYMBOLS:
-        if name not in ("snch_last_error",):
+        if name not in ("snch_last_error", "snch_scene_last_kernel"):
             getattr(L, name).restype = C.c_int
+    L.snch_scene_last_kernel.restype = C.c_char_p
     _lib = L
     return L
 
@@ -224,7 +227,7 @@ class Scene3:
         a = _Arg(vertices, np.float32, (3,))
         if a.n != self.stats()["num_vertices"]:
             raise ValueError("update_vertices: vertex count differs from the scene's")
-        _check(self._L.snch_scene_update_vertices(self._h, a.ptr, _stream_ptr(stream)))
+        _check(self._L.snch_scene_update_vertices(self._h, a.ptr, _stream_ptr(stream, a)))
         if not a.torch:
             self.vertices_h = a.obj
         return self
@@ -286,19 +289,29 @@ class Scene3:
         q = _Arg(points, np.float32, (3,))
         idx, ip = _out(q, (q.n,), np.uint32)
         dist, dp = _out(q, (q.n,), np.float32)
-        _check(self._L.snch_closest_point_batch(self._h, q.ptr, q.n, ip, dp, _stream_ptr(stream)))
+        _check(self._L.snch_closest_point_batch(self._h, q.ptr, q.n, ip, dp, _stream_ptr(stream, q)))
         return idx, dist
 
-    def closest_silhouette(self, points, flip=None, r_max=None, stream=None):
-        """-> distance float32 (+inf when none).  query_device(bvh, nearest_silhouette(p, flip), ...)"""
+    def closest_silhouette(self, points, flip=None, r_max=None, stream=None, with_edge=False):
+        """-> distance float32 (+inf when none).  query_device(bvh, nearest_silhouette(p, flip), ...)
+        with_edge=True -> (distance, edge index uint32 (0xFFFFFFFF when none), closest point on that edge float32[n, 3])."""
         q = _Arg(points, np.float32, (3,))
         if isinstance(flip, (bool, np.bool_)):
             flip = None if not flip else (np.ones(q.n, np.uint8) if not q.torch else _torch_full(q, 1))
         f = _Arg(flip, np.uint8, None, allow_none=True)
         r = _Arg(r_max, np.float32, None, allow_none=True)
         dist, dp = _out(q, (q.n,), np.float32)
-        _check(self._L.snch_closest_silhouette_batch(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, _stream_ptr(stream)))
-        return dist
+        if not with_edge:
+            _check(self._L.snch_closest_silhouette_batch(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, None, None, _stream_ptr(stream, q)))
+            return dist
+        edge, ep = _out(q, (q.n,), np.uint32)
+        pt, pp = _out(q, (q.n, 3), np.float32)
+        _check(self._L.snch_closest_silhouette_batch(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, ep, pp, _stream_ptr(stream, q)))
+        return dist, edge, pt
+
+    def last_kernel(self) -> str:
+        """Name of the traversal kernel the last batched call launched (include/snch_b200.h: snch_scene_last_kernel)."""
+        return self._L.snch_scene_last_kernel(self._h).decode()
 
     def intersect(self, origins, directions, t_max=None, any_hit=False, stream=None):
         """-> (found uint8, hits[t,u,v,prim]).  query_device(bvh, ray_intersect<any_hit>(ray, max_dist), intersect_test())"""
@@ -307,7 +320,7 @@ class Scene3:
         tm = _Arg(t_max, np.float32, None, allow_none=True)
         found, fp = _out(o, (o.n,), np.uint8)
         if any_hit:
-            _check(self._L.snch_intersect_batch(self._h, o.ptr, d.ptr, tm.ptr, o.n, None, fp, 1, _stream_ptr(stream)))
+            _check(self._L.snch_intersect_batch(self._h, o.ptr, d.ptr, tm.ptr, o.n, None, fp, 1, _stream_ptr(stream, o)))
             return found, None
         if o.torch:
             import torch
@@ -316,7 +329,7 @@ class Scene3:
         else:
             hits = np.zeros(o.n, HIT_DTYPE)
             hp = hits.ctypes.data
-        _check(self._L.snch_intersect_batch(self._h, o.ptr, d.ptr, tm.ptr, o.n, hp, fp, 0, _stream_ptr(stream)))
+        _check(self._L.snch_intersect_batch(self._h, o.ptr, d.ptr, tm.ptr, o.n, hp, fp, 0, _stream_ptr(stream, o)))
         return found, hits
 
     def sample_in_sphere(self, spheres, rnd, stream=None):
@@ -326,10 +339,10 @@ class Scene3:
         idx, ip = _out(s, (s.n,), np.int32)
         pdf, pp = _out(s, (s.n,), np.float32)
         pt, tp = _out(s, (s.n, 3), np.float32)
-        _check(self._L.snch_sample_in_sphere_batch(self._h, s.ptr, r.ptr, s.n, ip, pp, tp, _stream_ptr(stream)))
+        _check(self._L.snch_sample_in_sphere_batch(self._h, s.ptr, r.ptr, s.n, ip, pp, tp, _stream_ptr(stream, s)))
         return idx, pdf, pt
 
-    def wost_step(self, points, directions=None, rnd=None, flip=None, stream=None) -> dict:
+    def wost_step(self, points, directions=None, rnd=None, flip=None, stream=None, with_edge=False) -> dict:
         """One wavefront walk-on-stars step per walker (include/snch_b200.h: snch_wost_step_batch): closest point, silhouette
         within the closest distance, star radius = min of both, ray along `directions` up to the star radius, triangle sampled
         in the star sphere.  Returns a dict of arrays (numpy in -> numpy out, torch CUDA in -> torch out)."""
@@ -344,6 +357,9 @@ class Scene3:
         out["closest_distance"], io.closest_distance = _out(q, (q.n,), np.float32)
         out["silhouette_distance"], io.silhouette_distance = _out(q, (q.n,), np.float32)
         out["star_radius"], io.star_radius = _out(q, (q.n,), np.float32)
+        if with_edge:
+            out["silhouette_edge"], io.silhouette_edge = _out(q, (q.n,), np.uint32)
+            out["silhouette_point"], io.silhouette_point_xyz = _out(q, (q.n, 3), np.float32)
         if d.ptr:
             out["found"], io.found = _out(q, (q.n,), np.uint8)
             if q.torch:
@@ -357,7 +373,7 @@ class Scene3:
             out["sample_index"], io.sample_index = _out(q, (q.n,), np.int32)
             out["sample_pdf"], io.sample_pdf = _out(q, (q.n,), np.float32)
             out["sample_point"], io.sample_point_xyz = _out(q, (q.n, 3), np.float32)
-        _check(self._L.snch_wost_step_batch(self._h, C.byref(io), q.n, _stream_ptr(stream)))
+        _check(self._L.snch_wost_step_batch(self._h, C.byref(io), q.n, _stream_ptr(stream, q)))
         return out
 
     # -- replication (multi-GPU) ---------------------------------------------------------------------------------
@@ -454,19 +470,25 @@ class Scene2:
         q = _Arg(points, np.float32, (2,))
         idx, ip = _out(q, (q.n,), np.uint32)
         dist, dp = _out(q, (q.n,), np.float32)
-        _check(self._L.snch_closest_point_batch2(self._h, q.ptr, q.n, ip, dp, _stream_ptr(stream)))
+        _check(self._L.snch_closest_point_batch2(self._h, q.ptr, q.n, ip, dp, _stream_ptr(stream, q)))
         return idx, dist
 
-    def closest_silhouette(self, points, flip=None, r_max=None, stream=None):
-        """-> distance float32 (+inf when none).  query_device(bvh, nearest_silhouette(p, flip), silhouette_distance_calculator())"""
+    def closest_silhouette(self, points, flip=None, r_max=None, stream=None, with_vertex=False):
+        """-> distance float32 (+inf when none).  query_device(bvh, nearest_silhouette(p, flip), silhouette_distance_calculator())
+        with_vertex=True -> (distance, silhouette vertex index uint32 (0xFFFFFFFF when none), its position float32[n, 2])."""
         q = _Arg(points, np.float32, (2,))
         if isinstance(flip, (bool, np.bool_)):
             flip = None if not flip else (np.ones(q.n, np.uint8) if not q.torch else _torch_full(q, 1))
         f = _Arg(flip, np.uint8, None, allow_none=True)
         r = _Arg(r_max, np.float32, None, allow_none=True)
         dist, dp = _out(q, (q.n,), np.float32)
-        _check(self._L.snch_closest_silhouette_batch2(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, _stream_ptr(stream)))
-        return dist
+        if not with_vertex:
+            _check(self._L.snch_closest_silhouette_batch2(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, None, None, _stream_ptr(stream, q)))
+            return dist
+        vid, vp_ = _out(q, (q.n,), np.uint32)
+        pt, pp = _out(q, (q.n, 2), np.float32)
+        _check(self._L.snch_closest_silhouette_batch2(self._h, q.ptr, f.ptr, r.ptr, q.n, dp, vp_, pp, _stream_ptr(stream, q)))
+        return dist, vid, pt
 
     def intersect(self, origins, directions, t_max=None, any_hit=False, stream=None):
         """-> (found uint8, hits[t,u=s,v=0,prim]).  query_device(bvh, ray_intersect<any_hit>(ray, max_dist), intersect_test())"""
@@ -475,7 +497,7 @@ class Scene2:
         tm = _Arg(t_max, np.float32, None, allow_none=True)
         found, fp = _out(o, (o.n,), np.uint8)
         if any_hit:
-            _check(self._L.snch_intersect_batch2(self._h, o.ptr, d.ptr, tm.ptr, o.n, None, fp, 1, _stream_ptr(stream)))
+            _check(self._L.snch_intersect_batch2(self._h, o.ptr, d.ptr, tm.ptr, o.n, None, fp, 1, _stream_ptr(stream, o)))
             return found, None
         if o.torch:
             import torch
@@ -484,7 +506,7 @@ class Scene2:
         else:
             hits = np.zeros(o.n, HIT_DTYPE)
             hp = hits.ctypes.data
-        _check(self._L.snch_intersect_batch2(self._h, o.ptr, d.ptr, tm.ptr, o.n, hp, fp, 0, _stream_ptr(stream)))
+        _check(self._L.snch_intersect_batch2(self._h, o.ptr, d.ptr, tm.ptr, o.n, hp, fp, 0, _stream_ptr(stream, o)))
         return found, hits
 
     def sample_in_sphere(self, circles, rnd, stream=None):
@@ -494,12 +516,18 @@ class Scene2:
         idx, ip = _out(s, (s.n,), np.int32)
         pdf, pp = _out(s, (s.n,), np.float32)
         pt, tp = _out(s, (s.n, 2), np.float32)
-        _check(self._L.snch_sample_in_sphere_batch2(self._h, s.ptr, r.ptr, s.n, ip, pp, tp, _stream_ptr(stream)))
+        _check(self._L.snch_sample_in_sphere_batch2(self._h, s.ptr, r.ptr, s.n, ip, pp, tp, _stream_ptr(stream, s)))
         return idx, pdf, pt
 
 
-def _stream_ptr(stream):
+def _stream_ptr(stream, like=None):
+    """cudaStream_t for the call.  With torch CUDA arguments and no explicit stream, torch's CURRENT stream of that device:
+    inputs and outputs were produced / allocated in that stream's order (the legacy default stream would not wait for a
+    non-blocking torch stream, and the caching allocator could reuse a temporary while the kernel still reads it)."""
     if stream is None:
+        if like is not None and getattr(like, "torch", False):
+            import torch
+            return C.c_void_p(torch.cuda.current_stream(like.obj.device).cuda_stream)
         return None
     if hasattr(stream, "cuda_stream"):
         return C.c_void_p(stream.cuda_stream)

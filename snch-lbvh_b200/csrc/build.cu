@@ -95,7 +95,7 @@ void compute_adjacency_host(snch_scene *s)
 // ---------------------------------------------------------------------------------------------------------------
 // arena layout
 // ---------------------------------------------------------------------------------------------------------------
-static void layout_arena(ArenaHeader &h, uint32_t nV, uint32_t nT, uint32_t nE, bool compact_nodes)
+void layout_arena(ArenaHeader &h, uint32_t nV, uint32_t nT, uint32_t nE)
 {
     std::memset(&h, 0, sizeof h);
     h.magic = kArenaMagic;
@@ -126,7 +126,6 @@ static void layout_arena(ArenaHeader &h, uint32_t nV, uint32_t nT, uint32_t nE, 
     h.off_q1 = take((uint64_t)h.n_nodes);
     h.off_bnode = take(n_rec * sizeof(BNode));
     h.off_snode = take(n_rec * sizeof(SNode));
-    h.off_cnode = compact_nodes ? take(n_rec * sizeof(CNode)) : 0; // optional ("build.compact_nodes")
     h.off_ltri = take((uint64_t)nT * sizeof(LTri));
     h.off_ledge = take((uint64_t)nE * sizeof(LEdge));
     h.off_edge_off = take((uint64_t)nT * 4);
@@ -149,7 +148,6 @@ void resolve_view(snch_scene *s)
     v.snode = (const SNode *)(b + h.off_snode);
     v.ltri = (const LTri *)(b + h.off_ltri);
     v.ledge = (const LEdge *)(b + h.off_ledge);
-    v.cnode = h.off_cnode ? (const CNode *)(b + h.off_cnode) : nullptr;
     v.edge_off = (const uint32_t *)(b + h.off_edge_off);
 }
 
@@ -331,8 +329,8 @@ SNCH_DI Cone load_cone_cg(const RefCone *src)
     return c;
 }
 // `left` / `right` are the children's node ids (internal < n_internal <= leaf), as in RefNode
-SNCH_DI void store_records(BNode *bn, SNode *sn, CNode *cn, Box lb, Box rb, Cone lc, Cone rc, uint32_t lbref, uint32_t rbref, uint32_t lsref,
-                           uint32_t rsref, uint32_t parent, uint32_t left, uint32_t right, uint32_t n_internal)
+SNCH_DI void store_records(BNode *bn, SNode *sn, Box lb, Box rb, Cone lc, Cone rc, uint32_t lbref, uint32_t rbref, uint32_t lsref, uint32_t rsref,
+                           uint32_t parent)
 {
     const float4 a = make_float4(lb.lo.x, lb.lo.y, lb.lo.z, lb.hi.x);
     const float4 b = make_float4(lb.hi.y, lb.hi.z, rb.lo.x, rb.lo.y);
@@ -349,17 +347,6 @@ SNCH_DI void store_records(BNode *bn, SNode *sn, CNode *cn, Box lb, Box rb, Cone
     sp[3] = make_float4(lc.axis.x, lc.axis.y, lc.axis.z, lc.half_angle);
     sp[4] = make_float4(lc.radius, rc.axis.x, rc.axis.y, rc.axis.z);
     sp[5] = make_float4(rc.half_angle, rc.radius, __uint_as_float(lsref), __uint_as_float(rsref));
-    if (!cn) return;
-    const bool lleaf = left >= n_internal, rleaf = right >= n_internal;
-    const uint32_t split = lleaf ? left - n_internal : left; // Karras: left = split (+ n_internal if a leaf), right = split + 1 (+ ...)
-    const uint64_t c0 = qcone_encode(lc, lb.lo, lb.hi), c1 = qcone_encode(rc, rb.lo, rb.hi);
-    float4 *cp = reinterpret_cast<float4 *>(cn);
-    cp[0] = a;
-    cp[1] = b;
-    cp[2] = c;
-    cp[3] = make_float4(__uint_as_float(split | (lleaf ? 0x40000000u : 0u) | (rleaf ? 0x80000000u : 0u)), __uint_as_float((uint32_t)c0),
-                        __uint_as_float((uint32_t)(c0 >> 32) | ((uint32_t)c1 << 16)), __uint_as_float((uint32_t)(c1 >> 16)));
-    (void)right;
 }
 
 // Leaf part of the refit, one thread per leaf k in Morton order: leaf box (scene.cuh:870-885), leaf normal cone from the
@@ -424,7 +411,7 @@ SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
         le[0] = make_float4(ea.x, ea.y, ea.z, eb.x);
         le[1] = make_float4(eb.y, eb.z, boundary ? __int_as_float(0x7FC00000) : u0.x, u0.y);
         le[2] = make_float4(u0.z, u1.x, u1.y, u1.z);
-        le[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        le[3] = make_float4(__int_as_float(owned[s]), 0.0f, 0.0f, 0.0f); // the edge's id: what out_edge of a silhouette query reports
         ++cnt;
     }
     if (cnt == 0) cone.half_angle = -kPi;
@@ -469,8 +456,8 @@ SNCH_DI void refit_single_leaf(const BuildCtx &c, Box box, Cone cone, uint32_t p
     ncone.axis = V3{0.f, 0.f, 0.f};
     ncone.half_angle = -kPi;
     ncone.radius = 0.f;
-    store_records(c.bnode, c.snode, c.cnode, box, nb, cone, ncone, kLeafFlag | 0u, kLeafFlag | 0u, kLeafFlag | packed, kLeafFlag | 0u, kNone, 0u,
-                  1u, 0u); // left = leaf 0, right = a leaf that does not exist behind an invalid cone
+    store_records(c.bnode, c.snode, box, nb, cone, ncone, kLeafFlag | 0u, kLeafFlag | 0u, kLeafFlag | packed, kLeafFlag | 0u,
+                  kNone); // left = leaf 0, right = a leaf that does not exist behind an invalid cone
 }
 
 // The reference's bottom-up climb (bvh.cuh:520-554 boxes, :556-604 cones, fused; with the fences its cone pass lacks, Q7)
@@ -511,8 +498,8 @@ SNCH_DI void refit_climb(const BuildCtx &c, uint32_t cur, Box box, Cone cone, ui
         store_cone(c.cones + parent, pcn);
         c.q1[parent] = taint ? 1 : 0;
         const uint32_t gp = nd.x;
-        store_records(c.bnode + parent, c.snode + parent, c.cnode ? c.cnode + parent : nullptr, lb, rb, lc, rc, cur_is_left ? cur_bref : sib_bref,
-                      cur_is_left ? sib_bref : cur_bref, cur_is_left ? cur_sref : sib_sref, cur_is_left ? sib_sref : cur_sref, gp, l, r, ni);
+        store_records(c.bnode + parent, c.snode + parent, lb, rb, lc, rc, cur_is_left ? cur_bref : sib_bref, cur_is_left ? sib_bref : cur_bref,
+                      cur_is_left ? cur_sref : sib_sref, cur_is_left ? sib_sref : cur_sref, gp);
         cur = parent;
         box = pbx;
         cone = pcn;
@@ -658,8 +645,7 @@ __global__ void __launch_bounds__(kRefitLeaves, 8) k_refit_coop(BuildCtx c)
                     store_aabb(c.aabbs + parent, pbx);
                     store_cone(c.cones + parent, pcn);
                     c.q1[parent] = taint ? 1 : 0;
-                    store_records(c.bnode + parent, c.snode + parent, c.cnode ? c.cnode + parent : nullptr, lb, rb, lc, rc, sh.bref[l_id], sh.bref[r_id], sh.sref[l_id],
-                                  sh.sref[r_id], gp, l, r, ni);
+                    store_records(c.bnode + parent, c.snode + parent, lb, rb, lc, rc, sh.bref[l_id], sh.bref[r_id], sh.sref[l_id], sh.sref[r_id], gp);
                     const uint32_t pl = B + pj;
                     sh_put(sh, pl, pbx, pcn, parent, parent);
                     sh.taint[pl] = taint ? 1 : 0;
@@ -764,42 +750,28 @@ int build_device(snch_scene *s, cudaStream_t stream)
     SNCH_CUDA(cudaSetDevice(s->device));
     const uint32_t nV = s->n_verts, nT = s->n_tris, nE = s->n_edges;
     ArenaHeader h;
-    layout_arena(h, nV, nT, nE, s->opt_compact_nodes != 0);
+    layout_arena(h, nV, nT, nE);
     const uint32_t prev_collision = s->hdr.collision;
     // refit-only: Morton order, hierarchy and edge slots of the previous build stay; only geometry-dependent products change
     const bool refit = s->opt_refit_only && s->built && s->arena && s->arena_bytes == h.total_bytes && s->arena_has_topology;
-    bool repatch = false;
+    s->built = false; // set again only when every step below has succeeded: a failed rebuild never leaves a half-written tree queryable
     if (!s->arena || s->arena_bytes != h.total_bytes)
     {
-        unsigned char *fresh = nullptr;
-        if (cudaMalloc(&fresh, h.total_bytes) != cudaSuccess)
+        if (s->arena) cudaFree(s->arena);
+        s->arena = nullptr;
+        s->arena_bytes = 0;
+        s->arena_has_topology = false;
+        if (cudaMalloc(&s->arena, h.total_bytes) != cudaSuccess)
         {
             cudaGetLastError();
+            s->arena = nullptr;
             set_error("cudaMalloc of the scene arena failed");
             return SNCH_ERR_OOM;
         }
-        // same scene, different set of optional arrays ("build.compact_nodes" changed): the topology that only lives in the
-        // arena (input geometry + adjacency, laid out first) moves over; its embedded pointers are patched below
-        const bool keep = s->arena && s->arena_has_topology && s->hdr.n_tris == nT && s->hdr.n_verts == nV && s->hdr.n_edges == nE &&
-                          s->hdr.off_nodes == h.off_nodes;
-        if (keep)
-        {
-            SNCH_CUDA(cudaMemcpyAsync(fresh, s->arena, h.off_nodes, cudaMemcpyDeviceToDevice, stream));
-            SNCH_CUDA(cudaStreamSynchronize(stream));
-            repatch = true;
-        }
-        if (s->arena) cudaFree(s->arena);
-        s->arena = fresh;
-        s->arena_has_topology = keep;
         s->arena_bytes = h.total_bytes;
     }
     s->hdr = h;
     resolve_view(s);
-    if (repatch)
-    {
-        const int rc = patch_pointers(s, stream);
-        if (rc != SNCH_OK) return rc;
-    }
     unsigned char *b = s->arena;
 
     // ---- uploads (host arrays -> arena); the reference does these in its constructors (scene.cuh:1131, bvh.cuh:330).
@@ -898,7 +870,6 @@ int build_device(snch_scene *s, cudaStream_t stream)
     c.q1 = (uint8_t *)(b + h.off_q1);
     c.bnode = (BNode *)(b + h.off_bnode);
     c.snode = (SNode *)(b + h.off_snode);
-    c.cnode = h.off_cnode ? (CNode *)(b + h.off_cnode) : nullptr;
     c.ltri = (LTri *)(b + h.off_ltri);
     c.ledge = (LEdge *)(b + h.off_ledge);
     c.edge_off = (uint32_t *)(b + h.off_edge_off);
@@ -907,10 +878,18 @@ int build_device(snch_scene *s, cudaStream_t stream)
     c.escapes = (uint32_t *)(sc + o_esc);
     c.counters = (uint32_t *)(sc + o_cnt);
 
-    cudaEvent_t ev0, ev1;
-    SNCH_CUDA(cudaEventCreate(&ev0));
-    SNCH_CUDA(cudaEventCreate(&ev1));
-    SNCH_CUDA(cudaEventRecord(ev0, stream));
+    struct EventPair
+    { // destroyed on every exit path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair()
+        {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    SNCH_CUDA(cudaEventCreate(&ev.a));
+    SNCH_CUDA(cudaEventCreate(&ev.b));
+    SNCH_CUDA(cudaEventRecord(ev.a, stream));
 
     const unsigned g256 = (nT + 255) / 256;
     SNCH_CUDA(cudaMemsetAsync(c.flags, 0, (size_t)nT * 4, stream));
@@ -941,7 +920,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     launches += 1;
     s->build_launches = (uint64_t)launches;
     SNCH_CUDA(cudaGetLastError());
-    SNCH_CUDA(cudaEventRecord(ev1, stream));
+    SNCH_CUDA(cudaEventRecord(ev.b, stream));
 
     // ---- stats read-back + header
     uint32_t counters[2] = {0, 0};
@@ -949,9 +928,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     SNCH_CUDA(cudaMemcpyAsync(counters, c.counters, 8, cudaMemcpyDeviceToHost, stream));
     SNCH_CUDA(cudaMemcpyAsync(boxi, c.scene_box, 24, cudaMemcpyDeviceToHost, stream));
     SNCH_CUDA(cudaStreamSynchronize(stream));
-    SNCH_CUDA(cudaEventElapsedTime(&s->build_ms, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
+    SNCH_CUDA(cudaEventElapsedTime(&s->build_ms, ev.a, ev.b));
     s->hdr.collision = refit ? prev_collision : counters[0];
     s->hdr.q1_nodes = counters[1];
     for (int a = 0; a < 3; ++a)

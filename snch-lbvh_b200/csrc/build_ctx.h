@@ -20,7 +20,6 @@ struct BuildCtx
     uint8_t *q1;
     BNode *bnode;
     SNode *snode;
-    CNode *cnode;
     LTri *ltri;
     LEdge *ledge;
     uint32_t *edge_off;

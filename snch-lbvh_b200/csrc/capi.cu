@@ -352,8 +352,7 @@ int snch_scene_destroy(snch_scene *s)
     if (s->copy_in) cudaStreamDestroy(s->copy_in);
     if (s->copy_out) cudaStreamDestroy(s->copy_out);
     if (s->compute_b) cudaStreamDestroy(s->compute_b);
-    if (s->counters.ev0) cudaEventDestroy(s->counters.ev0);
-    if (s->counters.ev1) cudaEventDestroy(s->counters.ev1);
+    s->counters.release();
     delete s;
     return SNCH_OK;
 }
@@ -614,7 +613,7 @@ int snch_closest_point_batch(const snch_scene *cs, const float *pts, uint64_t n,
 }
 
 int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const uint8_t *flip, const float *r_max, uint64_t n,
-                                  float *out_distance, snch_stream stream)
+                                  float *out_distance, uint32_t *out_edge, float *out_point, snch_stream stream)
 {
     int st = check_built(cs);
     if (st != SNCH_OK) return st;
@@ -626,7 +625,7 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
     }
     snch_scene *s = const_cast<snch_scene *>(cs);
     SNCH_CUDA(cudaSetDevice(s->device));
-    const PtrKind k = common_kind({pts, flip, r_max, out_distance});
+    const PtrKind k = common_kind({pts, flip, r_max, out_distance, out_edge, out_point});
     if (k == PK_NULL)
     {
         set_error("snch_closest_silhouette_batch: mixed host/device pointers");
@@ -638,14 +637,16 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = query_scratch_bytes(cm, s->tuning);
-        const uint64_t stage = k == PK_DEVICE ? 0 : Stager::pad(m * 12) + Stager::pad(m) + 2 * Stager::pad(m * 4);
+        const uint64_t stage = k == PK_DEVICE ? 0 : 2 * Stager::pad(m * 12) + Stager::pad(m) + 3 * Stager::pad(m * 4);
         PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         const uint8_t *fo = flip ? flip + off : nullptr;
         const float *ro = r_max ? r_max + off : nullptr;
+        uint32_t *eo = out_edge ? out_edge + off : nullptr;
+        float *po = out_point ? out_point + 3 * off : nullptr;
         if (k == PK_DEVICE)
         {
-            st = launch_silhouette(s->view, s->tuning, pts + 3 * off, fo, ro, m, out_distance + off, buf.p, cst, &s->counters);
+            st = launch_silhouette(s->view, s->tuning, pts + 3 * off, fo, ro, m, out_distance + off, eo, po, buf.p, cst, &s->counters);
             if (st != SNCH_OK) return st;
             continue;
         }
@@ -654,9 +655,11 @@ int snch_closest_silhouette_batch(const snch_scene *cs, const float *pts, const 
         const uint8_t *df = sg.in(fo, 1);
         const float *dr = sg.in(ro, 4);
         float *dd = sg.out(out_distance + off, 4);
+        uint32_t *de = sg.out(eo, 4);
+        float *dp = sg.out(po, 12);
         st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
-            return launch_silhouette(s->view, s->tuning, dq + 3 * o, df ? df + o : nullptr, dr ? dr + o : nullptr, c, dd + o, buf.p + lane * qs, ls,
-                                     &s->counters);
+            return launch_silhouette(s->view, s->tuning, dq + 3 * o, df ? df + o : nullptr, dr ? dr + o : nullptr, c, dd + o, de ? de + o : nullptr,
+                                     dp ? dp + 3 * o : nullptr, buf.p + lane * qs, ls, &s->counters);
         });
         if (st != SNCH_OK) return st;
     }
@@ -774,26 +777,16 @@ int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset
     }
     const std::string k(name);
     QueryCounters &c = s->counters;
-    if (k == "query.launches") *value = (double)c.launches;
-    else if (k == "query.traversal_launches") *value = (double)c.traversal_launches;
+    if (k == "query.launches") *value = (double)c.launches.load();
+    else if (k == "query.traversal_launches") *value = (double)c.traversal_launches.load();
     else if (k == "query.traversal_ms")
     {
         cudaSetDevice(s->device);
         c.fold();
+        std::lock_guard<std::mutex> lock(c.mu);
         *value = c.traversal_ms;
     }
     else if (k == "build.launches") *value = (double)s->build_launches;
-    else if (k.rfind("query.sil_stats.", 0) == 0 && k.size() == 17 && k[16] >= '0' && k[16] <= '7')
-    { // cone tests, undecided, exact-only codes, warp steps, warp steps with an undecided test, node visits
-        unsigned long long st[8];
-        cudaSetDevice(s->device);
-        cudaDeviceSynchronize();
-        const int rc = read_sil_stats(st, false);
-        if (rc != SNCH_OK) return rc;
-        *value = (double)st[k[16] - '0'];
-        if (reset && k[16] == '7') read_sil_stats(st, true);
-        return SNCH_OK;
-    }
     else
     {
         set_error("snch_scene_counter: unknown counter '" + k + "'");
@@ -801,12 +794,13 @@ int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset
     }
     if (reset)
     {
-        c.fold();
-        c.launches = c.traversal_launches = 0;
-        c.traversal_ms = 0.0;
+        cudaSetDevice(s->device);
+        c.reset();
     }
     return SNCH_OK;
 }
+
+const char *snch_scene_last_kernel(const snch_scene *s) { return s ? s->counters.last_kernel.load() : ""; }
 
 int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
 {
@@ -820,23 +814,21 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     if (k == "query.sort_min_n") t.sort_min_n = (int)value;
     else if (k == "query.sort_bits") t.sort_bits = (int)value;
     else if (k == "query.sort_rays") t.sort_rays = (int)value;
-    else if (k == "query.packet") t.packet = (int)value;
     else if (k == "query.cone_filter") t.cone_filter = (int)value;
     else if (k == "query.seed") t.seed = (int)value;
-    else if (k == "query.sil_kernel") t.sil_kernel = (int)value;
-    else if (k == "query.feed") t.feed = (int)value;
     else if (k == "query.sort_radius") t.sort_radius = (int)value;
     else if (k == "query.sil_seed") t.sil_seed = (int)value;
+    else if (k == "query.sil_tail") t.sil_tail = (int)value;
     else if (k == "query.wide_max_n") t.wide_max_n = (int)value;
     else if (k == "query.wide_max_n_sil") t.wide_max_n_sil = (int)value;
-    else if (k == "query.sil_nodes") t.sil_nodes = (int)value;
-    else if (k == "query.sil_stats") t.sil_stats = (int)value;
+    else if (k == "query.ray_kernel") t.ray_kernel = (int)value;
+    else if (k == "query.ray_flush") t.ray_flush = (int)value;
+    else if (k == "query.ray_refill") t.ray_refill = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;
     else if (k == "build.refit_kernel") s->opt_refit_kernel = (int)value;
-    else if (k == "build.compact_nodes") s->opt_compact_nodes = (int)value; // takes effect at the next build
     else if (k == "sort.onesweep") set_sort_onesweep((int)value); // process-wide (A/B of the two radix sorts)
     else
     {
@@ -876,6 +868,22 @@ static int adopt_from(const void *src, bool src_is_host, uint64_t bytes, int dev
     {
         set_error(std::string(who) + ": not a scene arena (magic/version/size mismatch)");
         return SNCH_ERR_INVALID;
+    }
+    { // the header is untrusted input (a file, a peer's bytes): every count and offset must be exactly what this library lays
+      // out for (n_verts, n_tris, n_edges) — the traversal kernels and the pointer patch index the arena through them
+        ArenaHeader want;
+        if (h.n_tris <= 0x3FFFFFFFu) layout_arena(want, h.n_verts, h.n_tris, h.n_edges);
+        const bool same = h.n_tris <= 0x3FFFFFFFu && want.total_bytes == h.total_bytes && want.n_nodes == h.n_nodes && want.n_internal == h.n_internal &&
+                          want.off_vertices == h.off_vertices && want.off_edges == h.off_edges && want.off_objects == h.off_objects &&
+                          want.off_tri_edges == h.off_tri_edges && want.off_nodes == h.off_nodes && want.off_aabbs == h.off_aabbs &&
+                          want.off_cones == h.off_cones && want.off_morton == h.off_morton && want.off_sorted_idx == h.off_sorted_idx &&
+                          want.off_ranges == h.off_ranges && want.off_q1 == h.off_q1 && want.off_bnode == h.off_bnode && want.off_snode == h.off_snode &&
+                          want.off_ltri == h.off_ltri && want.off_ledge == h.off_ledge && want.off_edge_off == h.off_edge_off;
+        if (!same)
+        {
+            set_error(std::string(who) + ": arena header is inconsistent with its own counts (corrupt or foreign arena)");
+            return SNCH_ERR_INVALID;
+        }
     }
     snch_scene *s = new (std::nothrow) snch_scene();
     if (!s)
@@ -1062,7 +1070,7 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
     SNCH_CUDA(cudaSetDevice(s->device));
     const PtrKind k = common_kind({io->points_xyz, io->flip, io->dirs_xyz, io->rnd_uvw, io->closest_index, io->closest_distance,
                                    io->silhouette_distance, io->star_radius, io->hits, io->found, io->sample_index, io->sample_pdf,
-                                   io->sample_point_xyz});
+                                   io->sample_point_xyz, io->silhouette_edge, io->silhouette_point_xyz});
     if (k == PK_NULL)
     {
         set_error("snch_wost_step_batch: mixed host/device pointers");
@@ -1074,7 +1082,7 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
         const uint64_t m = n - off < kMaxLaunch ? n - off : kMaxLaunch;
         const uint64_t cm = k == PK_DEVICE ? m : host_chunk(s, m);
         const uint64_t qs = wost_scratch_bytes(cm, s->tuning);
-        const uint64_t stage = k == PK_DEVICE ? 0 : 4 * Stager::pad(m * 12) + 2 * Stager::pad(m) + 6 * Stager::pad(m * 4) + Stager::pad(m * 16);
+        const uint64_t stage = k == PK_DEVICE ? 0 : 5 * Stager::pad(m * 12) + 2 * Stager::pad(m) + 7 * Stager::pad(m * 4) + Stager::pad(m * 16);
         PoolBuffer buf(s, cst, k == PK_DEVICE ? qs : Stager::kLanes * qs + stage);
         if (buf.status != SNCH_OK) return buf.status;
         WostBuffers w;
@@ -1094,6 +1102,8 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
             w.sample_index = at(io->sample_index, 1);
             w.sample_pdf = at(io->sample_pdf, 1);
             w.sample_point = at(io->sample_point_xyz, 3);
+            w.silhouette_edge = at(io->silhouette_edge, 1);
+            w.silhouette_point = at(io->silhouette_point_xyz, 3);
             st = launch_wost_step(s->view, s->tuning, w, m, buf.p, cst, &s->counters);
             if (st != SNCH_OK) return st;
             continue;
@@ -1112,6 +1122,8 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
         w.sample_index = sg.out(at(io->sample_index, 1), 4);
         w.sample_pdf = sg.out(at(io->sample_pdf, 1), 4);
         w.sample_point = sg.out(at(io->sample_point_xyz, 3), 12);
+        w.silhouette_edge = sg.out(at(io->silhouette_edge, 1), 4);
+        w.silhouette_point = sg.out(at(io->silhouette_point_xyz, 3), 12);
         st = sg.run(cm, [&](uint64_t o, uint64_t c, cudaStream_t ls, int lane) {
             WostBuffers wc;
             auto sl = [&](auto *p, uint64_t stride) { return p ? p + stride * o : p; };
@@ -1128,6 +1140,8 @@ int snch_wost_step_batch(const snch_scene *cs, const snch_wost_io *io, uint64_t 
             wc.sample_index = sl(w.sample_index, 1);
             wc.sample_pdf = sl(w.sample_pdf, 1);
             wc.sample_point = sl(w.sample_point, 3);
+            wc.silhouette_edge = sl(w.silhouette_edge, 1);
+            wc.silhouette_point = sl(w.silhouette_point, 3);
             return launch_wost_step(s->view, s->tuning, wc, c, buf.p + lane * qs, ls, &s->counters);
         });
         if (st != SNCH_OK) return st;

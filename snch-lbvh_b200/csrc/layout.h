@@ -14,7 +14,7 @@ namespace snch
 {
 
 constexpr uint64_t kArenaMagic = 0x534e43484c425648ull; // "SNCHLBVH"
-constexpr uint32_t kArenaVersion = 3;
+constexpr uint32_t kArenaVersion = 4;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -66,16 +66,6 @@ struct __align__(32) SNode // 96 B: silhouette traversal = boxes + both normal c
     float4 e;       // radius0 axis1.xyz
     float4 f;       // half1 radius1 ref0(bits) ref1(bits)
 };
-// Compact silhouette record (2 sectors): both child boxes, the Karras split, and both normal cones as 48-bit filter codes
-// (snch_math.cuh qcone_*).  Children follow from the split: left = split, right = split + 1, each a leaf (sorted leaf position)
-// when its flag is set; a leaf's edge payload is looked up in edge_off[].  The exact cones stay in SNode for the few tests
-// the codes cannot decide.
-struct __align__(32) CNode // 64 B
-{
-    float4 a, b, c; // boxes as in BNode
-    uint32_t split; // bits 0-29 split position, bit 30 left child is a leaf, bit 31 right child is a leaf
-    uint32_t q0, q1, q2; // cone0 = bits 0-47, cone1 = bits 48-95 of (q0 | q1 << 32 | q2 << 64)
-};
 struct __align__(32) LTri // 64 B (two sectors, two 256-bit loads), Morton (leaf) order
 {
     float4 v0; // xyz, w = object index bits
@@ -88,9 +78,8 @@ struct __align__(32) LEdge // 64 B, grouped by owning leaf in Morton order
     float4 a; // pa.xyz pb.x
     float4 b; // pb.y pb.z n0.x n0.y       n0.x = NaN  <=> boundary edge (fewer than two faces: always a silhouette)
     float4 c; // n0.z n1.xyz
-    float4 pad;
+    float4 id; // x = edge id bits (index into scene<3>::silhouettes), yzw = 0
 };
-static_assert(sizeof(CNode) == 64, "record sizes");
 static_assert(sizeof(BNode) == 64 && sizeof(SNode) == 96 && sizeof(LTri) == 64 && sizeof(LEdge) == 64, "record sizes");
 
 struct ArenaHeader
@@ -110,8 +99,7 @@ struct ArenaHeader
     uint64_t off_morton, off_sorted_idx, off_ranges, off_q1;
     // traversal records
     uint64_t off_bnode, off_snode, off_ltri, off_ledge, off_edge_off;
-    uint64_t off_cnode;
-    uint64_t reserved[7];
+    uint64_t reserved[8];
 };
 
 // Device-side view with resolved pointers (built on the host from header + base; passed by value to kernels).
@@ -125,7 +113,6 @@ struct SceneView
     const SNode *snode;
     const LTri *ltri;
     const LEdge *ledge;
-    const CNode *cnode;
     const uint32_t *edge_off; // per sorted leaf: (first_edge << 2) | edge_count
 };
 

@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(256) k_query_bounds(const float *__restrict__ 
 // With `radius` (silhouette star radii) the top 4 key bits are the radius octave relative to the batch extent, so the 32
 // queries a warp walks together also have similar search radii (a scheduling hint only: any key is correct).
 __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q, int stride, int dims, uint32_t n, const int *__restrict__ box,
-                                                    const float *__restrict__ radius, int radius_desc, uint32_t *__restrict__ keys,
-                                                    uint32_t *__restrict__ perm)
+                                                    const float *__restrict__ radius, int radius_desc, const float *__restrict__ dirs,
+                                                    uint32_t *__restrict__ keys, uint32_t *__restrict__ perm)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -115,128 +115,18 @@ __global__ void __launch_bounds__(256) k_query_keys(const float *__restrict__ q,
         if (radius_desc) cls = (uint32_t)top - cls; // largest search radii (the most expensive walks) first: the kernel's tail is then made of cheap queries
         code = (cls << (26 - e)) | (code >> (4 + e));
     }
+    if (dirs)
+    { // rays: direction octant first (a warp's rays then descend the same side of every split), origin Morton code below it
+        const uint32_t oct = (__ldg(dirs + 3 * (uint64_t)i) < 0.0f ? 4u : 0u) | (__ldg(dirs + 3 * (uint64_t)i + 1) < 0.0f ? 2u : 0u) |
+                             (__ldg(dirs + 3 * (uint64_t)i + 2) < 0.0f ? 1u : 0u);
+        code = (oct << 27) | (code >> 3);
+    }
     keys[i] = code;
     perm[i] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // nearest primitive                                                                      query.cuh:238-318
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kQueryThreads)
-    k_closest(SceneView sv, const float *__restrict__ q, const uint32_t *__restrict__ perm, uint32_t n, uint32_t *__restrict__ out_idx,
-              float *__restrict__ out_dist, unsigned long long *counter, int use_seed)
-{
-    const int lane = threadIdx.x & 31;
-    Feeder fd{0u, 0u, false};
-    StackEntry stk[kStackDepth];
-    int sp = 0;
-    V3 p = V3{0.f, 0.f, 0.f};
-    float best2 = INFINITY;
-    uint32_t best = kNone, best_leaf = kNone, slot = kNone, node = kNone;
-    for (;;)
-    {
-        const unsigned idle = __ballot_sync(kFull, node == kNone);
-        if (idle)
-        {
-            const uint32_t s = feeder_take(fd, idle, node == kNone, lane, n, counter);
-            if (s != kNone)
-            {
-                slot = perm ? __ldg(perm + s) : s;
-                p = load_point(q, slot);
-                best2 = INFINITY;
-                best = kNone;
-                sp = 0;
-                node = 0;
-                if (use_seed && best_leaf != kNone)
-                { // the triangle that answered this lane's previous (neighbouring) query bounds this one
-                    const LTri *tp = sv.ltri + best_leaf;
-                    float4 t0, t1, t2, t3;
-                    ld256(tp, t0, t1);
-                    ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
-                    float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
-                    dist *= dist;
-                    if (dist < INFINITY)
-                    { // if nothing closer turns up, this triangle IS the answer (best_leaf keeps pointing at it)
-                        best2 = dist;
-                        best = __float_as_uint(t0.w);
-                    }
-                    else best_leaf = kNone;
-                }
-            }
-            if (fd.exhausted && __all_sync(kFull, node == kNone)) break;
-        }
-        if (node != kNone)
-        {
-
-            float4 a, b, c, d;
-            ld256(sv.bnode + node, a, b);
-            ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
-            const NodeBoxes nb = unpack_boxes(a, b, c);
-            float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
-            uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
-            if (m1 < m0)
-            {
-                const float tm = m0;
-                m0 = m1;
-                m1 = tm;
-                const uint32_t tr = r0;
-                r0 = r1;
-                r1 = tr;
-            }
-            uint32_t next = kNone;
-    #pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-            {
-                const float m = ch ? m1 : m0;
-                const uint32_t r = ch ? r1 : r0;
-                if (!(m < best2)) continue;
-                if (r & kLeafFlag)
-                {
-                    const uint32_t k = r & ~kLeafFlag;
-                    const LTri *tp = sv.ltri + k;
-                    float4 t0, t1, t2, t3;
-                    ld256(tp, t0, t1);
-                    ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
-                    float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
-                    dist *= dist; // the reference squares the distance it got back (query.cuh:284-285)
-                    if (dist < best2)
-                    {
-                        best2 = dist;
-                        best = __float_as_uint(t0.w);
-                        best_leaf = k;
-                    }
-                }
-                else if (next == kNone) next = r;
-                else
-                {
-                    stk[sp] = StackEntry{r, m};
-                    ++sp;
-                }
-            }
-            if (next == kNone)
-            {
-                while (sp > 0)
-                {
-                    --sp;
-                    const StackEntry se = stk[sp];
-                    if (se.key < best2)
-                    {
-                        next = se.node;
-                        break;
-                    }
-                }
-                if (next == kNone)
-                {
-                    out_idx[slot] = best;
-                    out_dist[slot] = sqrtf(best2);
-                }
-            }
-            node = next;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // warp-cooperative ("packet") traversal for Morton-ordered batches
 // ---------------------------------------------------------------------------------------------------------------
 // The 32 lanes of a warp hold 32 consecutive queries of the ordered batch and walk the tree TOGETHER: one node record is
@@ -290,7 +180,7 @@ SNCH_DI bool tri_cannot_improve(V3 pa, V3 n, float ra, V3 x, float xmax, float b
 // the plain packets.
 constexpr int kSoloStack = 512;  // entries per warp; above kSoloStack - 128 the walk pops one entry per step (growth <= tree depth)
 SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, int owner, int lane, V3 p_lane, float &best2_lane, uint32_t &best_lane,
-                          uint32_t &best_leaf_lane)
+                          uint32_t &best_leaf_lane, bool use_lb)
 {
     const V3 p = V3{__shfl_sync(kFull, p_lane.x, owner), __shfl_sync(kFull, p_lane.y, owner), __shfl_sync(kFull, p_lane.z, owner)};
     float b2 = __shfl_sync(kFull, best2_lane, owner);
@@ -334,7 +224,7 @@ SNCH_DI void solo_closest(const SceneView &sv, StackEntry *st, uint32_t root, in
                     float4 t0, t1, t2, t3;
                     ld256(tp, t0, t1);
                     ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
-                    if (tri_cannot_improve(V3{t0.x, t0.y, t0.z}, V3{t3.x, t3.y, t3.z}, t3.w, p, pmax, bd)) continue;
+                    if (use_lb && tri_cannot_improve(V3{t0.x, t0.y, t0.z}, V3{t3.x, t3.y, t3.z}, t3.w, p, pmax, bd)) continue;
                     float dist = point_triangle_distance(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, p);
                     dist *= dist;
                     if (dist < b2 && __float_as_uint(dist) < cand)
@@ -402,7 +292,7 @@ __global__ void __launch_bounds__(kQueryThreads)
         if (base >= n) break;
         const uint32_t s = (uint32_t)base + lane;
         const bool valid = s < n;
-        const uint32_t slot = valid ? __ldg(perm + s) : 0u;
+        const uint32_t slot = valid ? (perm ? __ldg(perm + s) : s) : 0u;
         const V3 p = valid ? load_point(q, slot) : V3{0.f, 0.f, 0.f};
         const float pmax = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fabsf(p.z));
         float best2 = INFINITY;
@@ -504,6 +394,8 @@ __global__ void __launch_bounds__(kQueryThreads)
     const int lane = threadIdx.x & 31;
     StackEntry *solo = s_solo[threadIdx.x >> 5];
     uint32_t best_leaf = kNone;
+    const bool use_lb = !(use_seed & 2); // "query.seed" bit 1 switches the cheap lower bound off (A/B, knob tests)
+    use_seed &= 1;
     constexpr unsigned long long kRun = 4; // consecutive (neighbouring) queries per draw
     for (;;)
     {
@@ -532,7 +424,7 @@ __global__ void __launch_bounds__(kQueryThreads)
                 }
                 else best_leaf = kNone;
             }
-            solo_closest(sv, solo, 0u, 0, lane, p, best2, best, best_leaf);
+            solo_closest(sv, solo, 0u, 0, lane, p, best2, best, best_leaf, use_lb);
             best_leaf = __shfl_sync(kFull, best_leaf, 0);
             if (lane == 0)
             {
@@ -554,19 +446,14 @@ __global__ void __launch_bounds__(kQueryThreads)
 // every branch decision the reference takes on exact float values — it defers to cone_overlap(), the reference's own
 // operation sequence.  Decisions are therefore the reference's; only their cost changes.
 constexpr float kConeBand = 2e-5f;
-// kMode 0: the reference's libm chain.  1: sine-space filter on correctly rounded sqrt/rcp.  2: the same filter on the
-// MUFU approximations (rel. error <= 2^-22, i.e. <= 5e-7 on every quantity compared against the 2e-5 band); the two
-// exact-value branch decisions of the reference (l > radius, s <= 0) and the ill-conditioned corner (view cone within
-// ~6 degrees of a half space, where cos(beta) amplifies the error of sin(beta)) are handed to the exact chain.
-//    3: mode 2 with the exact chain kept OUT OF LINE (one copy per kernel instead of one per hand-off site: the walk's hot loop
-//       shrinks by ~2000 instructions, profiles/r01j showed 0.74 "no instruction" stall cycles per issue).
+// kMode 0: the reference's libm chain, verbatim ("query.cone_filter" = 0: the A/B the parity tests sweep).
+// kMode 1: the sine-space filter on the MUFU approximations (rel. error <= 2^-22, i.e. <= 5e-7 on every quantity compared
+//    against the 2e-5 band); the two exact-value branch decisions of the reference (l > radius, s <= 0) and the
+//    ill-conditioned corner (view cone within ~6 degrees of a half space, where cos(beta) amplifies the error of sin(beta))
+//    are handed to the exact chain, which is kept OUT OF LINE (one copy per kernel instead of one per hand-off site: the
+//    walk's hot loop shrinks by ~2000 instructions, profiles/r01j showed 0.74 "no instruction" stall cycles per issue).
 __device__ __noinline__ bool cone_overlap_ool(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
 {
-    return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
-}
-template <int kMode> SNCH_DI bool cone_exact(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
-{
-    if (kMode == 3) return cone_overlap_ool(axis, half_angle, radius, o, lo, hi, md2);
     return cone_overlap(axis, half_angle, radius, o, lo, hi, md2);
 }
 template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float radius, V3 o, V3 lo, V3 hi, float md2)
@@ -575,19 +462,10 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
     if (half_angle >= kHalfPi || md2 < FLT_EPSILON) return true;
     const V3 c = V3{(hi.x + lo.x) * 0.5f, (hi.y + lo.y) * 0.5f, (hi.z + lo.z) * 0.5f};
     const V3 w = c - o;
-    float l, rl;
-    if (kMode == 1)
-    {
-        l = len(w); // exact: the reference branches on l > radius
-        rl = __frcp_rn(l);
-    }
-    else
-    {
-        const float l2 = w.x * w.x + w.y * w.y + w.z * w.z;
-        rl = rsqrt_approx(l2);
-        l = l2 * rl;
-        if (!(fabsf(l - radius) > 4e-6f * radius)) return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2); // also NaN / l2 == 0
-    }
+    const float l2 = w.x * w.x + w.y * w.y + w.z * w.z;
+    const float rl = rsqrt_approx(l2);
+    const float l = l2 * rl;
+    if (!(fabsf(l - radius) > 4e-6f * radius)) return cone_overlap_ool(axis, half_angle, radius, o, lo, hi, md2); // also NaN / l2 == 0
     const float t = fabsf(__fmaf_rn(axis.x, w.x, __fmaf_rn(axis.y, w.y, axis.z * w.z))) * rl;
     float sa, ca;
     __sincosf(half_angle, &sa, &ca);
@@ -596,12 +474,8 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
     {
         sb = radius * rl;
         const float cb2 = fmaxf(__fmaf_rn(-sb, sb, 1.0f), 0.0f);
-        if (kMode == 1) cb = sqrtf(cb2);
-        else
-        {
-            if (cb2 < 0.01f) return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2);
-            cb = sqrt_approx(cb2);
-        }
+        if (cb2 < 0.01f) return cone_overlap_ool(axis, half_angle, radius, o, lo, hi, md2);
+        cb = sqrt_approx(cb2);
     }
     else
     {
@@ -611,7 +485,7 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
         const float s = l - d;
         const float sband = kConeBand * l;
         if (s < -sband) return true; // the reference returns true for s <= 0
-        if (!(s > sband)) return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2);
+        if (!(s > sband)) return cone_overlap_ool(axis, half_angle, radius, o, lo, hi, md2);
         // project_to_plane(v, e)                                                        cone.cuh:34-42, 58-66
         const float sign = copysignf(1.0f, v.z);
         const float ia = -__frcp_rn(sign + v.z);
@@ -633,136 +507,318 @@ template <int kMode> SNCH_DI bool cone_test(V3 axis, float half_angle, float rad
         if (t <= sg - kConeBand) return true;
         if (t >= sg + kConeBand) return false;
     }
-    return cone_exact<kMode>(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
+    return cone_overlap_ool(axis, half_angle, radius, o, lo, hi, md2); // inside the band (or NaN): the reference's own sequence
 }
 
-// The same filter on the 48-bit cone codes of a CNode (snch_math.cuh qcone_*): 1 = overlap, 0 = no overlap, 2 = undecided
-// (the caller fetches the exact cone from the SNode record and runs cone_test on it).  The decoded axis, half-angle and
-// radius are within kQAxisErr / kQAlphaErr / kQRadiusErr * S of the exact ones (checked by the encoder for every cone it
-// does not mark kQExact), so each quantity the filter compares moves by at most that much: the guard band is widened by
-// those bounds and an answer here implies the same answer from cone_test<2> on the exact cone, i.e. the reference's.
-SNCH_DI int cone_test_compact(uint32_t qx, uint32_t qy, uint32_t qa, uint32_t qr, V3 o, V3 lo, V3 hi, float md2)
+// silhouette_distance_calculator over the owned edges of one leaf (scene.cuh:978-1003 -> silhouette_edge::
+// find_closest_silhouette_point, :788-824), `bound` = the running best (inclusive, as there).  Returns true when an edge
+// improved it; `bound` / `slot` (LEdge index of that edge) are updated.
+SNCH_DI bool leaf_silhouette(const SceneView &sv, uint32_t first, uint32_t cnt, V3 p, bool flip, float &bound, uint32_t &slot)
 {
-    if (qa >= kQExact) return qa == kQInvalid ? 0 : (qa == kQWide ? 1 : 2);
-    if (md2 < FLT_EPSILON) return 1;
-    const float scale = qcone_scale(lo, hi);
-    const QCone q = qcone_decode(qx, qy, qa, qr, scale);
-    const V3 c = V3{(hi.x + lo.x) * 0.5f, (hi.y + lo.y) * 0.5f, (hi.z + lo.z) * 0.5f};
-    const V3 w = c - o;
-    const float l2 = w.x * w.x + w.y * w.y + w.z * w.z;
-    const float rl = rsqrt_approx(l2);
-    const float l = l2 * rl;
-    const float dr = kQRadiusErr * scale;
-    if (!(fabsf(l - q.radius) > __fmaf_rn(4e-6f, q.radius, dr))) return 2; // the reference branches on l > radius (also NaN / l2 == 0)
-    const float t = fabsf(__fmaf_rn(q.axis.x, w.x, __fmaf_rn(q.axis.y, w.y, q.axis.z * w.z))) * rl;
-    float sa, ca;
-    __sincosf(q.half_angle, &sa, &ca);
-    float band = kConeBand + kQAxisErr + kQAlphaErr;
-    float sb, cb;
-    if (l > q.radius)
+    float b2 = bound * bound;
+    bool hit = false;
+    for (uint32_t k = 0; k < cnt; ++k)
     {
-        sb = q.radius * rl;
-        const float dsb = dr * rl; // |sb' - sb|
-        const float cb2 = fmaxf(__fmaf_rn(-sb, sb, 1.0f), 0.0f);
-        if (!(dsb <= 0.005f) || cb2 < 0.02f) return 2;
-        cb = sqrt_approx(cb2);
-        band = __fmaf_rn(dsb * 1.01f, rsqrt_approx(cb2 - 2.0f * dsb), band); // |beta' - beta| <= dsb / min(cos beta, cos beta')
-    }
-    else
-    {
-        const V3 v = V3{w.x * rl, w.y * rl, w.z * rl};
-        const V3 e = hi - c;
-        const float d = __fmaf_rn(e.x, fabsf(v.x), __fmaf_rn(e.y, fabsf(v.y), e.z * fabsf(v.z)));
-        const float s = l - d;
-        const float sband = kConeBand * l;
-        if (s < -sband) return 1; // the reference returns true for s <= 0
-        if (!(s > sband)) return 2;
-        const float sign = copysignf(1.0f, v.z);
-        const float ia = -__frcp_rn(sign + v.z);
-        const float bb = v.x * v.y * ia;
-        const float b1x = __fmaf_rn(sign * v.x * v.x, ia, 1.0f), b1y = sign * bb, b1z = -sign * v.x;
-        const float b2x = bb, b2y = __fmaf_rn(v.y * v.y, ia, sign), b2z = -v.y;
-        const float r1 = __fmaf_rn(e.x, fabsf(b1x), __fmaf_rn(e.y, fabsf(b1y), e.z * fabsf(b1z)));
-        const float r2 = __fmaf_rn(e.x, fabsf(b2x), __fmaf_rn(e.y, fabsf(b2y), e.z * fabsf(b2z)));
-        const float pr2 = __fmaf_rn(r1, r1, r2 * r2);
-        const float rh = rsqrtf(__fmaf_rn(s, s, pr2));
-        sb = sqrtf(pr2) * rh;
-        cb = s * rh;
-    }
-    const float cg = __fmaf_rn(ca, cb, -sa * sb); // cos(alpha + beta)
-    const float sg = __fmaf_rn(sa, cb, ca * sb);  // sin(alpha + beta)
-    if (cg <= -band) return 1;
-    if (cg >= band)
-    {
-        if (t <= sg - band) return 1;
-        if (t >= sg + band) return 0;
-    }
-    return 2;
-}
-
-// Per-lane traversal with DEFERRED leaves.  A leaf costs up to three edge tests (~100 instructions each) and only one lane
-// in ~15 reaches one in a given step: tested inline, that code ran at 2 of 32 lanes and was 42% of all issued
-// instructions (profiles/r01b_*).  Instead a lane parks the leaves it reaches (at the top end of its stack array) and the
-// warp tests parked leaves together — when half the warp has some, when a lane's park is nearly full, or when a lane has
-// finished its walk and needs its answer.  A parked leaf only delays a tightening of that lane's own bound, so the
-// result is unchanged.
-constexpr int kParkCap = 8;     // parked leaves per lane (stack slots kStackDepth-1 downwards)
-constexpr int kParkFlushLanes = 16;
-template <int kFilter>
-__global__ void __launch_bounds__(kQueryThreads)
-    k_silhouette(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                 const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
-{
-    const int lane = threadIdx.x & 31;
-    Feeder fd{0u, 0u, false};
-    StackEntry stk[kStackDepth + kParkCap];
-    int sp = 0, npark = 0;
-    V3 p = V3{0.f, 0.f, 0.f};
-    bool flip = false, found = false, busy = false;
-    float best = INFINITY, best2 = INFINITY;
-    uint32_t slot = kNone, node = kNone;
-    for (;;)
-    {
-        // ---- 1. parked leaves
-        const unsigned parked = __ballot_sync(kFull, npark > 0);
-        if (parked && (__popc(parked) >= kParkFlushLanes || __any_sync(kFull, npark >= kParkCap - 2 || (npark > 0 && node == kNone))))
+        float4 e0, e1, e2, e3;
+        ld256(sv.ledge + first + k, e0, e1);
+        ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
+        const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
+        V3 cp;
+        const float dist = point_segment_distance(pa, pb, p, &cp);
+        if (dist * dist > b2) continue;
+        bool is_sil = isnan(e1.z); // boundary edge
+        if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
+        if (is_sil && dist <= bound)
         {
-            while (__any_sync(kFull, npark > 0))
+            bound = dist;
+            b2 = dist * dist;
+            slot = first + k;
+            hit = true;
+        }
+    }
+    return hit;
+}
+// The optional outputs of a silhouette query (the reference computes the point at scene.cuh:796-799 and
+// drops it, and leaves the index as a TODO at query.cuh:386,411): the id of the silhouette edge that attains the distance
+// (its index in scene<3>::silhouettes) and the closest point on it — recomputed from the edge's record with the very
+// call that produced the distance, so |p - point| is that distance bit for bit.
+SNCH_DI void write_silhouette_point(const SceneView &sv, uint32_t slot, uint32_t ledge_slot, V3 p, bool found, uint32_t *__restrict__ out_edge,
+                                    float *__restrict__ out_point)
+{
+    uint32_t id = kNone;
+    V3 cp = V3{0.f, 0.f, 0.f};
+    if (found)
+    {
+        float4 e0, e1, e2, e3;
+        ld256(sv.ledge + ledge_slot, e0, e1);
+        ld256(reinterpret_cast<const char *>(sv.ledge + ledge_slot) + 32, e2, e3);
+        point_segment_distance(V3{e0.x, e0.y, e0.z}, V3{e0.w, e1.x, e1.y}, p, &cp);
+        id = __float_as_uint(e3.x);
+    }
+    if (out_edge) out_edge[slot] = id;
+    if (out_point)
+    {
+        out_point[3 * (uint64_t)slot] = cp.x;
+        out_point[3 * (uint64_t)slot + 1] = cp.y;
+        out_point[3 * (uint64_t)slot + 2] = cp.z;
+    }
+}
+
+// COOPERATIVE WALK of one silhouette query by a whole warp: every lane opens one node (both child boxes, the reference's
+// per-child cone test, the edges of leaf children), survivors are pushed with warp-aggregated offsets, the bound is the
+// warp minimum.  The answer is the minimum over the silhouette edges of the leaves the reference's predicate chain
+// reaches, which does not depend on the order of the walk.  `Stk` is the warp's (node, key) stack: a flat array in the
+// one-query-per-warp kernel, the warp's slice of the per-lane stack levels when the per-lane kernel finishes its last
+// walks this way.  kCap = its capacity; above kCap - 128 the walk pops one entry per step (growth <= tree depth).
+struct FlatStack
+{
+    StackEntry *e;
+    SNCH_DI StackEntry get(int i) const { return e[i]; }
+    SNCH_DI void put(int i, StackEntry v) const { e[i] = v; }
+};
+template <int kFilter, bool kEdge, int kCap, typename Stk>
+SNCH_DI float solo_silhouette(const SceneView &sv, const Stk st, int lane, V3 p, bool flip, float best, uint32_t &best_slot)
+{
+    float best2 = best * best;
+    bool found = false;
+    const unsigned lt = (1u << lane) - 1u;
+    if (lane == 0) st.put(0, StackEntry{0u, 0.0f});
+    int sp = 1;
+    __syncwarp();
+    while (sp > 0)
+    {
+        const int take = sp > kCap - 128 ? 1 : (sp < 32 ? sp : 32);
+        sp -= take;
+        StackEntry en = StackEntry{kNone, INFINITY};
+        if (lane < take) en = st.get(sp + lane);
+        __syncwarp();
+        uint32_t cand = 0xFFFFFFFFu, cand_slot = kNone; // distance as ordered bits (>= +0)
+        uint32_t pr0 = kNone, pr1 = kNone;
+        float pk0 = 0.0f, pk1 = 0.0f;
+        if (en.node != kNone && en.key <= best2)
+        {
+            float4 a, b, c, d, e, f;
+            ld256(sv.snode + en.node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.snode + en.node) + 32, c, d);
+            ld256(reinterpret_cast<const char *>(sv.snode + en.node) + 64, e, f);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
+            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
+            const bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
+            const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
+            const bool far1 = m0 < m1; // the farther child is pushed first, so the nearer one is popped first
+            float ob = best;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
             {
-                if (npark > 0)
+                const bool one = (ch == 0) == far1;
+                if (!(one ? h1 : h0)) continue;
+                const float m = one ? m1 : m0;
+                const uint32_t r = one ? r1 : r0;
+                if (r & kLeafFlag)
                 {
-                    --npark;
-                    const StackEntry se = stk[kStackDepth + npark];
-                    if (se.key <= best2)
-                    {
-                        const uint32_t first = se.node >> 2, cnt = se.node & 3u;
-                        for (uint32_t k = 0; k < cnt; ++k)
-                        { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
-                            float4 e0, e1, e2, e3;
-                            ld256(sv.ledge + first + k, e0, e1);
-                            ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
-                            const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
-                            V3 cp;
-                            const float dist = point_segment_distance(pa, pb, p, &cp);
-                            if (dist * dist > best2) continue;
-                            bool is_sil = isnan(e1.z); // boundary edge
-                            if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
-                            if (is_sil && dist <= best)
-                            {
-                                best = dist;
-                                best2 = dist * dist;
-                                found = true;
-                            }
-                        }
-                    }
+                    const uint32_t payload = r & ~kLeafFlag;
+                    if (leaf_silhouette(sv, payload >> 2, payload & 3u, p, flip, ob, cand_slot)) cand = __float_as_uint(ob);
+                }
+                else if (pr0 == kNone)
+                {
+                    pr0 = r;
+                    pk0 = m;
+                }
+                else
+                {
+                    pr1 = r;
+                    pk1 = m;
                 }
             }
         }
-        // ---- 2. finished walks hand in their answer; idle lanes take the next query
-        if (busy && node == kNone && npark == 0)
+        const unsigned c1 = __ballot_sync(kFull, pr0 != kNone), c2 = __ballot_sync(kFull, pr1 != kNone);
+        const int off = sp + __popc(c1 & lt) + __popc(c2 & lt);
+        if (pr0 != kNone) st.put(off, StackEntry{pr0, pk0});
+        if (pr1 != kNone) st.put(off + 1, StackEntry{pr1, pk1});
+        sp += __popc(c1) + __popc(c2);
+        const uint32_t mn = __reduce_min_sync(kFull, cand);
+        if (mn != 0xFFFFFFFFu)
+        { // cand <= best by construction
+            best = __uint_as_float(mn);
+            best2 = best * best;
+            found = true;
+            if (kEdge) best_slot = __shfl_sync(kFull, cand_slot, __ffs(__ballot_sync(kFull, cand == mn)) - 1);
+        }
+        __syncwarp();
+    }
+    return found ? best : INFINITY;
+}
+
+// Per-lane traversal with a WARP-SHARED leaf queue.  A leaf costs up to three edge tests (~100 instructions each) and only
+// one lane in ~15 reaches one in a given step: tested inline, that code ran at 2 of 32 lanes and was 42% of all issued
+// instructions (profiles/r01b_*); parked per lane and drained by each lane for itself, at 3-4 of 32 (profiles/r01k).  Here
+//   * a lane that reaches a leaf appends (first edge, edge count | owner lane) to a queue in shared memory; when the
+//     queue holds a warp's worth — or a lane has finished walking and needs its answer — the warp tests the queued
+//     leaves one per lane, reading the owner's query through shuffles, and hands results back through a shared
+//     per-lane minimum.  The answer is min over the silhouette edges within the bound, which does not depend on the
+//     order or grouping of the tests, so results are identical to the sequential loop's;
+//   * the lowest kSStack levels of each lane's traversal stack live in shared memory (conflict-free: the bank depends
+//     on the lane only), deeper levels spill to local memory;
+//   * kSeed: a lane remembers the leaf that answered its previous query (its neighbour in the ordered batch) and queues that
+//     leaf as a HINT when it takes a new query.  A hint distance only tightens the pruning bound; the answer is still the
+//     minimum over edges the walk itself reaches, and if the walk ends without confirming the hint (no reached edge within
+//     it — the reference's cone chain does not lead to that leaf) the query is walked again from the answer found so far
+//     without a hint.  So the result is the unseeded one;
+//   * kEdge: the per-lane minimum is the 64-bit key (distance bits, LEdge slot), so the edge that attains the answer comes
+//     back with it (snch_closest_silhouette_batch out_edge / out_point); instantiated only when those outputs are asked for;
+//   * TAIL: once the batch has no more queries to hand out, a warp left with at most `tail_lanes` walking lanes stops
+//     walking them one lane each: it drains its queue and puts those queries, with the bound each has found so far, on a
+//     list that the next launch (k_silhouette_wide) finishes ONE QUERY PER WARP from the root.  The few queries that open
+//     thousands of nodes (a point in the hole of the torus) were a fixed ~8 ms single-lane tail of every unbounded batch;
+//     same predicate chain, same edge tests, same minimum (an edge found before the restart lies within the inclusive
+//     bound and is reached again).
+constexpr int kSStack = 12;
+constexpr int kLeafQueue = 128;  // >= kLeafFlushAt - 1 + 64 + 32 (every lane can add two leaves per step, plus one hint)
+constexpr int kLeafFlushAt = 32;
+constexpr uint32_t kOwnerHint = 32u; // queue owner byte: lane | kOwnerHint for a hint entry
+template <bool kEdge> struct SilResult
+{
+    using T = uint32_t;
+    static constexpr T kEmpty = 0xFFFFFFFFu;
+    SNCH_DI static T make(float d, uint32_t) { return __float_as_uint(d); } // distances are >= +0: uint order = float order
+    SNCH_DI static float dist(T r) { return __uint_as_float(r); }
+    SNCH_DI static uint32_t slot(T) { return kNone; }
+};
+template <> struct SilResult<true>
+{
+    using T = unsigned long long;
+    static constexpr T kEmpty = ~0ull;
+    SNCH_DI static T make(float d, uint32_t s) { return ((T)__float_as_uint(d) << 32) | s; }
+    SNCH_DI static float dist(T r) { return __uint_as_float((uint32_t)(r >> 32)); }
+    SNCH_DI static uint32_t slot(T r) { return (uint32_t)r; }
+};
+template <int kFilter, bool kSeed, bool kEdge>
+__global__ void __launch_bounds__(kQueryThreads, 8)
+    k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
+                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
+                      float *__restrict__ out_point, unsigned long long *counter, int tail_lanes, uint32_t *__restrict__ tail_slot,
+                      float *__restrict__ tail_bound)
+{
+    static_assert(!(kSeed && kEdge), "the hinted walk does not carry edge slots");
+    using Res = SilResult<kEdge>;
+    __shared__ StackEntry s_stk[kSStack][kQueryThreads];
+    struct WarpQueue // one base address per warp: payloads, owner bytes and the fill count are immediate offsets from it
+    {
+        uint32_t payload[kLeafQueue];
+        uint8_t owner[kLeafQueue];
+        uint32_t count;
+    };
+    __shared__ WarpQueue s_wq[kQueryThreads / 32];
+    __shared__ typename Res::T s_result[kQueryThreads];
+    __shared__ uint32_t s_hint[kSeed ? kQueryThreads : 1], s_seed[kSeed ? kQueryThreads : 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpQueue &wq = s_wq[wid];
+    Feeder fd{0u, 0u, false};
+    StackEntry lstk[kStackDepth - kSStack];
+    int sp = 0;
+    V3 p = V3{0.f, 0.f, 0.f};
+    bool flip = false, found = false, busy = false, pend = false, tail = false;
+    float best = INFINITY, best2 = INFINITY;
+    float ans = INFINITY;    // kSeed: smallest distance the walk itself has reached (best = min(ans, hint) is only the pruning bound)
+    uint32_t seed = kNone;   // kSeed: queue payload of the leaf that answered this lane's previous query
+    bool hinted = false;     // kSeed: a hint has lowered `best` below what the walk itself has reached
+    uint32_t best_slot = kNone; // kEdge: LEdge slot of the edge that attains `best`
+    uint32_t slot = kNone, node = kNone;
+    s_result[threadIdx.x] = Res::kEmpty;
+    if (kSeed)
+    {
+        s_hint[threadIdx.x] = kNone;
+        s_seed[threadIdx.x] = kNone;
+    }
+    if (lane == 0) wq.count = 0;
+    __syncwarp();
+    for (;;)
+    {
+        // ---- 1. queued leaves
+        uint32_t qc = wq.count;
+        if (qc >= kLeafFlushAt || tail || __any_sync(kFull, pend && node == kNone))
         {
-            out_dist[slot] = found ? best : INFINITY;
-            busy = false;
+            while (qc > 0)
+            {
+                const uint32_t take = qc < 32u ? qc : 32u;
+                qc -= take;
+                const bool mine = (uint32_t)lane < take;
+                const uint32_t payload = mine ? wq.payload[qc + lane] : 0u;
+                const uint32_t ow = mine ? (uint32_t)wq.owner[qc + lane] : (uint32_t)lane;
+                const int owner = (int)(ow & 31u);
+                const bool is_hint = kSeed && (ow & kOwnerHint) != 0;
+                const V3 op = V3{__shfl_sync(kFull, p.x, owner), __shfl_sync(kFull, p.y, owner), __shfl_sync(kFull, p.z, owner)};
+                float ob = __shfl_sync(kFull, best, owner);
+                const bool oflip = __shfl_sync(kFull, (int)flip, owner) != 0;
+                uint32_t eslot = kNone;
+                if (leaf_silhouette(sv, payload >> 2, payload & 3u, op, oflip, ob, eslot))
+                {
+                    if (is_hint) atomicMin(&s_hint[(wid << 5) + owner], __float_as_uint(ob));
+                    else
+                    {
+                        const typename Res::T nb = Res::make(ob, eslot);
+                        const typename Res::T old = atomicMin(&s_result[(wid << 5) + owner], nb);
+                        if (kSeed && nb <= old) s_seed[(wid << 5) + owner] = payload; // (racy between two improving lanes: any of them is a usable seed)
+                    }
+                }
+                __syncwarp();
+            }
+            const typename Res::T rb = s_result[threadIdx.x];
+            if (rb != Res::kEmpty)
+            {
+                const float v = Res::dist(rb);
+                if (v <= best)
+                {
+                    best = v;
+                    best2 = v * v;
+                    found = true;
+                    if (kEdge) best_slot = Res::slot(rb);
+                }
+                if (kSeed && v <= ans)
+                {
+                    ans = v;
+                    seed = s_seed[threadIdx.x];
+                }
+                s_result[threadIdx.x] = Res::kEmpty;
+            }
+            if (kSeed)
+            {
+                const uint32_t hb = s_hint[threadIdx.x];
+                if (hb != kNone)
+                {
+                    const float v = __uint_as_float(hb);
+                    if (node != kNone && v < best)
+                    { // a hint that arrives after the walk has ended changes nothing: that walk used only confirmed bounds
+                        best = v;
+                        best2 = v * v;
+                        hinted = true;
+                    }
+                    s_hint[threadIdx.x] = kNone;
+                }
+            }
+            pend = false;
+            if (lane == 0) wq.count = 0;
+            __syncwarp();
+            if (tail) break;
+        }
+        // ---- 2. finished walks hand in their answer; idle lanes take the next query
+        if (busy && node == kNone)
+        {
+            if (kSeed && hinted && ans > best)
+            { // the hint was never confirmed by an edge the walk reached: walk again, bounded by what it did reach
+                best = found ? ans : (rmax ? __ldg(rmax + slot) : INFINITY);
+                best2 = best * best;
+                hinted = false;
+                sp = 0;
+                node = 0;
+            }
+            else
+            {
+                out_dist[slot] = found ? (kSeed ? ans : best) : INFINITY;
+                if (kEdge) write_silhouette_point(sv, slot, best_slot, p, found, out_edge, out_point);
+                busy = false;
+            }
         }
         const unsigned idle = __ballot_sync(kFull, !busy);
         if (idle)
@@ -779,8 +835,30 @@ __global__ void __launch_bounds__(kQueryThreads)
                 busy = true;
                 sp = 0;
                 node = 0;
+                if (kSeed)
+                {
+                    ans = INFINITY;
+                    hinted = false;
+                    if (seed != kNone)
+                    {
+                        const uint32_t pos = atomicAdd(&wq.count, 1u);
+                        wq.payload[pos] = seed;
+                        wq.owner[pos] = (uint8_t)((uint32_t)lane | kOwnerHint);
+                        pend = true;
+                    }
+                }
             }
-            if (fd.exhausted && __all_sync(kFull, !busy)) break;
+            if (fd.exhausted)
+            {
+                const int walking = __popc(__ballot_sync(kFull, busy));
+                if (walking == 0) break;
+                if (walking <= tail_lanes)
+                { // nothing left to hand out and few lanes still walk: drain the queue (top of the loop), then finish cooperatively
+                    tail = true;
+                    __syncwarp();
+                    continue;
+                }
+            }
         }
         // ---- 3. one traversal step
         if (node != kNone)
@@ -808,308 +886,9 @@ __global__ void __launch_bounds__(kQueryThreads)
                 if (!h) continue;
                 if (r & kLeafFlag)
                 {
-                    stk[kStackDepth + npark] = StackEntry{r & ~kLeafFlag, m};
-                    ++npark;
-                }
-                else if (next == kNone) next = r;
-                else
-                {
-                    stk[sp] = StackEntry{r, m};
-                    ++sp;
-                }
-            }
-            if (next == kNone)
-            {
-                while (sp > 0)
-                {
-                    --sp;
-                    const StackEntry se = stk[sp];
-                    if (se.key <= best2)
-                    {
-                        next = se.node;
-                        break;
-                    }
-                }
-            }
-            node = next;
-        }
-    }
-}
-
-// Per-lane traversal with a WARP-SHARED leaf queue (v4).  profiles/r01k: in k_silhouette the parked-leaf loop ran at 3-4 of
-// 32 lanes (24% of all warp instructions) because every lane walks its own park list while the others wait, and the
-// per-thread stacks (576 B of local memory x 1024 threads per SM) missed L1 on 73% of their loads.  Here
-//   * a lane that reaches a leaf appends (owner lane, first edge, edge count) to a queue in shared memory; when the
-//     queue holds a warp's worth — or a lane has finished walking and needs its answer — the warp tests the queued
-//     leaves one per lane, reading the owner's query through shuffles, and hands results back through a shared
-//     per-lane minimum.  The answer is min over the silhouette edges within the bound, which does not depend on the
-//     order or grouping of the tests, so results are identical to the sequential loop's;
-//   * the lowest kSStack levels of each lane's traversal stack live in shared memory (conflict-free: the bank depends
-//     on the lane only), deeper levels spill to local memory.
-constexpr int kSStack = 12;
-constexpr int kLeafQueue = 128;  // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
-constexpr int kLeafFlushAt = 32;
-constexpr uint32_t kCoopMaxPayload = 1u << 27; // (first_edge << 2 | count) must leave 5 bits for the owner lane
-constexpr uint32_t kCoopHintFlag = 1u << 26;   // kSeed: bit 26 marks a hint entry, payloads keep 26 bits
-//   * kSeed: a lane remembers the leaf that answered its previous query (its neighbour in the ordered batch) and queues that
-//     leaf as a HINT when it takes a new query.  A hint distance only tightens the pruning bound; the answer is still the
-//     minimum over edges the walk itself reaches, and if the walk ends without confirming the hint (no reached edge within
-//     it — the reference's cone chain does not lead to that leaf) the query is walked again from the answer found so far
-//     without a hint.  So the result is the unseeded one; measured: 301 -> ~222 node visits per answered query if the hint
-//     were perfect (tools/dbg notes in DESIGN.md).
-//   * kCompact: the walk reads the 64 B CNode (boxes + split + 48-bit cone codes: 2 sectors) instead of the 96 B SNode.
-//     profiles/r01j: the kernel is bound by the L1 data pipe (88% of peak), which serves a divergent warp one 32 B sector per
-//     cycle, and 3 of every ~4 sectors are node records.  The exact cones are fetched only for the tests the codes leave
-//     undecided (cone_test_compact); a leaf child carries its sorted position and its edge payload comes from edge_off[].
-__device__ unsigned long long g_sil_stats[8]; // "query.sil_stats" instrumentation (kStats instantiation only)
-template <int kFilter, bool kCompact, bool kStats, bool kSeed>
-__global__ void __launch_bounds__(kQueryThreads, 8)
-    k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter,
-                      int feed_mode, uint32_t feed_regions, uint32_t feed_per)
-{
-    __shared__ StackEntry s_stk[kSStack][kQueryThreads];
-    __shared__ uint32_t s_queue[kQueryThreads / 32][kLeafQueue];
-    __shared__ uint32_t s_qcount[kQueryThreads / 32];
-    __shared__ uint32_t s_result[kQueryThreads];
-    __shared__ uint32_t s_hint[kSeed ? kQueryThreads : 1], s_seed[kSeed ? kQueryThreads : 1];
-    constexpr uint32_t kPayloadMask = (kSeed ? kCoopHintFlag : kCoopMaxPayload) - 1u;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t *queue = s_queue[wid];
-    Feeder fd{0u, 0u, false};
-    const RegionFeed rf{counter + kScratchCounters / 8, (feed_mode & 255) ? feed_regions : 0u, feed_per,
-                        (feed_mode & 255) == 1 ? blockIdx.x % (feed_regions ? feed_regions : 1u) : smid() % (feed_regions ? feed_regions : 1u)};
-    StackEntry lstk[kStackDepth - kSStack];
-    int sp = 0;
-    V3 p = V3{0.f, 0.f, 0.f};
-    bool flip = false, found = false, busy = false, pend = false;
-    float best = INFINITY, best2 = INFINITY;
-    float ans = INFINITY;    // kSeed: smallest distance the walk itself has reached (best = min(ans, hint) is only the pruning bound)
-    uint32_t seed = kNone;   // kSeed: queue payload of the leaf that answered this lane's previous query
-    bool hinted = false;     // kSeed: a hint has lowered `best` below what the walk itself has reached
-    uint32_t slot = kNone, node = kNone;
-    s_result[threadIdx.x] = kNone;
-    if (kSeed)
-    {
-        s_hint[threadIdx.x] = kNone;
-        s_seed[threadIdx.x] = kNone;
-    }
-    if (lane == 0) s_qcount[wid] = 0;
-    __syncwarp();
-    for (;;)
-    {
-        // ---- 1. queued leaves
-        uint32_t qc = s_qcount[wid];
-        if (qc >= kLeafFlushAt || __any_sync(kFull, pend && node == kNone))
-        {
-            while (qc > 0)
-            {
-                const uint32_t take = qc < 32u ? qc : 32u;
-                qc -= take;
-                const bool mine = (uint32_t)lane < take;
-                const uint32_t ent = mine ? queue[qc + lane] : ((uint32_t)lane << 27);
-                const int owner = (int)(ent >> 27);
-                const float ox = __shfl_sync(kFull, p.x, owner), oy = __shfl_sync(kFull, p.y, owner), oz = __shfl_sync(kFull, p.z, owner);
-                float ob = __shfl_sync(kFull, best, owner);
-                const bool oflip = __shfl_sync(kFull, (int)flip, owner) != 0;
-                const uint32_t raw = ent & kPayloadMask;
-                const bool is_hint = kSeed && (ent & kCoopHintFlag) != 0;
-                uint32_t payload = raw;
-                if (kCompact) payload = mine ? __ldg(sv.edge_off + payload) : 0u; // queue entries carry the sorted leaf position
-                const uint32_t first = payload >> 2, cnt = payload & 3u;
-                const V3 op = V3{ox, oy, oz};
-                float ob2 = ob * ob;
-                bool hit = false;
-                for (uint32_t k = 0; k < cnt; ++k)
-                { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
-                    float4 e0, e1, e2, e3;
-                    ld256(sv.ledge + first + k, e0, e1);
-                    ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
-                    const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
-                    V3 cp;
-                    const float dist = point_segment_distance(pa, pb, op, &cp);
-                    if (dist * dist > ob2) continue;
-                    bool is_sil = isnan(e1.z); // boundary edge
-                    if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, op - cp, dist, oflip);
-                    if (is_sil && dist <= ob)
-                    {
-                        ob = dist;
-                        ob2 = dist * dist;
-                        hit = true;
-                    }
-                }
-                if (hit)
-                { // distances are >= +0: uint order = float order
-                    const uint32_t nb = __float_as_uint(ob);
-                    if (is_hint) atomicMin(&s_hint[(wid << 5) + owner], nb);
-                    else
-                    {
-                        const uint32_t old = atomicMin(&s_result[(wid << 5) + owner], nb);
-                        if (kSeed && nb <= old) s_seed[(wid << 5) + owner] = raw; // (racy between two improving lanes: any of them is a usable seed)
-                    }
-                }
-                __syncwarp();
-            }
-            const uint32_t rb = s_result[threadIdx.x];
-            if (rb != kNone)
-            {
-                const float v = __uint_as_float(rb);
-                if (v <= best)
-                {
-                    best = v;
-                    best2 = v * v;
-                    found = true;
-                }
-                if (kSeed && v <= ans)
-                {
-                    ans = v;
-                    seed = s_seed[threadIdx.x];
-                }
-                s_result[threadIdx.x] = kNone;
-            }
-            if (kSeed)
-            {
-                const uint32_t hb = s_hint[threadIdx.x];
-                if (hb != kNone)
-                {
-                    const float v = __uint_as_float(hb);
-                    if (node != kNone && v < best)
-                    { // a hint that arrives after the walk has ended changes nothing: that walk used only confirmed bounds
-                        best = v;
-                        best2 = v * v;
-                        hinted = true;
-                    }
-                    s_hint[threadIdx.x] = kNone;
-                }
-            }
-            pend = false;
-            if (lane == 0) s_qcount[wid] = 0;
-            __syncwarp();
-        }
-        // ---- 2. finished walks hand in their answer; idle lanes take the next query
-        if (busy && node == kNone)
-        {
-            if (kSeed && hinted && ans > best)
-            { // the hint was never confirmed by an edge the walk reached: walk again, bounded by what it did reach
-                best = found ? ans : (rmax ? __ldg(rmax + slot) : INFINITY);
-                best2 = best * best;
-                hinted = false;
-                sp = 0;
-                node = 0;
-            }
-            else
-            {
-                out_dist[slot] = found ? (kSeed ? ans : best) : INFINITY;
-                busy = false;
-            }
-        }
-        const unsigned idle = __ballot_sync(kFull, !busy);
-        if (idle)
-        {
-            const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter, &rf);
-            if (s != kNone)
-            {
-                slot = perm ? __ldg(perm + s) : s;
-                p = load_point(q, slot);
-                flip = flipv ? (__ldg(flipv + slot) != 0) : false;
-                best = rmax ? __ldg(rmax + slot) : INFINITY;
-                best2 = best * best;
-                found = false;
-                busy = true;
-                sp = 0;
-                node = 0;
-                if (kSeed)
-                {
-                    ans = INFINITY;
-                    hinted = false;
-                    if (seed != kNone)
-                    {
-                        const uint32_t pos = atomicAdd(&s_qcount[wid], 1u);
-                        queue[pos] = ((uint32_t)lane << 27) | kCoopHintFlag | seed;
-                        pend = true;
-                    }
-                }
-            }
-            if (fd.exhausted && __all_sync(kFull, !busy)) break;
-        }
-        // ---- 3. one traversal step
-        if (node != kNone)
-        {
-            float4 a, b, c, d, e, f;
-            NodeBoxes nb;
-            float m0, m1;
-            uint32_t r0, r1;
-            bool h0, h1;
-            if (kCompact)
-            {
-                ld256(sv.cnode + node, a, b);
-                ld256(reinterpret_cast<const char *>(sv.cnode + node) + 32, c, d);
-                nb = unpack_boxes(a, b, c);
-                m0 = box_mindist2(nb.lo0, nb.hi0, p);
-                m1 = box_mindist2(nb.lo1, nb.hi1, p);
-                const uint32_t sw = __float_as_uint(d.x), q0 = __float_as_uint(d.y), q1 = __float_as_uint(d.z), q2 = __float_as_uint(d.w);
-                const uint32_t split = sw & 0x3FFFFFFFu;
-                r0 = (sw & 0x40000000u) ? (kLeafFlag | split) : split;
-                r1 = (sw & 0x80000000u) ? (kLeafFlag | (split + 1u)) : split + 1u;
-                int t0 = 0, t1 = 0;
-                if (kStats)
-                {
-                    atomicAdd(&g_sil_stats[0], (unsigned long long)((m0 <= best2) + (m1 <= best2)));
-                    atomicAdd(&g_sil_stats[5], 1ull);
-                }
-                if (m0 <= best2) t0 = cone_test_compact(q0 & 0xFFFu, (q0 >> 12) & 0xFFFu, (q0 >> 24) | ((q1 & 0xFu) << 8), (q1 >> 4) & 0xFFFu, p, nb.lo0, nb.hi0, m0);
-                if (m1 <= best2) t1 = cone_test_compact((q1 >> 16) & 0xFFFu, (q1 >> 28) | ((q2 & 0xFFu) << 4), (q2 >> 8) & 0xFFFu, q2 >> 20, p, nb.lo1, nb.hi1, m1);
-                if (kStats)
-                {
-                    atomicAdd(&g_sil_stats[1], (unsigned long long)((t0 == 2) + (t1 == 2)));
-                    const uint32_t qa0 = (q0 >> 24) | ((q1 & 0xFu) << 8), qa1 = (q2 >> 8) & 0xFFFu;
-                    atomicAdd(&g_sil_stats[2], (unsigned long long)((t0 == 2 && qa0 == kQExact) + (t1 == 2 && qa1 == kQExact)));
-                    const unsigned any = __ballot_sync(__activemask(), t0 == 2 || t1 == 2);
-                    if ((threadIdx.x & 31) == __ffs(__activemask()) - 1)
-                    {
-                        atomicAdd(&g_sil_stats[3], 1ull);
-                        if (any) atomicAdd(&g_sil_stats[4], 1ull);
-                    }
-                }
-                if (t0 == 2 || t1 == 2)
-                { // undecided by the codes: the exact cones of this node
-                    ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
-                    ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
-                    if (t0 == 2) t0 = (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-                    if (t1 == 2) t1 = (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
-                }
-                h0 = t0 != 0;
-                h1 = t1 != 0;
-            }
-            else
-            {
-                ld256(sv.snode + node, a, b);
-                ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
-                ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
-                nb = unpack_boxes(a, b, c);
-                m0 = box_mindist2(nb.lo0, nb.hi0, p);
-                m1 = box_mindist2(nb.lo1, nb.hi1, p);
-                r0 = __float_as_uint(f.z);
-                r1 = __float_as_uint(f.w);
-                // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367),
-                // evaluated only for children that can still beat the current best
-                h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-                h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
-            }
-            const bool swap = m1 < m0;
-            uint32_t next = kNone;
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-            {
-                const bool second = (ch == 1) != swap; // visit the nearer child first
-                const bool h = second ? h1 : h0;
-                const float m = second ? m1 : m0;
-                const uint32_t r = second ? r1 : r0;
-                if (!h) continue;
-                if (r & kLeafFlag)
-                {
-                    const uint32_t pos = atomicAdd(&s_qcount[wid], 1u);
-                    queue[pos] = ((uint32_t)lane << 27) | (r & kPayloadMask);
+                    const uint32_t pos = atomicAdd(&wq.count, 1u);
+                    wq.payload[pos] = r & ~kLeafFlag;
+                    wq.owner[pos] = (uint8_t)lane;
                     pend = true;
                 }
                 else if (next == kNone) next = r;
@@ -1138,111 +917,42 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         }
         __syncwarp(); // queue appends of this step are visible to the whole warp before the next count is read
     }
+    if (!tail) return;
+    // ---- TAIL: the queue is drained and every confirmed result is folded into found / best (/ ans).  Lanes whose walk had
+    // already ended hand in; the queries still being walked go on the tail list with the bound found so far, and the launch
+    // that follows (k_silhouette_wide over that list) finishes each of them on 32 lanes.
+    const bool need = busy && (node != kNone || (kSeed && hinted && ans > best));
+    if (busy && !need)
+    {
+        out_dist[slot] = found ? (kSeed ? ans : best) : INFINITY;
+        if (kEdge) write_silhouette_point(sv, slot, best_slot, p, found, out_edge, out_point);
+    }
+    if (need)
+    {
+        float bound = best;
+        if (kSeed) bound = ans < INFINITY ? ans : (rmax ? __ldg(rmax + slot) : INFINITY); // only confirmed distances bound the restart
+        const uint32_t at = (uint32_t)atomicAdd(counter + 1, 1ull); // < gridDim.x * blockDim.x entries by construction
+        tail_slot[at] = slot;
+        tail_bound[at] = bound;
+    }
 }
 
-// The same cooperative walk for the silhouette query: every lane opens one node of ONE query (both child boxes, the
-// reference's per-child cone test, the edges of leaf children), survivors are pushed with warp-aggregated offsets, the bound
-// is the warp minimum.  The answer is the minimum over the silhouette edges of the leaves the reference's predicate chain
-// reaches, which does not depend on the order of the walk.  Used for batches too small to fill the machine with per-lane
-// walks (k_silhouette_wide).
-template <int kFilter>
-SNCH_DI float solo_silhouette(const SceneView &sv, StackEntry *st, int lane, V3 p, bool flip, float best)
-{
-    float best2 = best * best;
-    bool found = false;
-    const unsigned lt = (1u << lane) - 1u;
-    if (lane == 0) st[0] = StackEntry{0u, 0.0f};
-    int sp = 1;
-    __syncwarp();
-    while (sp > 0)
-    {
-        const int take = sp > kSoloStack - 128 ? 1 : (sp < 32 ? sp : 32);
-        sp -= take;
-        StackEntry en = StackEntry{kNone, INFINITY};
-        if (lane < take) en = st[sp + lane];
-        __syncwarp();
-        uint32_t cand = 0xFFFFFFFFu; // distance as ordered bits (>= +0)
-        uint32_t pr0 = kNone, pr1 = kNone;
-        float pk0 = 0.0f, pk1 = 0.0f;
-        if (en.node != kNone && en.key <= best2)
-        {
-            float4 a, b, c, d, e, f;
-            ld256(sv.snode + en.node, a, b);
-            ld256(reinterpret_cast<const char *>(sv.snode + en.node) + 32, c, d);
-            ld256(reinterpret_cast<const char *>(sv.snode + en.node) + 64, e, f);
-            const NodeBoxes nb = unpack_boxes(a, b, c);
-            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
-            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w);
-            const bool h0 = (m0 <= best2) && (d.w >= 0.0f) && cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-            const bool h1 = (m1 <= best2) && (f.x >= 0.0f) && cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
-            const bool far1 = m0 < m1; // the farther child is pushed first, so the nearer one is popped first
-            float ob = best, ob2 = best2;
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
-            {
-                const bool one = (ch == 0) == far1;
-                if (!(one ? h1 : h0)) continue;
-                const float m = one ? m1 : m0;
-                const uint32_t r = one ? r1 : r0;
-                if (r & kLeafFlag)
-                {
-                    const uint32_t payload = r & ~kLeafFlag, first = payload >> 2, cnt = payload & 3u;
-                    for (uint32_t k = 0; k < cnt; ++k)
-                    { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
-                        float4 e0, e1, e2, e3;
-                        ld256(sv.ledge + first + k, e0, e1);
-                        ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
-                        const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
-                        V3 cp;
-                        const float dist = point_segment_distance(pa, pb, p, &cp);
-                        if (dist * dist > ob2) continue;
-                        bool is_sil = isnan(e1.z); // boundary edge
-                        if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
-                        if (is_sil && dist <= ob)
-                        {
-                            ob = dist;
-                            ob2 = dist * dist;
-                            cand = __float_as_uint(dist);
-                        }
-                    }
-                }
-                else if (pr0 == kNone)
-                {
-                    pr0 = r;
-                    pk0 = m;
-                }
-                else
-                {
-                    pr1 = r;
-                    pk1 = m;
-                }
-            }
-        }
-        const unsigned c1 = __ballot_sync(kFull, pr0 != kNone), c2 = __ballot_sync(kFull, pr1 != kNone);
-        const int off = sp + __popc(c1 & lt) + __popc(c2 & lt);
-        if (pr0 != kNone) st[off] = StackEntry{pr0, pk0};
-        if (pr1 != kNone) st[off + 1] = StackEntry{pr1, pk1};
-        sp += __popc(c1) + __popc(c2);
-        const uint32_t mn = __reduce_min_sync(kFull, cand);
-        if (mn != 0xFFFFFFFFu)
-        { // cand <= best by construction
-            best = __uint_as_float(mn);
-            best2 = best * best;
-            found = true;
-        }
-        __syncwarp();
-    }
-    return found ? best : INFINITY;
-}
-template <int kFilter>
+// One query per WARP (solo_silhouette from the root): for batches too small to fill the machine with per-lane walks the
+// run time is the critical path of the most expensive query.
+constexpr int kSoloStackSil = 512;
+template <int kFilter, bool kEdge>
 __global__ void __launch_bounds__(kQueryThreads)
     k_silhouette_wide(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+                      const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
+                      float *__restrict__ out_point, unsigned long long *counter, const unsigned long long *__restrict__ list_n,
+                      const float *__restrict__ list_bound)
 {
-    __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStack];
+    __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStackSil];
     const int lane = threadIdx.x & 31;
-    StackEntry *solo = s_solo[threadIdx.x >> 5];
-    constexpr unsigned long long kRun = 4;
+    const FlatStack solo{s_solo[threadIdx.x >> 5]};
+    // list mode (the tail of k_silhouette_coop): `perm` is the list, *list_n its length, list_bound[i] the bound of entry i
+    if (list_n) n = (uint32_t)*list_n;
+    const unsigned long long kRun = list_n ? 1 : 4;
     for (;;)
     {
         unsigned long long base = 0;
@@ -1254,108 +964,15 @@ __global__ void __launch_bounds__(kQueryThreads)
             const uint32_t slot = perm ? __ldg(perm + s) : (uint32_t)s;
             const V3 p = load_point(q, slot);
             const bool flip = flipv ? (__ldg(flipv + slot) != 0) : false;
-            const float r = rmax ? __ldg(rmax + slot) : INFINITY;
-            const float ans = solo_silhouette<kFilter>(sv, solo, lane, p, flip, r);
-            if (lane == 0) out_dist[slot] = ans;
-        }
-    }
-}
-
-template <int kFilter>
-__global__ void __launch_bounds__(kQueryThreads)
-    k_silhouette_packet(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                        const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
-{
-    __shared__ PacketStack s_stack[kQueryThreads / 32];
-    const int lane = threadIdx.x & 31;
-    uint2 *stk = s_stack[threadIdx.x >> 5].e;
-    for (;;)
-    {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, 32ull);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= n) break;
-        const uint32_t s = (uint32_t)base + lane;
-        const bool valid = s < n;
-        const uint32_t slot = valid ? __ldg(perm + s) : 0u;
-        const V3 p = valid ? load_point(q, slot) : V3{0.f, 0.f, 0.f};
-        const bool flip = (valid && flipv) ? (__ldg(flipv + slot) != 0) : false;
-        float best = (valid && rmax) ? __ldg(rmax + slot) : INFINITY;
-        float best2 = best * best;
-        bool found = false;
-        unsigned mask = __ballot_sync(kFull, valid);
-        uint32_t node = 0;
-        int sp = 0;
-        for (;;)
-        {
-            float4 a, b, c, d, e, f;
-            ld256(sv.snode + node, a, b);
-            ld256(reinterpret_cast<const char *>(sv.snode + node) + 32, c, d);
-            ld256(reinterpret_cast<const char *>(sv.snode + node) + 64, e, f);
-            const NodeBoxes nb = unpack_boxes(a, b, c);
-            const float m0 = box_mindist2(nb.lo0, nb.hi0, p), m1 = box_mindist2(nb.lo1, nb.hi1, p);
-            const uint32_t r0 = __float_as_uint(f.z), r1 = __float_as_uint(f.w); // warp-uniform
-            const bool in = (mask >> lane) & 1u;
-            // the reference's per-child test: is_valid(cone) && overlap(cone, p, box, mindist^2)   (query.cuh:366-367)
-            bool h0 = in && (m0 <= best2) && (d.w >= 0.0f);
-            bool h1 = in && (m1 <= best2) && (f.x >= 0.0f);
-            if (h0) h0 = cone_test<kFilter>(V3{d.x, d.y, d.z}, d.w, e.x, p, nb.lo0, nb.hi0, m0);
-            if (h1) h1 = cone_test<kFilter>(V3{e.y, e.z, e.w}, f.x, f.y, p, nb.lo1, nb.hi1, m1);
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
+            const float r = list_n ? __ldg(list_bound + s) : (rmax ? __ldg(rmax + slot) : INFINITY);
+            uint32_t eslot = kNone;
+            const float ans = solo_silhouette<kFilter, kEdge, kSoloStackSil>(sv, solo, lane, p, flip, r, eslot);
+            if (lane == 0)
             {
-                const uint32_t r = ch ? r1 : r0;
-                if (!(r & kLeafFlag)) continue;
-                const bool w = (ch ? h1 : h0) && ((ch ? m1 : m0) <= best2);
-                if (!__any_sync(kFull, w)) continue;
-                const uint32_t payload = r & ~kLeafFlag;
-                const uint32_t first = payload >> 2, cnt = payload & 3u;
-                for (uint32_t k = 0; k < cnt; ++k)
-                { // silhouette_distance_calculator over the owned edges          scene.cuh:978-1003, 788-824
-                    float4 e0, e1, e2, e3;
-                    ld256(sv.ledge + first + k, e0, e1);
-                    ld256(reinterpret_cast<const char *>(sv.ledge + first + k) + 32, e2, e3);
-                    const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
-                    V3 cp;
-                    const float dist = point_segment_distance(pa, pb, p, &cp);
-                    if (!w || dist * dist > best2) continue;
-                    bool is_sil = isnan(e1.z); // boundary edge
-                    if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
-                    if (is_sil && dist <= best)
-                    {
-                        best = dist;
-                        best2 = dist * dist;
-                        found = true;
-                    }
-                }
-            }
-            const bool w0 = h0 && !(r0 & kLeafFlag) && m0 <= best2;
-            const bool w1 = h1 && !(r1 & kLeafFlag) && m1 <= best2;
-            const unsigned b0 = __ballot_sync(kFull, w0), b1 = __ballot_sync(kFull, w1);
-            if (b0 && b1)
-            {
-                const unsigned near1 = __ballot_sync(kFull, (w0 && w1) ? (m1 < m0) : w1);
-                const bool first1 = 2 * __popc(near1) > __popc(b0 | b1);
-                stk[sp] = first1 ? make_uint2(r0, b0) : make_uint2(r1, b1);
-                ++sp;
-                node = first1 ? r1 : r0;
-                mask = first1 ? b1 : b0;
-            }
-            else if (b0 | b1)
-            {
-                node = b0 ? r0 : r1;
-                mask = b0 | b1;
-            }
-            else
-            {
-                if (sp == 0) break;
-                --sp;
-                const uint2 en = stk[sp];
-                node = en.x;
-                mask = en.y;
+                out_dist[slot] = ans;
+                if (kEdge) write_silhouette_point(sv, slot, eslot, p, ans < INFINITY, out_edge, out_point);
             }
         }
-        if (valid) out_dist[slot] = found ? best : INFINITY;
     }
 }
 
@@ -1477,6 +1094,158 @@ __global__ void __launch_bounds__(kQueryThreads)
     }
 }
 
+// Per-lane walk in the REFERENCE'S ORDER with the leaf tests taken out of the traversal step (default, "query.ray_kernel" = 1).
+// profiles/r2a: in k_intersect above a warp runs the Moeller-Trumbore code on the 2-3 lanes that happen to stand at a leaf in
+// almost every step, and tests a far leaf child before the near subtree has been searched.  Here a hit leaf child is not
+// tested where it is met:
+//   * the children of a node are taken nearer first, as in the reference (query.cuh:128-160, L first on ties).  If the first
+//     hit child is an internal node the lane descends into it and the other hit child — leaf or internal — goes on the stack
+//     with its entry distance; if the first hit child is a LEAF the lane parks on it (`pleaf`), the other child goes on the
+//     stack and the lane waits;
+//   * when `flush_lanes` lanes of the warp are parked (or no lane can walk) the warp tests all parked leaves at once — the
+//     triangle code runs on many lanes instead of two — and each of those lanes then pops its next entry under the
+//     reference's pop-time rejection (query.cuh:106) with its NEW best t; a popped leaf parks the lane again.
+//   So every lane tests exactly the leaves, in exactly the order, of the reference's stack walk: same t, same triangle.
+//   * the lowest kRStack stack levels live in shared memory (bank = lane), deeper ones in local memory;
+//   * finished lanes take their next ray when `refill_lanes` of them are idle (the refill code — six loads, three divisions —
+//     is then not run for one lane at a time in nearly every step).
+constexpr int kRStack = 12;
+template <bool kAnyHit>
+__global__ void __launch_bounds__(kQueryThreads)
+    k_intersect_parked(SceneView sv, const float *__restrict__ org, const float *__restrict__ dir, const float *__restrict__ tmaxv,
+                       const uint32_t *__restrict__ perm, uint32_t n, snch_hit *__restrict__ hits, uint8_t *__restrict__ found_out,
+                       unsigned long long *counter, int flush_lanes, int refill_lanes)
+{
+    __shared__ StackEntry s_stk[kRStack][kQueryThreads];
+    const int lane = threadIdx.x & 31;
+    Feeder fd{0u, 0u, false};
+    StackEntry lstk[kStackDepth - kRStack];
+    int sp = 0;
+    V3 o = V3{0.f, 0.f, 0.f}, dv = o, dinv = o;
+    float max_dist = INFINITY, best_t = INFINITY, best_u = 0.f, best_v = 0.f;
+    uint32_t best_prim = kNone, slot = kNone, node = kNone, pleaf = kNone;
+    bool busy = false;
+    // next entry of this lane's stack that survives the pop-time rejection: an internal node to walk, a leaf to park on, or the end of the ray
+    auto advance = [&]()
+    {
+        node = kNone;
+        pleaf = kNone;
+        while (sp > 0)
+        {
+            --sp;
+            const StackEntry se = sp < kRStack ? s_stk[sp][threadIdx.x] : lstk[sp - kRStack];
+            if (se.key > best_t) continue;
+            if (se.node & kLeafFlag) pleaf = se.node & ~kLeafFlag;
+            else node = se.node;
+            return;
+        }
+        if (found_out) found_out[slot] = best_prim != kNone ? 1 : 0;
+        if (!kAnyHit && hits)
+        {
+            snch_hit h;
+            h.t = best_t;
+            h.u = best_u;
+            h.v = best_v;
+            h.prim = best_prim;
+            hits[slot] = h;
+        }
+        busy = false;
+    };
+    for (;;)
+    {
+        // ---- 1. parked leaves
+        const unsigned parked = __ballot_sync(kFull, pleaf != kNone);
+        if (parked && (__popc(parked) >= flush_lanes || !__any_sync(kFull, node != kNone)))
+        {
+            if (pleaf != kNone)
+            {
+                const LTri *tp = sv.ltri + pleaf;
+                float4 t0, t1, t2, t3;
+                ld256(tp, t0, t1);
+                ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
+                float t, u, v;
+                bool done = false;
+                if (ray_triangle(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, o, dv, &t, &u, &v) && t < max_dist && t < best_t)
+                {
+                    best_t = t;
+                    best_u = u;
+                    best_v = v;
+                    best_prim = __float_as_uint(t0.w);
+                    done = kAnyHit;
+                }
+                if (done) sp = 0;
+                advance();
+            }
+        }
+        // ---- 2. idle lanes take the next ray
+        const unsigned idle = __ballot_sync(kFull, !busy);
+        if (idle)
+        {
+            if (!fd.exhausted && (__popc(idle) >= refill_lanes || !__any_sync(kFull, node != kNone)))
+            {
+                const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter);
+                if (s != kNone)
+                {
+                    slot = perm ? __ldg(perm + s) : s;
+                    o = load_point(org, slot);
+                    dv = load_point(dir, slot);
+                    dinv = V3{1.0f / dv.x, 1.0f / dv.y, 1.0f / dv.z}; // aabb.cuh:305-312
+                    max_dist = tmaxv ? __ldg(tmaxv + slot) : INFINITY;
+                    best_t = INFINITY;
+                    best_u = best_v = 0.f;
+                    best_prim = kNone;
+                    busy = true;
+                    sp = 0;
+                    node = 0;
+                    pleaf = kNone;
+                }
+            }
+            if (fd.exhausted && idle == kFull) break;
+        }
+        // ---- 3. one traversal step
+        if (node != kNone)
+        {
+            float4 a, b, c, d;
+            ld256(sv.bnode + node, a, b);
+            ld256(reinterpret_cast<const char *>(sv.bnode + node) + 32, c, d);
+            const NodeBoxes nb = unpack_boxes(a, b, c);
+            float e0, e1;
+            bool h0 = box_ray(nb.lo0, nb.hi0, o, dinv, max_dist, &e0);
+            bool h1 = box_ray(nb.lo1, nb.hi1, o, dinv, max_dist, &e1);
+            h0 = h0 && !(e0 > best_t); // the rejection the reference applies when it pops the child (query.cuh:106)
+            h1 = h1 && !(e1 > best_t);
+            uint32_t r0 = __float_as_uint(d.x), r1 = __float_as_uint(d.y);
+            if (h0 && h1 && e1 < e0)
+            { // nearer child first; L first on ties (query.cuh:141)
+                const uint32_t tr = r0;
+                r0 = r1;
+                r1 = tr;
+                const float te = e0;
+                e0 = e1;
+                e1 = te;
+            }
+            if (h0 && h1)
+            {
+                const StackEntry se = StackEntry{r1, e1};
+                if (sp < kRStack) s_stk[sp][threadIdx.x] = se;
+                else lstk[sp - kRStack] = se;
+                ++sp;
+            }
+            if (h0 || h1)
+            {
+                const uint32_t r = h0 ? r0 : r1;
+                if (r & kLeafFlag)
+                {
+                    pleaf = r & ~kLeafFlag;
+                    node = kNone;
+                }
+                else node = r;
+            }
+            else advance();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // SampleTriangleInSphere                                              sample.cuh:23-92 + 7-21, scene.cuh:14-27
 // One root-to-leaf path per query: no stack, no variance in length beyond the tree depth -> one query per thread.
@@ -1582,52 +1351,79 @@ __global__ void k_fill_empty(uint64_t n, uint32_t *idx, float *dist, snch_hit *h
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-// Counts the traversal launch and, when kernel timing is on ("query.time_kernels"), brackets it with CUDA events on the
-// launching stream; the elapsed time of the PREVIOUS timed launch is folded into the counters lazily.
+// Counts the traversal launch and, when kernel timing is on ("query.time_kernels"), brackets it with its own CUDA event pair
+// on the launching stream; elapsed times are folded into the counters when they are read (QueryCounters::fold).
 struct TraversalTimer
 {
     QueryCounters *qc;
     cudaStream_t st;
+    QueryCounters::Pair pair{nullptr, nullptr};
+    bool timed = false;
     TraversalTimer(QueryCounters *qc_, cudaStream_t st_) : qc(qc_), st(st_)
     {
         if (!qc) return;
         qc->launches += 1;
         qc->traversal_launches += 1;
-        if (!qc->time_kernels) return;
-        qc->fold();
-        if (!qc->ev0)
-        {
-            cudaEventCreate(&qc->ev0);
-            cudaEventCreate(&qc->ev1);
-        }
-        cudaEventRecord(qc->ev0, st);
+        if (qc->time_kernels.load()) timed = qc->begin(pair, st);
     }
     ~TraversalTimer()
     {
-        if (qc && qc->time_kernels && qc->ev0)
-        {
-            cudaEventRecord(qc->ev1, st);
-            qc->pending = true;
-        }
+        if (timed) qc->end(pair, st);
     }
 };
-int read_sil_stats(unsigned long long out[8], bool reset)
+bool QueryCounters::begin(Pair &p, cudaStream_t st)
 {
-    SNCH_CUDA(cudaMemcpyFromSymbol(out, g_sil_stats, 64));
-    if (reset)
     {
-        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        SNCH_CUDA(cudaMemcpyToSymbol(g_sil_stats, z, 64));
+        std::lock_guard<std::mutex> lock(mu);
+        if (!spare.empty())
+        {
+            p = spare.back();
+            spare.pop_back();
+        }
     }
-    return SNCH_OK;
+    if (!p.a && (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess))
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return cudaEventRecord(p.a, st) == cudaSuccess;
+}
+void QueryCounters::end(const Pair &p, cudaStream_t st)
+{
+    cudaEventRecord(p.b, st);
+    std::lock_guard<std::mutex> lock(mu);
+    pending.push_back(p);
 }
 void QueryCounters::fold()
 {
-    if (!pending) return;
-    float ms = 0.f;
-    if (cudaEventSynchronize(ev1) == cudaSuccess && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) traversal_ms += ms;
-    else cudaGetLastError();
-    pending = false;
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Pair &p : pending)
+    {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) traversal_ms += ms;
+        else cudaGetLastError();
+        spare.push_back(p);
+    }
+    pending.clear();
+}
+void QueryCounters::reset()
+{
+    fold();
+    launches = 0;
+    traversal_launches = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    traversal_ms = 0.0;
+}
+void QueryCounters::release()
+{
+    fold();
+    std::lock_guard<std::mutex> lock(mu);
+    for (const Pair &p : spare)
+    {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    spare.clear();
 }
 
 static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kQueryThreads - 1) / kQueryThreads); }
@@ -1635,30 +1431,32 @@ static inline unsigned grid_for(uint64_t n) { return (unsigned)((n + kQueryThrea
 // bytes of device scratch one batch of n queries needs (ordering buffers + sort counters + the work counter)
 uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t)
 {
-    uint64_t b = kScratchHeader; // work counter + query box + region counters
+    uint64_t b = kScratchHeader + kTailBytes; // work counters + query box | tail list of the silhouette kernel
     if (t.sort_min_n > 0 && n >= (uint64_t)t.sort_min_n) b += 4 * align_up(n * 4, 256) + align_up(sort_scratch_elems(n) * 4, 256);
     return b;
 }
 
 // Lays the scratch out and, for batches worth ordering, produces the Morton permutation.  *perm_out = nullptr otherwise.
 int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n, unsigned char *scratch,
-                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims, int radius_desc)
+                  cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims, int radius_desc,
+                  const float *dirs)
 {
-    SNCH_CUDA(cudaMemsetAsync(scratch, 0, t.feed ? kScratchHeader : 64, st));
+    SNCH_CUDA(cudaMemsetAsync(scratch, 0, 64, st));
     *counter_out = reinterpret_cast<unsigned long long *>(scratch);
     *perm_out = nullptr;
     if (!(order && t.sort_min_n > 0 && n >= (uint32_t)t.sort_min_n)) return SNCH_OK;
     int *box = reinterpret_cast<int *>(scratch + 64);
     const uint64_t a = align_up((uint64_t)n * 4, 256);
-    uint32_t *keys = reinterpret_cast<uint32_t *>(scratch + kScratchHeader);
-    uint32_t *perm = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + a);
-    uint32_t *ktmp = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 2 * a);
-    uint32_t *vtmp = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 3 * a);
-    uint32_t *sscr = reinterpret_cast<uint32_t *>(scratch + kScratchHeader + 4 * a);
+    unsigned char *ord = scratch + kScratchHeader + kTailBytes;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(ord);
+    uint32_t *perm = reinterpret_cast<uint32_t *>(ord + a);
+    uint32_t *ktmp = reinterpret_cast<uint32_t *>(ord + 2 * a);
+    uint32_t *vtmp = reinterpret_cast<uint32_t *>(ord + 3 * a);
+    uint32_t *sscr = reinterpret_cast<uint32_t *>(ord + 4 * a);
     const unsigned g = (n + 255) / 256;
     k_query_box_init<<<1, 32, 0, st>>>(box);
     k_query_bounds<<<g < 1184 ? g : 1184, 256, 0, st>>>(pts, stride, dims, n, box);
-    k_query_keys<<<g, 256, 0, st>>>(pts, stride, dims, n, box, radius, radius_desc, keys, perm);
+    k_query_keys<<<g, 256, 0, st>>>(pts, stride, dims, n, box, radius, radius_desc, dirs, keys, perm);
     int bits = t.sort_bits < 8 ? 8 : (t.sort_bits > 30 ? 30 : t.sort_bits);
     const int sort_launches = radix_sort_pairs(keys, perm, ktmp, vtmp, n, bits, sscr, st, 30 - bits);
     if (qc) qc->launches += 3 + sort_launches;
@@ -1667,52 +1465,48 @@ int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride
     return SNCH_OK;
 }
 
-// per-lane silhouette traversal: v4 (warp-shared leaf queue, shared-memory stack) unless the knob or the scene size
-// (queue entries pack the owner lane next to the leaf payload) asks for v3; cone test per "query.cone_filter"
-template <int kFilter>
-static void launch_silhouette_lanes_f(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,
-                                      const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
+// silhouette traversal: one query per warp for batches too small to fill the machine ("query.wide_max_n_sil"), per-lane walks
+// with the warp-shared leaf queue otherwise; cone test per "query.cone_filter"; the edge-carrying instantiation only when
+// the caller asked for the edge index or the point
+template <int kFilter, bool kEdge>
+static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,
+                                     const uint32_t *perm, uint32_t n, float *dist, uint32_t *edge, float *point, unsigned long long *counter,
+                                     unsigned char *tail, cudaStream_t st, QueryCounters *qc)
 {
-    const bool coop = t.sil_kernel != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopMaxPayload;
-    // region feed: per CTA (1) or per SM (2); `per` is a whole number of chunks so regions never share a chunk
-    const unsigned grid = persistent_grid(k_silhouette_coop<kFilter, false, false, false>, t, n);
-    int sms = 1;
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    uint32_t regions = (t.feed & 255) == 1 ? grid : ((t.feed & 255) == 2 ? (uint32_t)sms : 0u);
-    if (regions > kMaxRegions) regions = kMaxRegions;
-    const int fm = (regions ? (t.feed & 255) : 0) | (t.feed & ~255);
-    const uint32_t per = regions ? (uint32_t)((((uint64_t)n + regions - 1) / regions + kChunk - 1) / kChunk * kChunk) : 0u;
     if (n < (uint32_t)t.wide_max_n_sil)
     {
-        k_silhouette_wide<kFilter><<<persistent_grid(k_silhouette_wide<kFilter>, t, n < (1u << 26) ? n * 16 : n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm,
-                                                                                                                                    n, dist, counter);
+        if (qc) qc->last_kernel = kEdge ? "k_silhouette_wide<edge>" : "k_silhouette_wide";
+        k_silhouette_wide<kFilter, kEdge><<<persistent_grid(k_silhouette_wide<kFilter, kEdge>, t, n < (1u << 26) ? n * 16 : n), kQueryThreads, 0, st>>>(
+            v, q, flip, rmax, perm, n, dist, edge, point, counter, nullptr, nullptr);
         return;
     }
-    constexpr int kCF = kFilter >= 2 ? kFilter : 2; // the compact walk exists for the MUFU filter modes only
-    const bool seeded = t.sil_seed != 0 && ((uint64_t)v.n_edges << 2) + 3 < kCoopHintFlag && (!v.cnode || v.n_tris < kCoopHintFlag);
-    if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode && t.sil_stats)
-        k_silhouette_coop<kCF, true, true, false><<<persistent_grid(k_silhouette_coop<kCF, true, true, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
-    else if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode && seeded)
-        k_silhouette_coop<kCF, true, false, true><<<persistent_grid(k_silhouette_coop<kCF, true, false, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
-    else if (coop && kFilter >= 2 && t.sil_nodes != 0 && v.cnode)
-        k_silhouette_coop<kCF, true, false, false><<<persistent_grid(k_silhouette_coop<kCF, true, false, false>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
-    else if (coop && seeded)
-        k_silhouette_coop<kFilter, false, false, true><<<persistent_grid(k_silhouette_coop<kFilter, false, false, true>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
-    else if (coop)
-        k_silhouette_coop<kFilter, false, false, false><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter, fm, regions, per);
-    else k_silhouette<kFilter><<<persistent_grid(k_silhouette<kFilter>, t, n), kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, counter);
+    const bool seeded = !kEdge && t.sil_seed != 0;
+    if (qc) qc->last_kernel = kEdge ? "k_silhouette_coop<edge>" : (seeded ? "k_silhouette_coop<seed>" : "k_silhouette_coop");
+    const unsigned grid = seeded ? persistent_grid(k_silhouette_coop<kFilter, true, false>, t, n) : persistent_grid(k_silhouette_coop<kFilter, false, kEdge>, t, n);
+    // the tail list holds at most one entry per resident lane (tail_scratch_bytes sizes it for the largest grid)
+    uint32_t *tail_slot = reinterpret_cast<uint32_t *>(tail);
+    float *tail_bound = reinterpret_cast<float *>(tail + kTailEntries * 4);
+    const int tl = (t.sil_tail > 0 && (uint64_t)grid * kQueryThreads <= kTailEntries) ? (t.sil_tail > 31 ? 31 : t.sil_tail) : 0;
+    if (seeded)
+        k_silhouette_coop<kFilter, true, false><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound);
+    else
+        k_silhouette_coop<kFilter, false, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound);
+    if (tl)
+    { // finish the listed queries one per warp; its own work counter is counter[2], the list length counter[1]
+        if (qc) qc->launches += 1;
+        k_silhouette_wide<kFilter, kEdge><<<grid < 592 ? grid : 592, kQueryThreads, 0, st>>>(v, q, flip, rmax, tail_slot, 0u, dist, edge, point, counter + 2, counter + 1,
+                                                                                          tail_bound);
+    }
 }
 static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,
-                                    const uint32_t *perm, uint32_t n, float *dist, unsigned long long *counter, cudaStream_t st)
+                                    const uint32_t *perm, uint32_t n, float *dist, uint32_t *edge, float *point, unsigned long long *counter,
+                                    unsigned char *tail, cudaStream_t st, QueryCounters *qc)
 {
-    if (t.cone_filter >= 3) launch_silhouette_lanes_f<3>(v, t, q, flip, rmax, perm, n, dist, counter, st);
-    else if (t.cone_filter == 2) launch_silhouette_lanes_f<2>(v, t, q, flip, rmax, perm, n, dist, counter, st);
-    else if (t.cone_filter == 1) launch_silhouette_lanes_f<1>(v, t, q, flip, rmax, perm, n, dist, counter, st);
-    else launch_silhouette_lanes_f<0>(v, t, q, flip, rmax, perm, n, dist, counter, st);
+    const bool e = edge || point;
+    if (t.cone_filter && e) launch_silhouette_kernel<1, true>(v, t, q, flip, rmax, perm, n, dist, edge, point, counter, tail, st, qc);
+    else if (t.cone_filter) launch_silhouette_kernel<1, false>(v, t, q, flip, rmax, perm, n, dist, edge, point, counter, tail, st, qc);
+    else if (e) launch_silhouette_kernel<0, true>(v, t, q, flip, rmax, perm, n, dist, edge, point, counter, tail, st, qc);
+    else launch_silhouette_kernel<0, false>(v, t, q, flip, rmax, perm, n, dist, edge, point, counter, tail, st, qc);
 }
 
 // One query per warp (k_closest_wide) instead of packets: for batches too small to fill the machine, and for batches SPARSE
@@ -1724,6 +1518,20 @@ static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, co
 static bool use_wide_closest(const QueryTuning &t, uint64_t n, uint64_t n_tris)
 {
     return t.wide_max_n > 0 && (n < (uint64_t)t.wide_max_n || n < 2 * n_tris);
+}
+static void launch_closest_kernel(const SceneView &v, const QueryTuning &t, const float *q, const uint32_t *perm, uint32_t n, uint32_t *idx,
+                                  float *dist, unsigned long long *counter, cudaStream_t st, QueryCounters *qc)
+{
+    if (use_wide_closest(t, n, v.n_tris))
+    {
+        if (qc) qc->last_kernel = "k_closest_wide";
+        k_closest_wide<<<persistent_grid(k_closest_wide, t, n < (1u << 26) ? n * 16 : n), kQueryThreads, 0, st>>>(v, q, perm, n, idx, dist, counter, t.seed);
+    }
+    else
+    {
+        if (qc) qc->last_kernel = "k_closest_packet";
+        k_closest_packet<<<persistent_grid(k_closest_packet, t, n), kQueryThreads, 0, st>>>(v, q, perm, n, idx, dist, counter, t.seed);
+    }
 }
 
 int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
@@ -1741,45 +1549,47 @@ int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uin
     const int rc = prepare_batch(t, true, q, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);
-    if (use_wide_closest(t, n, v.n_tris))
-        k_closest_wide<<<persistent_grid(k_closest_wide, t, (uint32_t)(n < (1u << 26) ? n * 16 : n)), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx,
-                                                                                                                        dist, counter, t.seed);
-    else if (perm && (t.packet & 1))
-        k_closest_packet<<<persistent_grid(k_closest_packet, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist,
-                                                                                                   counter, t.seed);
-    else
-        k_closest<<<persistent_grid(k_closest, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, q, perm, (uint32_t)n, idx, dist, counter, t.seed);
+    launch_closest_kernel(v, t, q, perm, (uint32_t)n, idx, dist, counter, st, qc);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
 int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax, uint64_t n,
-                      float *dist, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)
+                      float *dist, uint32_t *edge, float *point, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)
 {
     if (n == 0) return SNCH_OK;
     if (v.n_tris == 0)
     {
-        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, edge, dist, nullptr, nullptr, nullptr, nullptr, point);
         SNCH_CUDA(cudaGetLastError());
         return SNCH_OK;
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, true, q, 3, ((t.packet & 2) || t.sort_radius) ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3,
-                                 (!(t.packet & 2) && t.sort_radius >= 2) ? t.sort_radius - 1 : 0);
+    const int rc = prepare_batch(t, true, q, 3, t.sort_radius ? rmax : nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3,
+                                 t.sort_radius >= 2 ? t.sort_radius - 1 : 0);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);
-    if (perm && (t.packet & 2))
-    {
-        if (t.cone_filter)
-            k_silhouette_packet<1><<<persistent_grid(k_silhouette_packet<1>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
-                v, q, flip, rmax, perm, (uint32_t)n, dist, counter);
-        else
-            k_silhouette_packet<0><<<persistent_grid(k_silhouette_packet<0>, t, (uint32_t)n), kQueryThreads, 0, st>>>(
-                v, q, flip, rmax, perm, (uint32_t)n, dist, counter);
-    }
-    else launch_silhouette_lanes(v, t, q, flip, rmax, perm, (uint32_t)n, dist, counter, st);
+    launch_silhouette_lanes(v, t, q, flip, rmax, perm, (uint32_t)n, dist, edge, point, counter, scratch + kScratchHeader, st, qc);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
+}
+static void launch_intersect_kernel(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, const uint32_t *perm,
+                                    uint32_t n, snch_hit *hits, uint8_t *found, bool any_hit, unsigned long long *counter, cudaStream_t st,
+                                    QueryCounters *qc)
+{
+    if (t.ray_kernel == 0)
+    {
+        if (qc) qc->last_kernel = "k_intersect";
+        if (any_hit) k_intersect<true><<<persistent_grid(k_intersect<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter);
+        else k_intersect<false><<<persistent_grid(k_intersect<false>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter);
+        return;
+    }
+    if (qc) qc->last_kernel = "k_intersect_parked";
+    const int fl = t.ray_flush < 1 ? 1 : t.ray_flush, rl = t.ray_refill < 1 ? 1 : t.ray_refill;
+    if (any_hit)
+        k_intersect_parked<true><<<persistent_grid(k_intersect_parked<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
+    else
+        k_intersect_parked<false><<<persistent_grid(k_intersect_parked<false>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
 }
 int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
                      uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)
@@ -1793,15 +1603,10 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc);
+    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3, 0, t.sort_rays >= 2 ? d : nullptr);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);
-    if (any_hit)
-        k_intersect<true><<<persistent_grid(k_intersect<true>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, (uint32_t)n, hits,
-                                                                                                      found, counter);
-    else
-        k_intersect<false><<<persistent_grid(k_intersect<false>, t, (uint32_t)n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, (uint32_t)n,
-                                                                                                        hits, found, counter);
+    launch_intersect_kernel(v, t, o, d, tmax, perm, (uint32_t)n, hits, found, any_hit != 0, counter, st, qc);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
 }
@@ -1818,6 +1623,7 @@ int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, co
     (void)t;
     (void)scratch; // one short root-to-leaf path per query: neither ordering nor work stealing pays for itself here
     TraversalTimer tt(qc, st);
+    if (qc) qc->last_kernel = "k_sample";
     k_sample<<<grid_for(n), kQueryThreads, 0, st>>>(v, sph, rnd, nullptr, (uint32_t)n, idx, pdf, pt);
     SNCH_CUDA(cudaGetLastError());
     return SNCH_OK;
@@ -1856,7 +1662,7 @@ int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers
     {
         k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, c_index, d_closest, io.hits, io.found, io.sample_index, io.sample_pdf,
                                                             io.sample_point);
-        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, d_sil, nullptr, nullptr, nullptr, nullptr, nullptr);
+        k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, io.silhouette_edge, d_sil, nullptr, nullptr, nullptr, nullptr, io.silhouette_point);
         k_fill_empty<<<grid_for(n), kQueryThreads, 0, st>>>(n, nullptr, radius, nullptr, nullptr, nullptr, nullptr, nullptr);
         SNCH_CUDA(cudaGetLastError());
         return SNCH_OK;
@@ -1868,20 +1674,13 @@ int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers
     if (rc != SNCH_OK) return rc;
     {
         TraversalTimer tt(qc, st);
-        if (use_wide_closest(t, m, v.n_tris))
-            k_closest_wide<<<persistent_grid(k_closest_wide, t, m < (1u << 26) ? m * 16 : m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index,
-                                                                                                                  d_closest, counter, t.seed);
-        else if (perm && (t.packet & 1))
-            k_closest_packet<<<persistent_grid(k_closest_packet, t, m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index, d_closest,
-                                                                                               counter, t.seed);
-        else
-            k_closest<<<persistent_grid(k_closest, t, m), kQueryThreads, 0, st>>>(v, io.points, perm, m, c_index, d_closest, counter,
-                                                                                   t.seed);
+        launch_closest_kernel(v, t, io.points, perm, m, c_index, d_closest, counter, st, qc);
     }
-    SNCH_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+    SNCH_CUDA(cudaMemsetAsync(counter, 0, 24, st));
     {
         TraversalTimer tt(qc, st);
-        launch_silhouette_lanes(v, t, io.points, io.flip, d_closest, perm, m, d_sil, counter, st);
+        launch_silhouette_lanes(v, t, io.points, io.flip, d_closest, perm, m, d_sil, io.silhouette_edge, io.silhouette_point, counter, scratch + kScratchHeader, st,
+                                qc);
     }
     k_star_radius<<<(m + 255) / 256, 256, 0, st>>>(io.points, d_closest, d_sil, m, radius, spheres);
     if (qc) qc->launches += 1;
@@ -1889,13 +1688,12 @@ int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers
     {
         SNCH_CUDA(cudaMemsetAsync(counter, 0, 8, st));
         TraversalTimer tt(qc, st);
-        const uint32_t *rperm = t.sort_rays ? perm : nullptr;
-        k_intersect<false><<<persistent_grid(k_intersect<false>, t, m), kQueryThreads, 0, st>>>(v, io.points, io.dirs, radius, rperm, m, io.hits,
-                                                                                               io.found, counter);
+        launch_intersect_kernel(v, t, io.points, io.dirs, radius, t.sort_rays ? perm : nullptr, m, io.hits, io.found, false, counter, st, qc);
     }
     if (io.rnd && io.sample_index && io.sample_pdf)
     {
         TraversalTimer tt(qc, st);
+        if (qc) qc->last_kernel = "k_sample";
         k_sample<<<grid_for(n), kQueryThreads, 0, st>>>(v, spheres, io.rnd, perm, m, io.sample_index, io.sample_pdf, io.sample_point);
     }
     SNCH_CUDA(cudaGetLastError());

@@ -52,64 +52,15 @@ struct Feeder
 {
     uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
     bool exhausted;     // the global counter ran past n
-    uint32_t hop = 0;   // region feed: regions this warp has seen run dry (it draws from region (home + hop) % regions)
 };
-// Region feed ("query.feed" = 1 per CTA, 2 per SM): the ordered batch is cut into `regions` contiguous ranges of `per` slots,
-// each with its own counter; a warp draws its chunks from its home region and moves on to the next region only when one
-// has run dry (counters only grow, so a dry region stays dry and `hop` never goes back).  Warps that share an L1 thus
-// work on neighbouring queries and re-read each other's node records.
-struct RegionFeed
-{
-    unsigned long long *counters; // regions x u64, zeroed per batch (scratch + kScratchCounters)
-    uint32_t regions, per, home;
-};
-constexpr uint32_t kMaxRegions = 2048;
-constexpr uint64_t kScratchCounters = 256, kScratchHeader = kScratchCounters + kMaxRegions * 8; // work counter + query box | region counters
-SNCH_DI uint32_t smid()
-{
-    uint32_t r;
-    asm("mov.u32 %0, %%smid;" : "=r"(r));
-    return r;
-}
-SNCH_DI void region_draw(Feeder &f, const RegionFeed &rf, int lane, uint32_t n)
-{
-    unsigned long long base = ~0ull;
-    uint32_t hop = f.hop;
-    if (lane == 0)
-    {
-        for (; hop < rf.regions; ++hop)
-        {
-            const uint32_t r = (rf.home + hop) % rf.regions;
-            const unsigned long long lo = (unsigned long long)r * rf.per;
-            if (lo >= n) continue;
-            const unsigned long long len = min((unsigned long long)rf.per, (unsigned long long)n - lo);
-            if (*reinterpret_cast<volatile unsigned long long *>(rf.counters + r) >= len) continue;
-            const unsigned long long off = atomicAdd(rf.counters + r, (unsigned long long)kChunk);
-            if (off < len)
-            {
-                base = lo + off;
-                f.end = (uint32_t)min(lo + len, base + kChunk);
-                break;
-            }
-        }
-    }
-    base = __shfl_sync(kFull, base, 0);
-    f.hop = __shfl_sync(kFull, hop, 0);
-    f.end = __shfl_sync(kFull, f.end, 0);
-    if (base == ~0ull)
-    {
-        f.exhausted = true;
-        f.end = f.next;
-    }
-    else f.next = (uint32_t)base;
-}
+constexpr uint64_t kScratchHeader = 256; // work counters (u64 x 8: [0] batch, [1] tail list length, [2] tail work) + query box (6 ordered ints at +64)
+constexpr uint64_t kTailEntries = 1u << 18; // tail list of the silhouette kernel: one (slot, bound) pair per resident lane at most
+constexpr uint64_t kTailBytes = kTailEntries * 8;
 // Gives every idle lane (bit set in `idle`) the next query slot of the warp's chunk; draws a new chunk when needed.
 // Returns the slot for this lane or kNone.  Warp-convergent call.
-SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter,
-                             const RegionFeed *rf = nullptr)
+SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter)
 {
-    if (f.next == f.end && !f.exhausted && rf && rf->regions) region_draw(f, *rf, lane, n);
-    else if (f.next == f.end && !f.exhausted)
+    if (f.next == f.end && !f.exhausted)
     {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)chunk_for(n));
@@ -135,7 +86,7 @@ SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane,
 // query points (`dims` = 2 or 3 coordinates at pts[stride * i]).  *perm_out = nullptr otherwise.            query.cu
 int prepare_batch(const QueryTuning &t, bool order, const float *pts, int stride, const float *radius, uint32_t n, unsigned char *scratch,
                   cudaStream_t st, unsigned long long **counter_out, const uint32_t **perm_out, QueryCounters *qc, int dims = 3,
-                  int radius_desc = 0);
+                  int radius_desc = 0, const float *dirs = nullptr);
 
 // grid of a persistent kernel: SMs x resident CTAs, or fewer when the batch has fewer chunks than that
 template <typename K> static inline unsigned persistent_grid(K kernel, const QueryTuning &t, uint32_t n)

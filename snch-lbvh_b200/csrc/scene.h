@@ -3,6 +3,7 @@
 #include "../../include/snch_b200.h"
 #include "layout.h"
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -14,43 +15,50 @@ struct QueryTuning
 {
     int sort_min_n = 16384; // batches at least this large are visited in Morton order of the query points (0 = never)
     int sort_bits = 24;     // Morton key bits the ordering sorts on (top bits of the 30-bit code)
-    int sort_radius = 2;    // bounded silhouette batches (per-lane kernels): 1 = order by search-radius octave first, then Morton code;
+    int sort_radius = 2;    // bounded silhouette batches: 1 = order by search-radius octave first, then Morton code;
                             // 2 = the same with the largest radii first (longest walks start first, the tail is made of cheap queries);
                             // 3, 4 = largest first with 2 / 4 classes per octave
-    int sort_rays = 0;      // also order ray batches by origin (off: random directions decorrelate the paths anyway)
-    int packet = 1;         // warp-cooperative traversal of ordered batches: bit 0 closest point, bit 1 silhouette
-    int cone_filter = 3;    // silhouette normal-cone test: 0 = the reference's libm chain, 1 = guard-banded sine-space filter on
-                            // correctly rounded sqrt/rcp, 2 = the same filter on MUFU approximations, 3 = 2 with the exact chain out of
-                            // line (decisions identical in all modes; 3 measured 52.3 vs 54.6 ms on C3: a 1768- instead of
-                            // 3648-instruction kernel)
-    int sil_kernel = 1;     // silhouette per-lane kernel: 1 = warp-shared leaf queue + shared-memory stack (v4), 0 = per-lane parks (v3)
-    int sil_nodes = 0;      // v4 kernel walks 1 = the 64 B compact records when the scene was built with "build.compact_nodes" (48-bit cone
-                            // codes, exact cones fetched when undecided), 0 = the 96 B records.  Bit-identical results; measured SLOWER on
-                            // C3 (69.1 vs 54.0 ms): 3.4% of the coded tests are undecided, so 73% of warp steps take the exact detour
-    int sil_stats = 0;      // instrumented instantiation of the compact kernel: counters "query.sil_stats.0..7" (slow; analysis only)
-    int feed = 0;           // v4 silhouette kernel work distribution: 0 = one global chunk counter, 1 = a contiguous region of the ordered
-                            // batch per CTA, 2 = per SM (warps sharing an L1 walk neighbouring queries; dry regions are stolen from)
-    int sil_seed = 1;       // v4 silhouette kernel: queue the leaf that answered the lane's previous query as a pruning hint (results unchanged:
+    int sort_rays = 1;      // ray batches: 0 = caller's order, 1 = Morton order of the origins, 2 = direction octant, then origin
+    int cone_filter = 1;    // silhouette normal-cone test: 0 = the reference's libm chain verbatim, 1 = guard-banded sine-space filter on
+                            // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
+    int sil_seed = 1;       // silhouette: queue the leaf that answered the lane's previous query as a pruning hint (results unchanged:
                             // an unconfirmed hint makes the query walk again without one)
+    int sil_tail = 4;       // silhouette: once the batch is handed out, a warp with at most this many walking lanes finishes them
+                            // cooperatively, one query at a time on 32 lanes (0 = never)
     int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical
                             // path of pathological queries in batches too small to fill the machine; 0 = never)
     int wide_max_n_sil = 262144; // silhouette: the same for k_silhouette_wide (measured crossover 0.25-0.5M queries)
-    int seed = 1;           // closest point: bound each query by the triangle that answered the lane's previous query
+    int seed = 1;           // closest point: bit 0 = bound each query by the triangle that answered the lane's previous query;
+                            // bit 1 = switch the per-triangle lower bound OFF (A/B)
+    int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked), 0 = leaves tested inline (k_intersect)
+    int ray_flush = 8;      // k_intersect_parked: parked lanes of a warp that trigger the triangle tests
+    int ray_refill = 4;     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
                               // Measured on C3 (16.7M queries): 0 -> 60.5 ms, 8M -> 59.5, 4M -> 60.0, 2M -> 63.5, 1M -> 73.1: every extra
                               // launch pays its own tail and orders a sparser batch, so chunks stay large
 };
-// Launch accounting of the batched queries (snch_scene_counter): kernels launched, traversal kernels among them, and —
-// when "query.time_kernels" is set — device time of the traversal kernels alone (CUDA events on the launching stream).
+// Launch accounting of the batched queries (snch_scene_counter): kernels launched, traversal kernels among them, the name of
+// the last traversal kernel, and — when "query.time_kernels" is set — device time of the traversal kernels alone (one CUDA
+// event pair per launch on the launching stream, folded on demand: nothing in the launch path waits for an event).  Safe
+// for concurrent batches from several host threads / streams.
 struct QueryCounters
 {
-    uint64_t launches = 0, traversal_launches = 0;
+    std::atomic<uint64_t> launches{0}, traversal_launches{0};
+    std::atomic<int> time_kernels{0};
+    std::atomic<const char *> last_kernel{""};
+    std::mutex mu; // guards everything below
     double traversal_ms = 0.0;
-    int time_kernels = 0;
-    bool pending = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct Pair
+    {
+        cudaEvent_t a, b;
+    };
+    std::vector<Pair> pending, spare;
+    bool begin(Pair &p, cudaStream_t st);
+    void end(const Pair &p, cudaStream_t st);
     void fold();
+    void reset();
+    void release();
 };
 } // namespace snch
 
@@ -88,7 +96,6 @@ struct snch_scene
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0, opt_refit_only = 0;
-    int opt_compact_nodes = 0; // "build.compact_nodes": also emit the 64 B CNode records ("query.sil_nodes" = 1 walks them)
     int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds (v2), 0 = one climbing thread per leaf (v1)
 };
 
@@ -111,16 +118,16 @@ void free_adjacency(snch_scene *s);
 // build.cu
 void compute_adjacency_host(snch_scene *s);
 int build_device(snch_scene *s, cudaStream_t stream);
+void layout_arena(ArenaHeader &h, uint32_t nV, uint32_t nT, uint32_t nE);
 void resolve_view(snch_scene *s);
 int patch_pointers(snch_scene *s, cudaStream_t stream);
 
-int read_sil_stats(unsigned long long out[8], bool reset);
 // query.cu — n <= 2^32 - 2^20 per launch (the C-ABI splits larger batches); `scratch` has query_scratch_bytes(n) bytes
 uint64_t query_scratch_bytes(uint64_t n, const QueryTuning &t);
 int launch_closest(const SceneView &v, const QueryTuning &t, const float *q, uint64_t n, uint32_t *idx, float *dist, unsigned char *scratch,
                    cudaStream_t st, QueryCounters *qc);
 int launch_silhouette(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax, uint64_t n,
-                      float *dist, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
+                      float *dist, uint32_t *edge, float *point, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
 int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
                      uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc);
 int launch_sample(const SceneView &v, const QueryTuning &t, const float *sph, const float *rnd, uint64_t n, int32_t *idx, float *pdf,
@@ -133,6 +140,8 @@ struct WostBuffers
     const float *dirs, *rnd;
     uint32_t *closest_index;
     float *closest_distance, *silhouette_distance, *star_radius;
+    uint32_t *silhouette_edge;
+    float *silhouette_point;
     snch_hit *hits;
     uint8_t *found;
     int32_t *sample_index;

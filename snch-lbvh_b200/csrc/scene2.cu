@@ -52,7 +52,7 @@ struct __align__(32) L2
 {
     float p0x, p0y, p1x, p1y;
     uint32_t object, owned, pad0, pad1;
-    float vert[2][8]; // owned silhouette vertex: {x, y, n0.x, n0.y, n1.x, n1.y, face bits (bit 0: has_face(0), bit 1: has_face(1)), -}
+    float vert[2][8]; // owned silhouette vertex: {x, y, n0.x, n0.y, n1.x, n1.y, face bits (bit 0: has_face(0), bit 1: has_face(1)), vertex id bits}
 };
 static_assert(sizeof(N2) == 96 && sizeof(L2) == 96, "record sizes");
 
@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(128) k2_leaf_records(const SegT *__restrict__ 
         float *o = r.vert[cnt];
         o[0] = p.x, o[1] = p.y, o[2] = n0.x, o[3] = n0.y, o[4] = n1.x, o[5] = n1.y;
         o[6] = __uint_as_float((f0 ? 1u : 0u) | (f1 ? 2u : 0u));
+        o[7] = __int_as_float(owned[j]); // the silhouette vertex's id: what out_vertex of a silhouette query reports
         ++cnt;
     }
     r.owned = cnt;
@@ -254,7 +255,8 @@ SNCH_DI bool may_hold_silhouette2(const float *cone4, float2 o, const Box2 &box,
 }
 __global__ void __launch_bounds__(kQueryThreads)
     k2_silhouette(View2 v, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                  const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+                  const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_vertex,
+                  float *__restrict__ out_point, unsigned long long *counter)
 {
     const int lane = threadIdx.x & 31;
     Feeder fd{0u, 0u, false};
@@ -264,12 +266,16 @@ __global__ void __launch_bounds__(kQueryThreads)
     bool busy = false, flip = false, found = false;
     float best = INFINITY;
     uint32_t slot = kNone, node = kNone;
+    uint32_t best_vid = kNone; // the optional outputs: id of the silhouette vertex that attains `best`, and the vertex itself —
+    float2 best_pt = make_float2(0.f, 0.f); // `p` of silhouette_vertex::find_closest_silhouette_point (scene.cuh:354-356)
     // silhouette_distance_calculator over the owned vertices (scene.cuh:518-541, 345-378)
     auto test_leaf = [&](uint32_t k, uint32_t cnt)
     {
         float max_r2 = best * best;
         float d_found = INFINITY;
         bool ok = false;
+        uint32_t vid = kNone;
+        float2 vpt = make_float2(0.f, 0.f);
         for (uint32_t j = 0; j < cnt; ++j)
         {
             float4 a, b;
@@ -285,12 +291,16 @@ __global__ void __launch_bounds__(kQueryThreads)
                 d_found = d;
                 ok = true;
                 max_r2 = d * d;
+                vid = __float_as_uint(b.w);
+                vpt = make_float2(a.x, a.y);
             }
         }
         if (ok && d_found <= best)
         {
             best = d_found;
             found = true;
+            best_vid = vid;
+            best_pt = vpt;
         }
     };
     for (;;)
@@ -298,6 +308,12 @@ __global__ void __launch_bounds__(kQueryThreads)
         if (busy && node == kNone)
         {
             out_dist[slot] = found ? best : INFINITY;
+            if (out_vertex) out_vertex[slot] = found ? best_vid : kNone;
+            if (out_point)
+            {
+                out_point[2 * (uint64_t)slot] = found ? best_pt.x : 0.0f;
+                out_point[2 * (uint64_t)slot + 1] = found ? best_pt.y : 0.0f;
+            }
             busy = false;
         }
         const unsigned idle = __ballot_sync(kFull, !busy);
@@ -471,7 +487,8 @@ __global__ void __launch_bounds__(kQueryThreads)
 }
 __global__ void __launch_bounds__(kQueryThreads)
     k2_silhouette_wide(View2 v, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
-                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, unsigned long long *counter)
+                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_vertex,
+                       float *__restrict__ out_point, unsigned long long *counter)
 {
     __shared__ StackEntry s_st[kQueryThreads / 32][kWide2Stack];
     const int lane = threadIdx.x & 31;
@@ -490,6 +507,8 @@ __global__ void __launch_bounds__(kQueryThreads)
             const bool flip = flipv ? (__ldg(flipv + slot) != 0) : false;
             float best = rmax ? __ldg(rmax + slot) : INFINITY;
             bool found = false;
+            uint32_t best_vid = kNone, cvid = kNone; // c*: this lane's candidate of the current step
+            float2 best_pt = make_float2(0.f, 0.f), cpt = make_float2(0.f, 0.f);
             // silhouette_distance_calculator over the owned vertices of leaf k (scene.cuh:518-541, 345-378), bound = `bound`
             auto test_leaf = [&](uint32_t k, uint32_t cnt, float bound, uint32_t &cand)
             {
@@ -508,6 +527,8 @@ __global__ void __launch_bounds__(kQueryThreads)
                         max_r2 = d * d;
                         bound = d;
                         cand = __float_as_uint(d);
+                        cvid = __float_as_uint(b.w);
+                        cpt = make_float2(a.x, a.y);
                     }
                 }
             };
@@ -524,6 +545,8 @@ __global__ void __launch_bounds__(kQueryThreads)
                 {
                     best = __uint_as_float(cand);
                     found = true;
+                    best_vid = cvid;
+                    best_pt = cpt;
                 }
             }
             else
@@ -587,10 +610,22 @@ __global__ void __launch_bounds__(kQueryThreads)
                 {
                     best = __uint_as_float(mn);
                     found = true;
+                    const int wl = __ffs(__ballot_sync(kFull, cand == mn)) - 1;
+                    best_vid = __shfl_sync(kFull, cvid, wl);
+                    best_pt = make_float2(__shfl_sync(kFull, cpt.x, wl), __shfl_sync(kFull, cpt.y, wl));
                 }
                 __syncwarp();
             }
-            if (lane == 0) out_dist[slot] = found ? best : INFINITY;
+            if (lane == 0)
+            {
+                out_dist[slot] = found ? best : INFINITY;
+                if (out_vertex) out_vertex[slot] = found ? best_vid : kNone;
+                if (out_point)
+                {
+                    out_point[2 * (uint64_t)slot] = found ? best_pt.x : 0.0f;
+                    out_point[2 * (uint64_t)slot + 1] = found ? best_pt.y : 0.0f;
+                }
+            }
         }
     }
 }
@@ -1019,6 +1054,7 @@ extern "C" int snch_scene2_create(const float *xy, uint32_t n_verts, const int32
     if (!s) return SNCH_ERR_OOM;
     s->device = device;
     s->tuning.wide_max_n_sil = 131072; // "query.wide_max_n" of a 2-D scene
+    s->tuning.sort_rays = 0;           // 2-D ray batches keep the caller's order unless asked ("query.sort_rays")
     s->n_verts = n_verts;
     s->n_segs = n_segs;
     s->verts_h.resize(n_verts);
@@ -1294,7 +1330,7 @@ extern "C" int snch_closest_point_batch2(const snch_scene2 *s, const float *poin
     return sg.finish();
 }
 extern "C" int snch_closest_silhouette_batch2(const snch_scene2 *s, const float *points_xy, const uint8_t *flip, const float *r_max, uint64_t n,
-                                              float *out_distance, snch_stream stream)
+                                              float *out_distance, uint32_t *out_vertex, float *out_point_xy, snch_stream stream)
 {
     int rc = check_ready(s, n, "snch_closest_silhouette_batch2");
     if (rc != SNCH_OK) return rc;
@@ -1311,13 +1347,15 @@ extern "C" int snch_closest_silhouette_batch2(const snch_scene2 *s, const float 
     const uint8_t *fl = sg.in(flip, n);
     const float *rm = sg.in(r_max, n * 4);
     float *dist = sg.out(out_distance, n * 4);
+    uint32_t *vid = sg.out(out_vertex, n * 4);
+    float *pt = sg.out(out_point_xy, n * 8);
     if (sg.status != SNCH_OK) return sg.status;
     if (sg.mixed())
     {
         set_error("snch_closest_silhouette_batch2: host and device pointers mixed in one call");
         return SNCH_ERR_POINTER_KIND;
     }
-    if (s->n_segs == 0) k2_fill_empty<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, nullptr, dist, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (s->n_segs == 0) k2_fill_empty<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, vid, dist, nullptr, nullptr, nullptr, nullptr, pt);
     else
     {
         Scratch2 scr(st, s->pool, query_scratch_bytes(n, s->tuning));
@@ -1332,10 +1370,10 @@ extern "C" int snch_closest_silhouette_batch2(const snch_scene2 *s, const float 
         if (rc != SNCH_OK) return rc;
         if (n < (uint64_t)s->tuning.wide_max_n_sil)
             k2_silhouette_wide<<<persistent_grid(k2_silhouette_wide, s->tuning, (uint32_t)(n * 16)), kQueryThreads, 0, st>>>(s->view(), q, fl, rm, perm,
-                                                                                                                       (uint32_t)n, dist, counter);
+                                                                                                                       (uint32_t)n, dist, vid, pt, counter);
         else
             k2_silhouette<<<persistent_grid(k2_silhouette, s->tuning, (uint32_t)n), kQueryThreads, 0, st>>>(s->view(), q, fl, rm, perm, (uint32_t)n, dist,
-                                                                                                           counter);
+                                                                                                           vid, pt, counter);
     }
     return sg.finish();
 }

@@ -228,74 +228,6 @@ SNCH_DI Cone cone_merge(Cone ca, Cone cb, V3 oa, V3 ob, V3 on, bool *q1)
     return r;
 }
 
-// ---- compact normal cones (CNode, layout.h) ----------------------------------------------------------------------
-// 48 bits per cone: axis as a 2 x 12-bit octahedral code, half-angle in 12 bits over [0, pi/2), radius in 12 bits relative
-// to the child box (S = 4 x its largest half extent).  The codes are a FILTER input only: the encoder decodes what it wrote
-// with qcone_decode() — the very function the traversal uses — and measures the error; a cone whose decoded axis, angle or
-// radius misses the bounds below is marked kQExact and always answered from the exact SNode record.  The traversal widens
-// its guard band by those bounds, so a filter answer implies the same answer on the exact cone.
-constexpr uint32_t kQAlphaSteps = 4092;  // codes 0..4092: half-angle = code * (pi/2) / 4092
-constexpr uint32_t kQExact = 4093;       // codes do not meet the error bounds: use the exact record
-constexpr uint32_t kQWide = 4094;        // half_angle >= pi/2: the reference's test passes unconditionally (cone.cuh:176)
-constexpr uint32_t kQInvalid = 4095;     // invalid cone (half_angle < 0): the child is never entered (query.cuh:366)
-constexpr float kQAxisErr = 1.0e-3f;     // |axis' x axis| bound checked by the encoder: 8e-4
-constexpr float kQAlphaErr = 2.5e-4f;    // |alpha' - alpha| bound checked by the encoder: 2e-4
-constexpr float kQRadiusErr = 2.5e-4f;   // |r' - r| <= kQRadiusErr * S; checked by the encoder: 2e-4 * S
-struct QCone
-{
-    V3 axis;
-    float half_angle, radius;
-};
-SNCH_DI float qcone_scale(V3 lo, V3 hi) // S: exact in both encoder and decoder (same floats, same operations)
-{
-    return __fmul_rn(2.0f, fmaxf(fmaxf(__fsub_rn(hi.x, lo.x), __fsub_rn(hi.y, lo.y)), __fsub_rn(hi.z, lo.z)));
-}
-SNCH_DI QCone qcone_decode(uint32_t qx, uint32_t qy, uint32_t qa, uint32_t qr, float scale)
-{
-    QCone q;
-    float x = __fmaf_rn((float)qx, 2.0f / 4095.0f, -1.0f), y = __fmaf_rn((float)qy, 2.0f / 4095.0f, -1.0f);
-    const float z = __fsub_rn(__fsub_rn(1.0f, fabsf(x)), fabsf(y));
-    const float t = fmaxf(-z, 0.0f);
-    x = __fadd_rn(x, x >= 0.0f ? -t : t);
-    y = __fadd_rn(y, y >= 0.0f ? -t : t);
-    float n2 = __fmaf_rn(x, x, __fmaf_rn(y, y, __fmul_rn(z, z)));
-    float rn;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(n2));
-    q.axis = V3{__fmul_rn(x, rn), __fmul_rn(y, rn), __fmul_rn(z, rn)};
-    q.half_angle = __fmul_rn((float)qa, kHalfPi / (float)kQAlphaSteps);
-    q.radius = __fmul_rn(__fmul_rn((float)qr, 1.0f / 4095.0f), scale);
-    return q;
-}
-// returns the 48-bit code: bits 0-11 qx, 12-23 qy, 24-35 qa, 36-47 qr
-SNCH_DI uint64_t qcone_encode(Cone c, V3 lo, V3 hi)
-{
-    if (!(c.half_angle >= 0.0f)) return (uint64_t)kQInvalid << 24;
-    if (c.half_angle >= kHalfPi) return (uint64_t)kQWide << 24;
-    const uint64_t exact = (uint64_t)kQExact << 24;
-    const float scale = qcone_scale(lo, hi);
-    const float an = fabsf(c.axis.x) + fabsf(c.axis.y) + fabsf(c.axis.z);
-    if (!(an > 0.5f) || !(scale > 0.0f) || !(c.radius >= 0.0f) || !(c.radius <= scale)) return exact;
-    float ox = c.axis.x / an, oy = c.axis.y / an;
-    if (c.axis.z < 0.0f)
-    {
-        const float fx = (1.0f - fabsf(oy)) * (ox >= 0.0f ? 1.0f : -1.0f), fy = (1.0f - fabsf(ox)) * (oy >= 0.0f ? 1.0f : -1.0f);
-        ox = fx;
-        oy = fy;
-    }
-    const uint32_t qx = (uint32_t)fminf(fmaxf(rintf((ox + 1.0f) * 2047.5f), 0.0f), 4095.0f);
-    const uint32_t qy = (uint32_t)fminf(fmaxf(rintf((oy + 1.0f) * 2047.5f), 0.0f), 4095.0f);
-    const uint32_t qa = (uint32_t)fminf(rintf(c.half_angle * ((float)kQAlphaSteps / kHalfPi)), (float)kQAlphaSteps);
-    const uint32_t qr = (uint32_t)fminf(rintf(c.radius / scale * 4095.0f), 4095.0f);
-    const QCone d = qcone_decode(qx, qy, qa, qr, scale);
-    const V3 cr = cross(d.axis, c.axis);
-    const float al = len(c.axis);
-    if (!(fabsf(al - 1.0f) <= 1e-4f)) return exact; // the traversal assumes a unit axis when it bounds the error of axis . dir
-    if (!(len(cr) <= 8e-4f) || !(dot(d.axis, c.axis) > 0.0f)) return exact;
-    if (!(fabsf(d.half_angle - c.half_angle) <= 2e-4f)) return exact;
-    if (!(fabsf(d.radius - c.radius) <= 2e-4f * scale)) return exact;
-    return (uint64_t)qx | ((uint64_t)qy << 12) | ((uint64_t)qa << 24) | ((uint64_t)qr << 36);
-}
-
 // ---- primitives ----------------------------------------------------------------------------------------------------
 // scene.cuh:34-110 (Ericson RTCD 5.1.5); returns the distance (not squared), like the reference
 SNCH_DI float point_triangle_distance(V3 pa, V3 pb, V3 pc, V3 x)

@@ -74,8 +74,23 @@ __global__ void k_brute3(lbvh::bvh_device<float, 3, scene3::triangle> bvh, const
     dist[i] = best;
     t[i] = bt;
 }
+// element_intersects functor of query_device(bvh, line_intersect(l), f, out, cap): the infinite line through l.origin along l.dir
+// against one segment; data = the line parameter of the crossing (the reference leaves the functor to the caller, query.cuh:12-77)
+struct line_hits_segment
+{
+    __device__ thrust::pair<bool, float> operator()(const lbvh::line<float, 2> &l, const scene2::line_segment &s) const
+    {
+        const float2 a = s.vertices[s.vertex_indices.x], b = s.vertices[s.vertex_indices.y];
+        const float2 e = make_float2(b.x - a.x, b.y - a.y), w = make_float2(a.x - l.origin.x, a.y - l.origin.y);
+        const float den = l.dir.x * e.y - l.dir.y * e.x;
+        if (fabsf(den) < 1e-12f) return thrust::make_pair(false, 0.0f);
+        const float t = (w.x * e.y - w.y * e.x) / den, u = (w.x * l.dir.y - w.y * l.dir.x) / den;
+        return thrust::make_pair(u >= 0.0f && u <= 1.0f, t);
+    }
+};
 __global__ void k_queries2(lbvh::bvh_device<float, 2, scene2::line_segment> bvh, const float2 *q, const float2 *d, int n, float *dist, float *sil,
-                           float *t, float *bdist, float *bsil, float *bt, unsigned int *overlap_count, int *sidx)
+                           float *t, float *bdist, float *bsil, float *bt, unsigned int *overlap_count, int *sidx, unsigned int *line_count,
+                           unsigned int *line_brute)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -99,6 +114,13 @@ __global__ void k_queries2(lbvh::bvh_device<float, 2, scene2::line_segment> bvh,
     unsigned int buf[8];
     const lbvh::aabb<float, 2> box(make_float2(q[i].x + 0.05f, q[i].y + 0.05f), make_float2(q[i].x - 0.05f, q[i].y - 0.05f));
     overlap_count[i] = lbvh::query_device(bvh, lbvh::overlaps(box), buf, 8);
+    // every segment the infinite line through q[i] along d[i] crosses (query.cuh:12-77) vs the same functor over all segments
+    thrust::pair<unsigned int, float> lbuf[4];
+    const lbvh::line<float, 2> ln(q[i], d[i]);
+    line_count[i] = lbvh::query_device(bvh, lbvh::line_intersect(ln), line_hits_segment(), lbuf, 4);
+    unsigned int lb = 0;
+    for (unsigned int k = 0; k < bvh.num_objects; ++k) lb += line_hits_segment()(ln, bvh.objects[k]).first ? 1u : 0u;
+    line_brute[i] = lb;
     const auto s = lbvh::sample_object_in_sphere(bvh, lbvh::sphere_intersect(lbvh::sphere<float, 2>(q[i], 0.5f)), scene2::intersect_sphere(),
                                                  scene2::measurement_getter(), scene2::green_weight(), 0.37f);
     sidx[i] = s.first;
@@ -232,7 +254,11 @@ int main(int argc, char **argv)
     for (int i = 0; i < n; ++i) rnd[i] = make_float3(u[i], 0.3f, 0.4f);
     rnd3 = dev(rnd);
     sc.closest_points(dq, n, bi, bdist);
-    sc.closest_silhouettes(dq, nullptr, nullptr, n, bsil);
+    unsigned int *bedge;
+    float3 *bpoint;
+    CUDA_OK(cudaMalloc(&bedge, n * 4));
+    CUDA_OK(cudaMalloc(&bpoint, n * 12));
+    sc.closest_silhouettes(dq, nullptr, nullptr, n, bsil, nullptr, bedge, bpoint);
     sc.intersect(dq, dd, nullptr, n, bh, bf);
     sc.sample_in_spheres(dsph, rnd3, n, bsi, bpdf, nullptr);
     CUDA_OK(cudaDeviceSynchronize());
@@ -257,6 +283,23 @@ int main(int argc, char **argv)
     std::printf("CHECK closest_vs_batched_worst_rel %.3e\n", worst_rel(h_dist, b_dist));
     std::printf("CHECK closest_vs_brute_worst_rel %.3e\n", worst_rel(h_dist, brute_d));
     std::printf("CHECK silhouette_vs_batched_mismatch_frac %.3e\n", mismatch_frac(h_sil, b_sil, 1e-5));
+    { // out_edge / out_point: a valid edge id and a point at exactly the reported distance whenever the distance is finite
+        const auto h_edge = host(bedge, n);
+        const auto h_point = host(bpoint, n);
+        size_t bad = 0;
+        for (int i = 0; i < n; ++i)
+        {
+            if (std::isinf(b_sil[i]))
+            {
+                bad += h_edge[i] != 0xFFFFFFFFu;
+                continue;
+            }
+            const double dx = (double)q[i].x - h_point[i].x, dy = (double)q[i].y - h_point[i].y, dz = (double)q[i].z - h_point[i].z;
+            const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
+            bad += h_edge[i] >= sc.silhouettes_h.size() || std::fabs(len - b_sil[i]) > 1e-5 * b_sil[i] + 1e-6;
+        }
+        std::printf("CHECK silhouette_edge_point_bad %zu\n", bad);
+    }
     std::printf("CHECK ray_found_diff %zu\nCHECK anyhit_diff %zu\n", found_diff, anyhit_diff);
     std::printf("CHECK ray_t_vs_batched_mismatch_frac %.3e\n", mismatch_frac(h_t_inf, b_t, 1e-5));
     std::printf("CHECK ray_t_vs_brute_mismatch_frac %.3e\n", mismatch_frac(h_t_inf, brute_t, 1e-5));
@@ -316,12 +359,24 @@ int main(int argc, char **argv)
         float2 *dq2 = dev(q2), *dd2 = dev(d2);
         float *o[6];
         for (auto &p : o) CUDA_OK(cudaMalloc(&p, n2 * 4));
-        unsigned int *oc;
+        unsigned int *oc, *lc, *lbr;
         int *os;
         CUDA_OK(cudaMalloc(&oc, n2 * 4));
         CUDA_OK(cudaMalloc(&os, n2 * 4));
-        k_queries2<<<(n2 + 127) / 128, 128>>>(b2, dq2, dd2, n2, o[0], o[1], o[2], o[3], o[4], o[5], oc, os);
+        CUDA_OK(cudaMalloc(&lc, n2 * 4));
+        CUDA_OK(cudaMalloc(&lbr, n2 * 4));
+        k_queries2<<<(n2 + 127) / 128, 128>>>(b2, dq2, dd2, n2, o[0], o[1], o[2], o[3], o[4], o[5], oc, os, lc, lbr);
         CUDA_OK(cudaDeviceSynchronize());
+        {
+            const auto a = host(lc, n2), b = host(lbr, n2);
+            size_t diff = 0, total = 0;
+            for (int i = 0; i < n2; ++i)
+            {
+                diff += a[i] != b[i];
+                total += b[i];
+            }
+            std::printf("CHECK line2d_count_diff %zu\nCHECK line2d_crossings %zu\n", diff, total);
+        }
         std::printf("CHECK seg2d %u\n", b2.num_objects);
         std::printf("CHECK closest2d_vs_brute_worst_rel %.3e\n", worst_rel(host(o[0], n2), host(o[3], n2)));
         // the cone-pruned silhouette search may only ever miss what brute force finds if a cone test is wrong

@@ -25,7 +25,7 @@ def test_header_symbols_exported(pkg):
     missing = [s for s in declared if s not in exported]
     assert not missing, f"declared in snch_b200.h but not exported: {missing}"
     L = pkg.lib()
-    assert L.snch_abi_version() == 1
+    assert L.snch_abi_version() == 2
     for s in declared:
         assert hasattr(L, s)
 

@@ -39,7 +39,7 @@ def test_cpp_dropin_api(meshes, tmp_path, mesh):
     assert c["tris"] == len(f) and c["nodes"] == 2 * len(f) - 1
     # per-thread header traversals vs the batched kernels of the same scene, and vs brute force with the same functors
     assert c["closest_vs_batched_worst_rel"] <= 1e-5 and c["closest_vs_brute_worst_rel"] <= 1e-5
-    assert c["silhouette_vs_batched_mismatch_frac"] <= 1e-3
+    assert c["silhouette_vs_batched_mismatch_frac"] <= 1e-3 and c["silhouette_edge_point_bad"] == 0
     assert c["ray_found_diff"] <= 2e-4 * 20000 and c["anyhit_diff"] <= 2e-4 * 20000
     assert c["ray_t_vs_batched_mismatch_frac"] <= 2e-4 and c["ray_t_vs_brute_mismatch_frac"] <= 2e-4
     assert c["sample_idx_diff"] <= 1e-3 * 20000 and c["sample_pdf_mismatch_frac"] <= 2e-3
@@ -51,6 +51,8 @@ def test_cpp_dropin_api(meshes, tmp_path, mesh):
     assert c["closest2d_vs_brute_worst_rel"] <= 1e-5 and c["ray2d_vs_brute_mismatch_frac"] <= 1e-3
     assert c["silhouette2d_vs_brute_mismatch_frac"] <= 2e-2  # cone pruning is only approximately conservative in the reference too
     assert c["sample2d_hits"] > 0
+    # query_device(line_intersect): the BVH walk finds exactly the segments the functor accepts (a crossing lies inside the leaf box)
+    assert c["line2d_crossings"] > 5000 and c["line2d_count_diff"] <= 5
     # batched 2-D entry points (snch_*_batch2) == the per-thread header traversals of the same scene
     assert c["closest2d_vs_batched_worst_rel"] <= 1e-5
     assert c["silhouette2d_vs_batched_mismatch_frac"] <= 1e-3 and c["ray2d_vs_batched_mismatch_frac"] <= 1e-3

@@ -6,7 +6,7 @@ import pytest
 
 from conftest import small_cases
 from oracle import OracleScene
-from parity import bits, check_closest, check_rays, check_silhouette, rel_close
+from parity import bits, check_closest, check_rays, check_silhouette, check_silhouette_edges, rel_close
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -56,10 +56,23 @@ def test_closest_silhouette_star_radius(scene, meshes):
     assert np.array_equal(bits(dist), bits(np.where(unb <= rmax, unb, np.inf).astype(np.float32)))
 
 
+@pytest.mark.parametrize("flip", [False, True])
+def test_closest_silhouette_edge_and_point(scene, meshes, flip):
+    """out_edge / out_point of snch_closest_silhouette_batch (what the reference computes at scene.cuh:796-799 and drops),
+    unbounded and with star radii, against the oracle's silhouette_ex; asking for them never changes a distance."""
+    _, sc, orc, q, _ = scene
+    dist, edge, pt = sc.closest_silhouette(q, flip=flip, with_edge=True)
+    assert np.array_equal(bits(dist), bits(sc.closest_silhouette(q, flip=flip)))
+    check_silhouette_edges(q, dist, edge, pt, orc, flip)
+    rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(len(q))).astype(np.float32)
+    dist, edge, pt = sc.closest_silhouette(q, flip=flip, r_max=rmax, with_edge=True)
+    check_silhouette_edges(q, dist, edge, pt, orc, flip, r_max=rmax)
+
+
 def test_rays_closest_hit(scene):
     _, sc, orc, q, d = scene
     found, hits = sc.intersect(q, d)
-    both = check_rays(found, hits["t"], hits["prim"], q, d, None, orc)
+    both = check_rays(found, hits, q, d, None, orc)
     # the reported primitive really is hit at the reported t (ties between triangles sharing an edge are legal, Q4)
     f_b, t_b, _, _ = orc.ray(q[both], d[both], brute=True)
     assert rel_close(hits["t"][both], t_b).all()
@@ -72,10 +85,11 @@ def test_rays_tmax_and_any_hit(scene):
     _, sc, orc, q, d = scene
     tm = np.full(len(q), 0.7, np.float32)
     found, hits = sc.intersect(q, d, t_max=tm)
-    check_rays(found, hits["t"], hits["prim"], q, d, tm, orc)
+    check_rays(found, hits, q, d, tm, orc)
     assert np.all(hits["t"][found.astype(bool)] < 0.7)
     any_found, _ = sc.intersect(q, d, t_max=tm, any_hit=True)
-    assert np.mean(any_found.astype(bool) == found.astype(bool)) > 0.9998
+    assert np.array_equal(any_found.astype(bool), orc.ray(q, d, tm, any_hit=True, nthreads=8)[0].astype(bool))
+    assert np.mean(any_found.astype(bool) == found.astype(bool)) > 0.9998  # (any-hit stops at the first hit in walk order: Q4 ties aside, same flag)
 
 
 def test_sample_in_sphere(scene, meshes):
@@ -85,13 +99,12 @@ def test_sample_in_sphere(scene, meshes):
     rnd = meshes.uniforms(len(q), 3, seed=43)
     idx, pdf, pt = sc.sample_in_sphere(sph, rnd)
     idx_o, pdf_o = orc.sample(sph, rnd[:, 0].copy())
-    same = idx == idx_o
-    assert same.mean() > 0.999, f"sampled primitive differs on {np.count_nonzero(~same)} of {len(same)}"
-    hit = same & (idx >= 0)
-    assert rel_close(pdf[hit], pdf_o[hit], 2e-5).all()
+    assert np.array_equal(idx, idx_o), f"sampled primitive differs on {np.count_nonzero(idx != idx_o)} of {len(idx)}"  # one deterministic descent
+    hit = idx >= 0
+    assert np.array_equal(bits(pdf[hit]), bits(pdf_o[hit])), "sampling pdf differs"
     assert np.all(pdf[idx < 0] == 0)
     pt_o = orc.sample_on_object(idx, rnd[:, 1].copy(), rnd[:, 2].copy())
-    assert np.allclose(pt[idx >= 0], pt_o[idx >= 0], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(bits(pt[hit]), bits(pt_o[hit])), "sampled point differs"
 
 
 @pytest.mark.parametrize("name", ["tet", "ico2", "grid6", "torus24x16"])
@@ -101,15 +114,15 @@ def test_queries_match_golden(pkg, name):
     sc = pkg.Scene3(g["verts"], g["tris"]).compute_silhouettes().build_bvh()
     q, d = g["q"], g["d"]
     _, dist = sc.closest_point(q)
-    assert rel_close(dist, g["closest_dist"]).all()
-    check_silhouette(sc.closest_silhouette(q, flip=False), g["sil_noflip"], 5e-3)
-    check_silhouette(sc.closest_silhouette(q, flip=True), g["sil_flip"], 5e-3)
+    assert np.array_equal(bits(dist), bits(g["closest_dist"]))
+    check_silhouette(sc.closest_silhouette(q, flip=False), g["sil_noflip"])
+    check_silhouette(sc.closest_silhouette(q, flip=True), g["sil_flip"])
     found, hits = sc.intersect(q, d)
-    assert np.mean(found.astype(bool) == g["ray_found"].astype(bool)) >= 0.995
-    both = found.astype(bool) & g["ray_found"].astype(bool)
-    assert rel_close(hits["t"][both], g["ray_t"][both]).all()
+    assert np.array_equal(found.astype(bool), g["ray_found"].astype(bool))
+    both = found.astype(bool)
+    assert np.array_equal(bits(hits["t"][both]), bits(g["ray_t"][both]))
     idx, pdf, _ = sc.sample_in_sphere(g["sph"], np.stack([g["u"], g["u"], g["u"]], 1))
-    assert np.mean(idx == g["sample_idx"]) >= 0.995
+    assert np.array_equal(idx, g["sample_idx"])
 
 
 def test_edge_cases(pkg, meshes):
@@ -119,6 +132,8 @@ def test_edge_cases(pkg, meshes):
     idx, dist = sc.closest_point(q)
     assert np.all(idx == 0xFFFFFFFF) and np.all(np.isinf(dist))
     assert np.all(np.isinf(sc.closest_silhouette(q)))
+    sd, se, sp_ = sc.closest_silhouette(q, with_edge=True)
+    assert np.all(np.isinf(sd)) and np.all(se == 0xFFFFFFFF) and np.all(sp_ == 0)
     found, hits = sc.intersect(q, np.ones((5, 3), np.float32))
     assert not found.any() and np.all(np.isinf(hits["t"]))
     sidx, pdf, _ = sc.sample_in_sphere(np.ones((5, 4), np.float32), np.zeros((5, 3), np.float32))
@@ -135,7 +150,8 @@ def test_edge_cases(pkg, meshes):
     q = meshes.points_in_box(500, [-1, -1, -1], [2, 2, 1], 1.0, seed=44)
     idx, dist = sc.closest_point(q)
     assert np.all(idx == 0) and rel_close(dist, orc.closest(q)[1]).all()
-    assert rel_close(sc.closest_silhouette(q), orc.silhouette(q)).all()
+    assert np.array_equal(bits(sc.closest_silhouette(q)), bits(orc.silhouette(q)))
+    check_silhouette_edges(q, *sc.closest_silhouette(q, with_edge=True), orc)
     d = meshes.unit_directions(500, seed=45)
     found, hits = sc.intersect(q, d)
     f_o, t_o, _, _ = orc.ray(q, d)
@@ -146,7 +162,7 @@ def test_edge_cases(pkg, meshes):
     orc = OracleScene(v, f)
     q = np.concatenate([v[:200], v[:200] * 1000.0, np.zeros((1, 3), np.float32)]).astype(np.float32)
     check_closest(q, *sc.closest_point(q), orc)
-    check_silhouette(sc.closest_silhouette(q), orc.silhouette(q), 2e-2)
+    check_silhouette(sc.closest_silhouette(q), orc.silhouette(q))
     # axis-aligned rays (zero direction components -> infinite inverse directions)
     o = np.tile(np.array([[0.1, 0.2, -3.0]], np.float32), (4, 1))
     dd = np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, 1, 0]], np.float32)
@@ -168,6 +184,9 @@ def test_host_and_device_pointer_paths_agree(pkg, meshes):
     torch.cuda.synchronize()
     assert np.array_equal(ih, it.cpu().numpy().view(np.uint32)) and np.array_equal(bits(dh), bits(dt.cpu().numpy()))
     assert np.array_equal(bits(sc.closest_silhouette(q)), bits(sc.closest_silhouette(qd).cpu().numpy()))
+    (sdh, seh, sph_), (sdt, set_, spt) = sc.closest_silhouette(q, with_edge=True), sc.closest_silhouette(qd, with_edge=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(sdh), bits(sdt.cpu().numpy())) and np.array_equal(bits(sph_), bits(spt.cpu().numpy()))
     fh, hh = sc.intersect(q, d)
     ft, ht = sc.intersect(qd, dd)
     torch.cuda.synchronize()
@@ -178,9 +197,10 @@ def test_host_and_device_pointer_paths_agree(pkg, meshes):
 
 
 def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
-    """Query ordering, the guard-banded cone test, seeding and grid size only change scheduling: bit-identical results."""
+    """Query ordering, the guard-banded cone test, seeding, the tail hand-off, the ray kernel and grid size only change
+    scheduling: bit-identical results for every knob setting, and the defaults' results are the oracle's."""
     v, f = meshes.bumpy_torus(120, 90)
-    sc = pkg.Scene3(v, f).set_option("build.compact_nodes", 1).compute_silhouettes().build_bvh()  # for the "query.sil_nodes" variants
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
     orc = OracleScene(v, f)
     lo, hi = meshes.mesh_bounds(v)
     n = 60000
@@ -188,32 +208,51 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
     d = meshes.unit_directions(n, seed=49)
     flip = (np.arange(n) % 3 == 0).astype(np.uint8)
     rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(n)).astype(np.float32)
-    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 2, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.sil_nodes": 0, "query.host_chunk": 1 << 23, "query.feed": 0, "query.sort_radius": 0, "query.sil_seed": 1, "query.wide_max_n": 0, "query.wide_max_n_sil": 0}
+    # the baseline forces the per-lane / packet kernels (the wide ones would take a batch this small); variants re-enable them
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 1, "query.cone_filter": 1, "query.seed": 1,
+                "query.blocks_per_sm": 0, "query.host_chunk": 1 << 23, "query.sort_radius": 0, "query.sil_seed": 1, "query.sil_tail": 4,
+                "query.wide_max_n": 0, "query.wide_max_n_sil": 0, "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 4}
 
     def run():
         idx, dist = sc.closest_point(q)
         found, hits = sc.intersect(q, d)
         sidx, pdf, _ = sc.sample_in_sphere(np.concatenate([q, rmax[:, None] + 0.05], 1).astype(np.float32), meshes.uniforms(n, 3, seed=50))
-        return dict(dist=dist, sil=sc.closest_silhouette(q, flip=flip), silr=sc.closest_silhouette(q, r_max=rmax), found=found,
-                    t=hits["t"].copy(), sidx=sidx, pdf=pdf), idx
+        sile, edge, pt = sc.closest_silhouette(q, flip=flip, with_edge=True)
+        return dict(dist=dist, sil=sc.closest_silhouette(q, flip=flip), silr=sc.closest_silhouette(q, r_max=rmax), sile=sile, found=found,
+                    t=hits["t"].copy(), u=hits["u"].copy(), v=hits["v"].copy(), prim=hits["prim"].copy(), sidx=sidx, pdf=pdf), idx, edge, pt
 
-    base, idx0 = run()
+    for k, val in defaults.items():
+        sc.set_option(k, val)
+    base, idx0, edge0, pt0 = run()
     check_closest(q[:5000], idx0[:5000], base["dist"][:5000], orc)
+    assert np.array_equal(bits(base["sil"]), bits(base["sile"])), "asking for the edge changed a distance"
     for fl in (0, 1):  # per-query flip bytes: each subset must match the oracle run with that scalar flag
         sel = np.nonzero(flip[:6000] == fl)[0]
-        check_silhouette(base["sil"][sel], orc.silhouette(q[sel], bool(fl), nthreads=8), 2e-3)
-    for kv in ({"query.packet": 0}, {"query.packet": 3}, {"query.packet": 2, "query.cone_filter": 0}, {"query.packet": 0, "query.cone_filter": 0}, {"query.sort_min_n": 0}, {"query.cone_filter": 0}, {"query.cone_filter": 1}, {"query.sil_kernel": 0}, {"query.sil_kernel": 0, "query.cone_filter": 1}, {"query.sil_kernel": 0, "query.cone_filter": 0},
-               {"query.sil_kernel": 1, "query.sort_min_n": 0}, {"query.cone_filter": 3}, {"query.seed": 3}, {"query.seed": 2, "query.sort_min_n": 16384}, {"query.wide_max_n": 1 << 30}, {"query.wide_max_n_sil": 1 << 30}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 0}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 1, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.seed": 0}, {"query.sil_seed": 0}, {"query.sil_seed": 0, "query.sort_min_n": 0}, {"query.sil_seed": 0, "query.sil_nodes": 1}, {"query.cone_filter": 3, "query.sil_nodes": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.feed": 1}, {"query.feed": 2}, {"query.feed": 2, "query.cone_filter": 3, "query.sort_min_n": 0}, {"query.sil_nodes": 1}, {"query.sil_nodes": 1, "query.sort_min_n": 0}, {"query.seed": 0}, {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
-               {"query.host_chunk": 7001}, {"query.host_chunk": 0}, {"query.host_chunk": 500, "query.sort_min_n": 0},  # host-pointer pipeline
-               {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0}):
+        check_silhouette_edges(q[sel], base["sile"][sel], edge0[sel], pt0[sel], orc, bool(fl))
+    check_rays(base["found"][:5000], {k: base[k][:5000] for k in ("t", "u", "v", "prim")}, q[:5000], d[:5000], None, orc)
+    variants = [{"query.sort_min_n": 0}, {"query.cone_filter": 0}, {"query.cone_filter": 0, "query.sort_min_n": 0}, {"query.seed": 3}, {"query.seed": 2},
+                {"query.seed": 0}, {"query.wide_max_n": 1 << 30}, {"query.wide_max_n": 1 << 30, "query.sort_min_n": 0}, {"query.wide_max_n": 1 << 30, "query.seed": 0},
+                {"query.wide_max_n": 1 << 30, "query.seed": 3}, {"query.wide_max_n_sil": 1 << 30}, {"query.wide_max_n_sil": 1 << 30, "query.cone_filter": 0},
+                {"query.wide_max_n_sil": 1 << 30, "query.sort_min_n": 0}, {"query.sil_seed": 0}, {"query.sil_seed": 0, "query.sort_min_n": 0},
+                {"query.sil_tail": 0}, {"query.sil_tail": 31}, {"query.sil_tail": 31, "query.sil_seed": 0}, {"query.sil_tail": 31, "query.cone_filter": 0},
+                {"query.sil_tail": 16, "query.blocks_per_sm": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.sort_radius": 3},
+                {"query.sort_rays": 0}, {"query.sort_rays": 2}, {"query.ray_kernel": 0}, {"query.ray_kernel": 0, "query.sort_rays": 0},
+                {"query.ray_flush": 1, "query.ray_refill": 1}, {"query.ray_flush": 32, "query.ray_refill": 32}, {"query.ray_flush": 16, "query.sort_rays": 0},
+                {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
+                {"query.host_chunk": 7001}, {"query.host_chunk": 0}, {"query.host_chunk": 500, "query.sort_min_n": 0},  # host-pointer pipeline
+                {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0, "query.sil_seed": 0, "query.sil_tail": 0, "query.ray_kernel": 0}]
+    for kv in variants:
         for k, val in {**defaults, **kv}.items():
             sc.set_option(k, val)
-        other, idx1 = run()
+        other, idx1, edge1, pt1 = run()
         for k in base:
             a, b = base[k], other[k]
             assert np.array_equal(bits(a) if a.dtype == np.float32 else a, bits(b) if b.dtype == np.float32 else b), (kv, k)
-        # indices may differ only between triangles at the same distance (documented tie rule, Q3)
-        assert rel_close(orc.point_triangle_distance(q, idx1), base["dist"]).all(), kv
+        # indices may differ only between triangles / edges at the same distance (documented tie rule, Q3)
+        assert np.array_equal(bits(orc.point_triangle_distance(q, idx1)), bits(base["dist"])), kv
+        fin = np.isfinite(base["sile"])
+        d_at, p_at = orc.point_edge_distance(q[fin], edge1[fin].astype(np.int32))
+        assert np.array_equal(bits(d_at), bits(base["sile"][fin])) and np.array_equal(bits(p_at), bits(pt1[fin])), kv
     with pytest.raises(pkg.SnchError):
         sc.set_option("query.no_such_knob", 1)
 

@@ -40,11 +40,21 @@ def test_against_reference_cuda(pkg, meshes, name):
     _, dist = sc.closest_point(q)
     _, rdist = ref.closest(q)
     assert rel_close(dist, rdist).all()
-    # The reference's cone pruning is numerically chaotic at the 1e-3 level: its own CPU and CUDA builds (same headers,
-    # with/without FMA contraction) disagree on this fraction of queries because a borderline cone test flips and one
-    # side misses its closest silhouette (profiles/parity_report_*.json: refcpu_vs_refcuda_sil_frac).  Beyond those
-    # flips every distance agrees to 1e-5.
-    check_silhouette(sc.closest_silhouette(q), ref.silhouette(q), 5e-3)
+    # The reference's cone pruning is numerically chaotic: its own CPU and CUDA builds (same headers, without / with FMA
+    # contraction) disagree on a fraction of queries because a borderline cone test flips and one side misses its closest
+    # silhouette.  That fraction is MEASURED here — the reference's CPU build (oracle/_ref/libsnch_ref_cpu.so where it
+    # travelled, else the C oracle pinned bit-identical to it by tests/test_oracle_pinning.py) against its CUDA build on the
+    # same queries — and this library must not disagree with the CUDA build on more queries than that (+1e-4 of slack for the
+    # sample size); beyond those flips every distance agrees to 1e-5.
+    sil_ref_cuda = ref.silhouette(q)
+    if ref_available("cpu") and len(f) <= 200000:
+        sil_ref_cpu = RefScene(v, f, "cpu").silhouette(q)
+    else:
+        from oracle import OracleScene
+        sil_ref_cpu = OracleScene(v, f).silhouette(q, nthreads=8)
+    ref_vs_ref = 1.0 - rel_close(sil_ref_cpu, sil_ref_cuda).mean()
+    ours = check_silhouette(sc.closest_silhouette(q), sil_ref_cuda, ref_vs_ref + 1e-4)
+    print(f"{name}: silhouette mismatch vs reference CUDA {ours:.2e}; reference CPU vs reference CUDA {ref_vs_ref:.2e}")
     found, hits = sc.intersect(q, d)
     rf, rt, _, _ = ref.ray(q, d)
     assert np.mean(found.astype(bool) == rf.astype(bool)) > 0.9998

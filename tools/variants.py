@@ -30,7 +30,7 @@ def main():
     n = args.queries
     v, f = m.bumpy_torus(args.torus, args.torus)
     lo, hi = m.mesh_bounds(v)
-    sc = pkg.Scene3(v, f).set_option("build.compact_nodes", 1).compute_silhouettes().build_bvh()  # CNode records for the sil_nodes variants
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
     q = torch.from_numpy(m.points_in_box(n, lo, hi, 1.1, seed=2025)).cuda()
     d = torch.from_numpy(m.unit_directions(n, seed=77)).cuda()
     s = torch.from_numpy(m.star_radius_scale(n, seed=4242)).cuda()
@@ -52,10 +52,20 @@ def main():
             best = min(best, a.elapsed_time(b))
         return best, out
 
-    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.packet": 1, "query.cone_filter": 3, "query.seed": 1, "query.blocks_per_sm": 0, "query.sil_kernel": 1, "query.feed": 0, "query.sort_radius": 2, "query.sil_seed": 1, "query.sil_nodes": 0, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144}
-    settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("compact", {"query.sil_nodes": 1}), ("compact_unseeded", {"query.sil_nodes": 1, "query.sil_seed": 0}), ("sil_unseeded", {"query.sil_seed": 0}), ("radius_asc", {"query.sort_radius": 1}), ("radius_desc", {"query.sort_radius": 2}), ("radius_desc5", {"query.sort_radius": 3}), ("radius_desc6", {"query.sort_radius": 4}), ("radius_desc_bits30", {"query.sort_radius": 2, "query.sort_bits": 30}), ("sil_ool", {"query.cone_filter": 3}), ("feed_cta", {"query.feed": 1}), ("feed_sm", {"query.feed": 2}), ("ool_feed_cta", {"query.cone_filter": 3, "query.feed": 1}), ("ool_feed_sm", {"query.cone_filter": 3, "query.feed": 2}), ("sil_v3", {"query.sil_kernel": 0}), ("sil_v3_filter1", {"query.sil_kernel": 0, "query.cone_filter": 1}), ("sil_v4_filter1", {"query.cone_filter": 1}), ("sil_v4_bps7", {"query.blocks_per_sm": 7}), ("sil_v4_bps6", {"query.blocks_per_sm": 6}), ("no_packet", {"query.packet": 0}), ("packet_both", {"query.packet": 3}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
-                ("no_seed", {"query.seed": 0}), ("sort_bits_30", {"query.sort_bits": 30}), ("sort_bits_18", {"query.sort_bits": 18}),
-                ("no_sort_no_filter_no_seed", {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0})]
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 1, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0,
+                "query.sort_radius": 2, "query.sil_seed": 1, "query.sil_tail": 4, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
+                "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 4}
+    settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("no_seed", {"query.seed": 0}), ("sil_unseeded", {"query.sil_seed": 0}),
+                ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
+                ("sil_tail31", {"query.sil_tail": 31}), ("radius_none", {"query.sort_radius": 0}), ("radius_asc", {"query.sort_radius": 1}),
+                ("sil_bps7", {"query.blocks_per_sm": 7}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
+                ("ray_v1", {"query.ray_kernel": 0}), ("ray_v1_unsorted", {"query.ray_kernel": 0, "query.sort_rays": 0}), ("ray_unsorted", {"query.sort_rays": 0}),
+                ("ray_octant", {"query.sort_rays": 2}), ("ray_flush1", {"query.ray_flush": 1}), ("ray_flush4", {"query.ray_flush": 4}),
+                ("ray_flush12", {"query.ray_flush": 12}), ("ray_flush16", {"query.ray_flush": 16}), ("ray_flush24", {"query.ray_flush": 24}),
+                ("ray_refill1", {"query.ray_refill": 1}), ("ray_refill2", {"query.ray_refill": 2}), ("ray_refill8", {"query.ray_refill": 8}),
+                ("ray_refill16", {"query.ray_refill": 16}), ("ray_f4_r2", {"query.ray_flush": 4, "query.ray_refill": 2}),
+                ("ray_f16_r8", {"query.ray_flush": 16, "query.ray_refill": 8}), ("ray_bps8", {"query.blocks_per_sm": 8}), ("ray_bps6", {"query.blocks_per_sm": 6}),
+                ("sort_bits_30", {"query.sort_bits": 30}), ("sort_bits_18", {"query.sort_bits": 18})]
     if args.sets != "all":
         settings = [x for x in settings if x[0] in args.sets.split(",")]
     ref = {}
@@ -64,19 +74,32 @@ def main():
         for k, val in {**defaults, **kv}.items():
             sc.set_option(k, val)
         row = {}
-        t, (idx, dist) = timed(lambda: sc.closest_point(q))
-        row["closest_ms"], row["closest_mqps"] = t, n / t / 1e3
-        t, sb = timed(lambda: sc.closest_silhouette(q, r_max=rmax))
-        row["sil_bounded_ms"], row["sil_bounded_mqps"] = t, n / t / 1e3
-        t, su = timed(lambda: sc.closest_silhouette(q))
-        row["sil_unbounded_ms"], row["sil_unbounded_mqps"] = t, n / t / 1e3
-        t, (fd, hits) = timed(lambda: sc.intersect(q, d))
-        row["ray_ms"], row["ray_mqps"] = t, n / t / 1e3
-        t, (fa, _) = timed(lambda: sc.intersect(q, d, any_hit=True))
-        row["ray_any_ms"] = t
-        res = {"dist": dist, "sb": sb, "su": su, "t": hits[:, 0].contiguous(), "found": fd}
+        # a knob family only re-times the kernels it can affect
+        fam = "ray" if name.startswith("ray") else ("sil" if name.startswith(("sil", "radius", "no_cone")) else ("closest" if name in ("no_lower_bound", "no_seed") else "all"))
+        res = {}
+        if fam in ("all", "closest"):
+            t, (idx, dist) = timed(lambda: sc.closest_point(q))
+            row["closest_ms"], row["closest_mqps"] = t, n / t / 1e3
+            res["dist"] = dist
+        if fam in ("all", "sil"):
+            t, sb = timed(lambda: sc.closest_silhouette(q, r_max=rmax))
+            row["sil_bounded_ms"], row["sil_bounded_mqps"] = t, n / t / 1e3
+            t, su = timed(lambda: sc.closest_silhouette(q))
+            row["sil_unbounded_ms"], row["sil_unbounded_mqps"] = t, n / t / 1e3
+            res.update(sb=sb, su=su)
+            if name in ("default", "sil_tail0"):
+                t, (se, _, _) = timed(lambda: sc.closest_silhouette(q, r_max=rmax, with_edge=True))
+                row["sil_bounded_with_edge_ms"] = t
+                res["se"] = se
+        if fam in ("all", "ray"):
+            t, (fd, hits) = timed(lambda: sc.intersect(q, d))
+            row["ray_ms"], row["ray_mqps"] = t, n / t / 1e3
+            t, (fa, _) = timed(lambda: sc.intersect(q, d, any_hit=True))
+            row["ray_any_ms"] = t
+            res.update(t=hits[:, 0].contiguous(), found=fd)
         if not ref:
             ref = {k: x.clone() for k, x in res.items()}
+            ref["se"] = ref["sb"].clone()
         row["identical_to_default"] = {k: bool(torch.equal(ref[k].view(torch.int32) if ref[k].dtype == torch.float32 else ref[k],
                                                            x.view(torch.int32) if x.dtype == torch.float32 else x)) for k, x in res.items()}
         table[name] = row
