@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py — the headline measurement of the SNCH-LBVH hot path on B200.
 
-Workload (BASELINE.json config C3, the one the north_star target is quoted on): 16 777 216 nearest-silhouette queries
-with WoSt star radii (r_max = s * closest-point distance, s ~ U[0.5,4)) against the LBVH+SNCH of the 1 002 528-triangle
-synthetic "bumpy torus".  A step = one pass of that batch through the traversal kernel.
+Workload (BASELINE.json config C3, the one the north_star target is quoted on): ONE batch of 16 777 216 nearest-silhouette
+queries with WoSt star radii (r_max = s * closest-point distance, s ~ U[0.5,4)) against the LBVH+SNCH of the
+1 002 528-triangle synthetic "bumpy torus".  A step = one pass of that batch through ordering + traversal.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 * value  : M queries/s with queries and results resident in HBM (CUDA events on the launching stream, max over ranks)
-* e2e    : the same batch through the C-ABI with HOST buffers (H2D + kernel + D2H inside the timed region)
+* e2e    : the same batch through the C-ABI with HOST buffers (H2D + kernels + D2H inside the timed region), results
+           gathered into ONE host array
 * roofline / cpu_baseline / extra: see DESIGN.md "Measurement"
 * --impl reference: the CPU baseline arm (fcpw's CPU backend bundled with the reference, BASELINE.json north_star; the
   reference's own host query path is broken), on the box's host cores.
-N > 1: launched by torchrun, one rank per GPU; rank 0 builds, the arena is broadcast over NCCL, every rank traverses its
-own 16M-query shard (weak scaling), results stay per rank (e2e gathers them to the host).
+N > 1 (launched by torchrun, one rank per GPU): STRONG scaling — rank 0 builds the tree, the library broadcasts its arena
+over NVLink (snch_scene_broadcast: libnccl.so.2, timed cold and warm), the one batch is cut into contiguous shards
+(shard_range) and every rank traverses its shard against its own replica.  For e2e the batch and the result array live in
+host memory shared by the ranks (/dev/shm, page-locked in every rank): each rank copies its shard in, traverses, and copies
+its results straight into its slice of the one host array.  torch.distributed only bootstraps the communicator id, the
+barriers and the max-over-ranks of the timings.  Configs C1 / C4 / C5 are timed at the same N into `extra`.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import mmap
 import os
 import statistics
 import subprocess
@@ -116,43 +122,73 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(m, n, seed_shift=0):
+def make_inputs(m, n):
     v, f = m.bumpy_torus(TORUS, TORUS)
     lo, hi = m.mesh_bounds(v)
-    q = m.points_in_box(n, lo, hi, 1.1, seed=2025 + seed_shift)
-    s = m.star_radius_scale(n, seed=4242 + seed_shift)
+    q = m.points_in_box(n, lo, hi, 1.1, seed=2025)
+    s = m.star_radius_scale(n, seed=4242)
     return v, f, q, s
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU baseline (fcpw CPU backend; falls back to the oracle port if the prebuilt fcpw library did not travel)
+# CPU baselines (fcpw CPU backend; falls back to the oracle port if the prebuilt fcpw library did not travel)
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_silhouette_baseline(v, f, q, rmax, target_s=12.0, max_n=1 << 21):
+def _cpu_scene(v, f):
     from oracle import FcpwScene, OracleScene, ref_available
     ncores = os.cpu_count() or 1
     if ref_available("fcpw"):
         sc = FcpwScene(v, f)
-        kind, cores = "reference", sc.threads
+        return sc, "reference", sc.threads, "fcpw CPU backend (ext/fcpw, Bvh_SurfaceArea, Enoki 8-wide)"
+    return OracleScene(v, f), "port", ncores, "oracle/snch_oracle.c (reference algorithm restated in C), pthreads"
 
-        def run(a, b):
+
+def _bounded(run, n_total, target_s, max_n):
+    """run(a, b) -> seconds for queries [a, b); a calibration slice, then a sample sized for ~target_s of CPU work"""
+    n0 = min(20000, n_total)
+    t = run(0, n0)
+    n1 = int(min(max_n, n_total - n0, max(n0, n0 * target_s / max(t, 1e-6))))
+    return n1, run(n0, n0 + n1)
+
+
+def cpu_silhouette_baseline(v, f, q, rmax, target_s=12.0, max_n=1 << 21, scene=None):
+    sc, kind, cores, what = scene or _cpu_scene(v, f)
+
+    def run(a, b):
+        if kind == "reference":
             sc.silhouette(q[a:b], r_max=rmax[a:b])
             return sc.last_ms / 1e3
-        what = "fcpw CPU backend (ext/fcpw, Bvh_SurfaceArea, Enoki 8-wide), findClosestSilhouettePoints"
-    else:
-        sc = OracleScene(v, f)
-        kind, cores = "port", ncores
-
-        def run(a, b):
-            t0 = time.perf_counter()
-            sc.silhouette(q[a:b], r_max=rmax[a:b], nthreads=ncores)
-            return time.perf_counter() - t0
-        what = "oracle/snch_oracle.c (reference algorithm restated in C), pthreads"
-    n0 = min(20000, len(q))
-    t = run(0, n0)
-    n1 = int(min(max_n, len(q) - n0, max(n0, n0 * target_s / max(t, 1e-6))))
-    t1 = run(n0, n0 + n1)
+        t0 = time.perf_counter()
+        sc.silhouette(q[a:b], r_max=rmax[a:b], nthreads=cores)
+        return time.perf_counter() - t0
+    n1, t1 = _bounded(run, len(q), target_s, max_n)
     return {"value": n1 / t1 / 1e6, "unit": "M queries/s", "cores": int(cores), "kind": kind,
-            "sample": f"{n1} of the {len(q)} C3 queries (same mesh, same star radii), {what}"}
+            "sample": f"{n1} of the {len(q)} C3 queries (same mesh, same star radii), {what}, findClosestSilhouettePoints"}
+
+
+def cpu_other_baselines(v, f, q, d, scene, target_s=4.0):
+    """closest point and closest-hit rays on the C3 mesh and query points: same CPU library, bounded samples"""
+    sc, kind, cores, what = scene
+    out = {}
+
+    def run_c(a, b):
+        if kind == "reference":
+            sc.closest(q[a:b])
+            return sc.last_ms / 1e3
+        t0 = time.perf_counter()
+        sc.closest(q[a:b], nthreads=cores)
+        return time.perf_counter() - t0
+
+    def run_r(a, b):
+        if kind == "reference":
+            sc.ray(q[a:b], d[a:b])
+            return sc.last_ms / 1e3
+        t0 = time.perf_counter()
+        sc.ray(q[a:b], d[a:b], nthreads=cores)
+        return time.perf_counter() - t0
+    for name, run in (("closest", run_c), ("ray", run_r)):
+        n1, t1 = _bounded(run, len(q), target_s, 1 << 21)
+        out[name] = {"value": n1 / t1 / 1e6, "unit": "M queries/s", "cores": int(cores), "kind": kind, "sample": f"{n1} of the C3 query points, {what}"}
+    return out
 
 
 def run_reference_arm(args):
@@ -170,62 +206,231 @@ def run_reference_arm(args):
     rmax = (dcp * s).astype(np.float32)
     vals = []
     info = None
+    scene = _cpu_scene(v, f)
     for i in range(args.warmup + args.steps):
-        info = cpu_silhouette_baseline(v, f, q, rmax, target_s=6.0, max_n=1 << 20)
+        info = cpu_silhouette_baseline(v, f, q, rmax, target_s=6.0, max_n=1 << 20, scene=scene)
         if i >= args.warmup:
             vals.append(info["value"])
     val = statistics.median(vals)
     info["value"] = val
     line = {"impl": "reference", "metric": "M queries/sec (nearest-silhouette, star radii) @1M tris", "value": val, "unit": "M queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of the workload"},
             "cpu_baseline": info, "e2e": {"value": val, "unit": "M queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     return line
 
 
-def other_config(cfg, pkg, m, dev, stream):
-    """BASELINE.json configs C4 / C5 at their per-GPU share of the 8-GPU batch (one rank's shard: the tree is replicated,
-    so a rank's throughput does not depend on the other ranks).  Device-resident, CUDA events on `stream`."""
-    import torch
-    if cfg == "2d":
-        return scene2_config(pkg, m, dev, stream)
-    if cfg == "c1":
-        return c1_config(pkg, m, dev, stream)
-    nu, per_gpu = {"c4": (1416, (1 << 24) // 8), "c5": (2240, (1 << 26) // 8)}[cfg]
-    v, f = m.bumpy_torus(nu, nu)
+# ----------------------------------------------------------------------------------------------------------------
+# multi-rank helpers
+# ----------------------------------------------------------------------------------------------------------------
+class Job:
+    """rank / world / device of this process plus the three collectives the bench needs (barrier, max, broadcast of a few
+    floats) — torch.distributed when world > 1, nothing otherwise."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.dev = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: snch-lbvh_b200 has no CPU fallback")
+        torch.cuda.set_device(self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.dev}"))
+            self.dist = dist
+        self.comm = None
+
+    def barrier(self, stream=None):
+        if stream is not None:
+            stream.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        if self.dist is None:
+            return float(x)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=f"cuda:{self.dev}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+class SharedHost:
+    """A host array shared by the ranks of this node (a file in /dev/shm mapped by every rank and page-locked with
+    cudaHostRegister in every rank): the job's ONE input batch / ONE result array of the e2e measurement."""
+
+    def __init__(self, job, name, nbytes):
+        self.job, self.nbytes = job, int(nbytes)
+        self.path = f"/dev/shm/snch_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if job.world > 1 else os.getpid()}_{name}"
+        if job.rank == 0:
+            with open(self.path, "wb") as fh:
+                fh.truncate(self.nbytes)
+        job.barrier()
+        self.fh = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.fh.fileno(), self.nbytes)
+        self.u8 = np.frombuffer(self.mm, dtype=np.uint8)
+        self.ptr = self.u8.ctypes.data
+        rc = job.torch.cuda.cudart().cudaHostRegister(self.ptr, self.nbytes, 0)
+        if int(rc) != 0:
+            raise SystemExit(f"cudaHostRegister failed: {rc}")
+
+    def array(self, dtype, shape):
+        return self.u8.view(dtype).reshape(shape)
+
+    def close(self):
+        self.job.torch.cuda.cudart().cudaHostUnregister(self.ptr)
+        self.job.barrier()
+        if self.job.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def build_and_replicate(job, pkg, v, f):
+    """rank 0 builds; the arena reaches the other ranks through the library's own broadcast.  Returns (scene, info)."""
+    from snch_lbvh_b200 import distributed as sd
+    torch = job.torch
+    info = {}
     t0 = time.perf_counter()
-    sc = pkg.Scene3(v, f, device=dev).compute_silhouettes().build_bvh(stream=stream)
-    setup_ms = (time.perf_counter() - t0) * 1e3
-    st = sc.stats()
-    lo, hi = m.mesh_bounds(v)
-    out = {"triangles": int(st["num_objects"]), "queries_per_gpu": per_gpu, "build_ms": st["build_ms"], "adjacency_ms": st["adjacency_ms"],
-           "arena_bytes": st["arena_bytes"], "scene_setup_wall_ms": setup_ms}
-    q = torch.from_numpy(m.points_in_box(per_gpu, lo, hi, 1.1 if cfg == "c4" else 1.0, seed=31)).to(f"cuda:{dev}")
-    d = torch.from_numpy(m.unit_directions(per_gpu, seed=32)).to(f"cuda:{dev}")
+    scene = None
+    if job.rank == 0:
+        scene = pkg.Scene3(v, f, device=job.dev).compute_silhouettes().build_bvh()
+    torch.cuda.synchronize()
+    info["scene_setup_wall_ms"] = (time.perf_counter() - t0) * 1e3
+    if job.world == 1:
+        return scene, info
+    job.barrier()
+    t1 = time.perf_counter()
+    if job.comm is None:
+        job.comm = sd.make_comm(job.rank, job.world, job.dev, job.dist)  # ncclCommInitRank of the library's communicator
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    scene = job.comm.broadcast(scene if job.rank == 0 else None, root=0)
+    job.barrier()
+    t3 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream()
+    ev0.record(cur)
+    job.comm.rebroadcast(scene, root=0, stream=cur)  # warm: communicator, arenas and NVLink paths exist
+    ev1.record(cur)
+    job.barrier()
+    warm = job.max(ev0.elapsed_time(ev1))
+    nbytes = scene.stats()["arena_bytes"]
+    info.update(comm_init_ms=job.max((t2 - t1) * 1e3), replicate_cold_ms=job.max((t3 - t2) * 1e3), replicate_ms=warm,
+                replicate_gbs=nbytes / (warm * 1e-3) / 1e9, arena_bytes=nbytes,
+                replicate_note="snch_scene_broadcast (ncclBroadcast via libnccl.so.2, received in place); cold = first broadcast incl. arena "
+                               "allocation + pointer patch, replicate_ms = warm rebroadcast into the existing arenas (device time, max over ranks)")
+    return scene, info
 
-    def timed(fn, reps=5):
+
+def timed_steps(job, stream, fn, steps, warmup):
+    """warmup untimed calls, then `steps` calls bracketed by barriers; device time on `stream`, max over ranks -> ms per step"""
+    torch = job.torch
+    for _ in range(warmup):
         fn()
-        stream.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(reps):
-            fn()
-        b.record(stream)
-        stream.synchronize()
-        return a.elapsed_time(b) / reps
+    job.barrier(stream)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(steps):
+        fn()
+    b.record(stream)
+    job.barrier(stream)
+    return job.max(a.elapsed_time(b)) / steps
 
+
+def kernel_roofline(scene, kind, n_local, b_q, V, L, peak, peak_src, step_ms, note):
+    """roofline entry of the traversal kernel the library just ran: its name from the library, its time from the library's
+    own CUDA events around it (query.time_kernels), algorithmic bytes from the frozen must-visit counts"""
+    launches = max(int(scene.counter("query.traversal_launches")), 1)
+    kernel_ms = scene.counter("query.traversal_ms") / launches
+    achieved = b_q * n_local / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": scene.last_kernel(), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_ms if step_ms else None,
+            "algorithmic_bytes_per_query": b_q, "must_visit_internal": V, "must_visit_leaves": L, "queries_per_launch": n_local,
+            "peak_source": peak_src, "kind": kind, "note": note}
+
+
+def attach_traffic(roof):
+    """dram bytes per launch of that kernel from the last committed `ncu --set full` capture (profiles/traffic.json), scaled to
+    this launch's query count when the capture was taken on another batch size"""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not roof or not os.path.exists(tp):
+        return
+    tj = json.load(open(tp))
+    base = roof["kernel"].split("<")[0]
+    ent = tj.get(base)
+    if isinstance(ent, dict) and ent.get("queries"):
+        roof["traffic"] = ent["dram_bytes"] * roof["queries_per_launch"] / ent["queries"]
+        roof["traffic_source"] = ent.get("source")
+        roof["l1_sectors_per_query"] = ent.get("l1_global_load_sectors_per_query")
+    elif base + "_bytes_per_launch" in tj:
+        roof["traffic"] = tj[base + "_bytes_per_launch"]
+        roof["traffic_source"] = tj.get("source")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, at the same N, into `extra`
+# ----------------------------------------------------------------------------------------------------------------
+def other_config(cfg, job, pkg, m, stream, peak, mv):
+    """C4: 16 777 216 closest-hit rays on the 4 010 112-triangle torus; C5: one wavefront WoSt step of 67 108 864 walkers on the
+    10 035 200-triangle torus.  ONE batch sharded over the N ranks (strong scaling), device-resident, max over ranks."""
+    torch = job.torch
+    if cfg == "2d":
+        return scene2_config(pkg, m, job.dev, stream) if job.rank == 0 else None
+    if cfg == "c1":
+        return c1_config(pkg, m, job.dev, stream) if job.rank == 0 else None
+    from snch_lbvh_b200.distributed import shard_range
+    nu, total = {"c4": (1416, 1 << 24), "c5": (2240, 1 << 26)}[cfg]
+    v = f = None
+    if job.rank == 0:
+        v, f = m.bumpy_torus(nu, nu)
+    scene, info = build_and_replicate(job, pkg, v, f)
+    st = scene.stats()
+    lo, hi = np.array(st["scene_lower"], np.float32), np.array(st["scene_upper"], np.float32)  # (padded by 1 ulp: irrelevant for query generation)
+    a, b = shard_range(total, job.rank, job.world)
+    n = b - a
+    out = {"triangles": int(st["num_objects"]), "queries_total": total, "queries_this_rank": n, "arena_bytes": st["arena_bytes"]}
+    out.update(info)
+    if job.rank == 0:
+        out.update(build_ms=st["build_ms"], adjacency_ms=st["adjacency_ms"])
+    dev = f"cuda:{job.dev}"
+    q = torch.from_numpy(m.points_in_box(n, lo, hi, 1.1 if cfg == "c4" else 1.0, seed=31 + job.rank)).to(dev)
+    d = torch.from_numpy(m.unit_directions(n, seed=131 + job.rank)).to(dev)
+    scene.set_option("query.time_kernels", 1)
     with torch.cuda.stream(stream):
         if cfg == "c4":
-            ms = timed(lambda: sc.intersect(q, d, stream=stream))
-            out.update(workload="C4 shard: closest-hit rays, t_max = inf", ms_per_step=ms, ray_mqps=per_gpu / ms / 1e3)
+            ms = timed_steps(job, stream, lambda: scene.intersect(q, d, stream=stream), 5, 2)
+            scene.counter("query.traversal_ms", reset=True)
+            scene.intersect(q, d, stream=stream)
+            stream.synchronize()
+            out.update(workload="C4: closest-hit rays, t_max = inf, origins in the bounding box x 1.1, uniform directions", ms_per_step=ms,
+                       ray_mqps=total / ms / 1e3)
+            e = (mv or {}).get("torus1416", {}).get("ray")
+            if e:
+                b_q = 12 + 12 + 16 + 1 + 64.0 * e["V"] + 64.0 * e["L"]
+                out["roofline"] = kernel_roofline(scene, "ray", n, b_q, e["V"], e["L"], peak, "measured", ms,
+                                                  "B_q = 41 B of ray in / hit out + 64 B per must-visit node + 64 B per must-test triangle")
         else:
-            u = torch.from_numpy(m.uniforms(per_gpu, 3, seed=33)).to(f"cuda:{dev}")
-            ms = timed(lambda: sc.wost_step(q, d, u, stream=stream), reps=3)
-            out.update(workload="C5 shard: one wavefront WoSt step per walker = closest point + silhouette (r_max = d) + ray (t_max = star "
-                                "radius) + sample-in-sphere, fused in snch_wost_step_batch",
-                       ms_per_step=ms, walker_steps_mqps=per_gpu / ms / 1e3, queries_mqps=4 * per_gpu / ms / 1e3)
-    del sc
+            u = torch.from_numpy(m.uniforms(n, 3, seed=231 + job.rank)).to(dev)
+            ms = timed_steps(job, stream, lambda: scene.wost_step(q, d, u, stream=stream), 2, 1)
+            out.update(workload="C5: one wavefront WoSt step per walker = closest point + silhouette (r_max = d) + ray (t_max = star radius) + "
+                                "sample-in-sphere, fused in snch_wost_step_batch",
+                       ms_per_step=ms, walker_steps_mqps=total / ms / 1e3, queries_mqps=4 * total / ms / 1e3)
+    scene.set_option("query.time_kernels", 0)
+    del scene, q, d
     torch.cuda.empty_cache()
     return out
 
@@ -271,6 +476,7 @@ def c1_config(pkg, m, dev, stream):
             for _ in range(10):
                 fn()
             out[f"{k}_kernel_ms"] = sc.counter("query.traversal_ms", reset=True) / 10
+            out[f"{k}_kernel"] = sc.last_kernel()
     sc.set_option("query.time_kernels", 0)
     out["note"] = "x_ms = whole call (ordering + kernels + per-call host overhead, back to back); x_kernel_ms = traversal kernel alone"
     try:
@@ -283,6 +489,7 @@ def c1_config(pkg, m, dev, stream):
                 fn()
                 rc[name] = ref.last_ms  # the traversal kernel alone (CUDA events inside the wrapper)
             out["reference_cuda"] = rc
+            out["ray_kernel_speedup_vs_reference_cuda"] = rc["ray_ms"] / out["ray_kernel_ms"]
     except Exception as ex:
         out["reference_cuda_error"] = repr(ex)
     del sc
@@ -372,10 +579,11 @@ def _run():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--queries", type=int, default=N_QUERIES, help="queries per GPU per step (default: the C3 batch)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (closest/ray/build/reference CUDA)")
-    ap.add_argument("--also", default="", help="comma list of further configs to time into `extra` on rank 0 (c1, c4, c5 of BASELINE.json; 2d = the scene<2> path): "
-                    "c4 (16M rays / 8 GPUs on a 4M-triangle mesh), c5 (wavefront WoSt step, 64M walkers / 8 GPUs on a 10M-triangle mesh)")
+    ap.add_argument("--queries", type=int, default=N_QUERIES, help="queries of the ONE batch all ranks share (default: the C3 batch)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (closest/ray/build/reference CUDA, C1/C4/C5)")
+    ap.add_argument("--configs", default="c1,c4,c5", help="comma list of further BASELINE.json configs timed into `extra` at the same N "
+                    "(c1, c4, c5; 2d = the scene<2> path); '' = none")
+    ap.add_argument("--also", default="", help="more configs on top of --configs (kept for the round scripts)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -383,61 +591,41 @@ def _run():
 
     import torch
     import snch_lbvh_b200 as pkg
-    from snch_lbvh_b200 import distributed as sd  # noqa: F401  (import through the shim)
+    from snch_lbvh_b200.distributed import shard_range
     m = pkg.meshes
+    job = Job()
+    world, rank, dev = job.world, job.rank, job.dev
+    n_total = args.queries
+    lo_i, hi_i = shard_range(n_total, rank, world)
+    n = hi_i - lo_i
+    peak, peak_src = load_peaks()
+    mvp = os.path.join(ROOT, "profiles", "must_visit.json")
+    mv = json.load(open(mvp))["configs"] if os.path.exists(mvp) else {}
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: snch-lbvh_b200 has no CPU fallback")
-    dev = local_rank
-    torch.cuda.set_device(dev)
-    n = args.queries
-
-    # ---- scene: built on rank 0, replicated by broadcasting the arena -----------------------------------------------
-    v, f, q_h, s_h = make_inputs(m, n, seed_shift=rank)
-    t0 = time.perf_counter()
-    scene = None
-    if rank == 0:
-        scene = pkg.Scene3(v, f, device=dev).compute_silhouettes().build_bvh()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    scene = sd.replicate_scene(scene, rank, world, dev, dist)
-    torch.cuda.synchronize()
-    replicate_ms = (time.perf_counter() - t1) * 1e3
+    # ---- scene: built on rank 0, replicated by the library's broadcast; the ONE batch: every rank derives it from the same seed
+    v, f, q_all, s_all = make_inputs(m, n_total)
+    scene, rep_info = build_and_replicate(job, pkg, v if rank == 0 else None, f if rank == 0 else None)
     stats = scene.stats()
     for kv in filter(None, os.environ.get("SNCH_OPTIONS", "").replace(",", " ").split()):  # diagnostic runs only (tools/gpu_exp.sh)
         k, val = kv.split("=")
         scene.set_option(k, int(val))
+    q_h, s_h = q_all[lo_i:hi_i], s_all[lo_i:hi_i]
 
     stream = torch.cuda.Stream(device=dev)
+    L = pkg.lib()
     with torch.cuda.stream(stream):
         q_d = torch.from_numpy(q_h).to(f"cuda:{dev}")
         _, dcp = scene.closest_point(q_d, stream=stream)  # WoSt: the star radius derives from the closest-point distance
         rmax_d = (dcp * torch.from_numpy(s_h).to(f"cuda:{dev}")).contiguous()
         out_d = torch.empty(n, dtype=torch.float32, device=f"cuda:{dev}")
-        L = pkg.lib()
 
         def step_device():
             st = L.snch_closest_silhouette_batch(scene._h, q_d.data_ptr(), None, rmax_d.data_ptr(), n, out_d.data_ptr(), None, None, stream.cuda_stream)
             assert st == 0, L.snch_last_error()
 
-        def barrier():
-            stream.synchronize()
-            if dist is not None:
-                dist.barrier()
-            torch.cuda.synchronize()
-
         for _ in range(args.warmup):
             step_device()
-        barrier()
+        job.barrier(stream)
         scene.set_option("query.time_kernels", 1)  # CUDA events around the traversal kernel itself, on `stream` (roofline.achieved)
         scene.counter("query.launches", reset=True)
         sampler = ClockSampler(dev)
@@ -448,32 +636,43 @@ def _run():
         for k in range(args.steps):
             step_device()
             evs[k + 1].record(stream)
-        barrier()
+        job.barrier(stream)
         launches = int(scene.counter("query.launches"))
-        trav_launches = int(scene.counter("query.traversal_launches"))
-        trav_ms = scene.counter("query.traversal_ms", reset=True)
-        scene.set_option("query.time_kernels", 0)
         clocks = sampler.stop() if rank == 0 else None
         step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
-        total_ms = evs[0].elapsed_time(evs[-1])
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{dev}")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms_max = float(tt.item())
+        total_ms_max = job.max(evs[0].elapsed_time(evs[-1]))
+        ms_per_step = total_ms_max / args.steps
+        roofline = None
+        e = mv.get("torus708", {}).get("silhouette_star_radius")
+        if e and n_total == N_QUERIES:
+            b_q = 12 + 4 + 4 + 64.0 * e["V"] + 192.0 * e["L"]  # B_q = IO_q + 64*V* + P*L*, P = 3 edges x 64 B; flip omitted (NULL)
+            roofline = kernel_roofline(scene, "silhouette_star_radius", n, b_q, e["V"], e["L"], peak, peak_src, statistics.mean(step_ms),
+                                       "divergent gather over SNode 96 MB + LEdge 96 MB; the kernel is issue/L1-bound, not DRAM-bound: traffic << "
+                                       "algorithmic bytes because records are re-read from L1/L2 (hit rates in profiles/)")
+            attach_traffic(roofline)
+        scene.counter("query.traversal_ms", reset=True)
+        scene.set_option("query.time_kernels", 0)
         finite_frac = float(torch.isfinite(out_d).float().mean().item())
 
-        # ---- e2e: HOST buffers through the C-ABI (H2D + kernel + D2H every step) ----------------------------------------
-        q_p = torch.from_numpy(q_h).pin_memory()
-        r_p = rmax_d.cpu().pin_memory()
-        o_p = torch.empty(n, dtype=torch.float32).pin_memory()
+        # ---- e2e: the batch and the results live in HOST memory shared by the ranks; every step each rank moves its shard
+        # H2D, traverses, and moves its results D2H into its slice of the one result array (snch_closest_silhouette_batch
+        # with host pointers).  Timed per rank as max(CUDA events on `stream`, host wall clock) — the call blocks until the
+        # results are in host memory — then max over ranks.
+        sh_q = SharedHost(job, "q", n_total * 12)
+        sh_r = SharedHost(job, "r", n_total * 4)
+        sh_o = SharedHost(job, "o", n_total * 4)
+        sh_q.array(np.float32, (n_total, 3))[lo_i:hi_i] = q_h
+        sh_r.array(np.float32, (n_total,))[lo_i:hi_i] = rmax_d.cpu().numpy()
+        job.barrier(stream)
+        qp, rp, op = sh_q.ptr + lo_i * 12, sh_r.ptr + lo_i * 4, sh_o.ptr + lo_i * 4
 
         def step_host():
-            st = L.snch_closest_silhouette_batch(scene._h, q_p.data_ptr(), None, r_p.data_ptr(), n, o_p.data_ptr(), None, None, stream.cuda_stream)
+            st = L.snch_closest_silhouette_batch(scene._h, qp, None, rp, n, op, None, None, stream.cuda_stream)
             assert st == 0, L.snch_last_error()
 
         for _ in range(2):
             step_host()
-        barrier()
+        job.barrier(stream)
         e2e_steps = max(3, min(args.steps, 10))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -481,51 +680,42 @@ def _run():
         for _ in range(e2e_steps):
             step_host()  # synchronises the stream before returning (results are on the host)
         e1.record(stream)
-        barrier()
-        e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - w0) * 1e3 * 0.0)  # device clock; host wall only as a floor guard
-        et = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{dev}")
-        if dist is not None:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e2e_ms_max = float(et.item())
-        assert np.array_equal(o_p.numpy().view(np.uint32), out_d.cpu().numpy().view(np.uint32)), "host path != device path"
+        stream.synchronize()
+        wall_ms = (time.perf_counter() - w0) * 1e3
+        job.barrier(stream)
+        e2e_event_ms, e2e_wall_ms = job.max(e0.elapsed_time(e1)), job.max(wall_ms)
+        e2e_ms_max = max(e2e_event_ms, e2e_wall_ms)
+        got = sh_o.array(np.float32, (n_total,))[lo_i:hi_i]
+        assert np.array_equal(got.view(np.uint32), out_d.cpu().numpy().view(np.uint32)), "host path != device path"
+        job.barrier(stream)
+        gathered_finite = float(np.isfinite(sh_o.array(np.float32, (n_total,))).mean()) if rank == 0 else None
+        del got
+        for sh in (sh_q, sh_r, sh_o):
+            sh.close()
 
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return None
+        # ---- weak-scaling companion (round 1's number): every rank runs a FULL 16.7M batch of its own
+        weak = None
+        if world > 1 and not args.no_extra:
+            qw = torch.from_numpy(m.points_in_box(n_total, *m.mesh_bounds(v), 1.1, seed=2025 + rank)).to(f"cuda:{dev}")
+            _, dw = scene.closest_point(qw, stream=stream)
+            rw = (dw * torch.from_numpy(s_all).to(f"cuda:{dev}")).contiguous()
+            ow = torch.empty(n_total, dtype=torch.float32, device=f"cuda:{dev}")
+            ms_w = timed_steps(job, stream, lambda: L.snch_closest_silhouette_batch(scene._h, qw.data_ptr(), None, rw.data_ptr(), n_total, ow.data_ptr(),
+                                                                                   None, None, stream.cuda_stream), 5, 2)
+            weak = {"queries_per_gpu": n_total, "ms_per_step": ms_w, "mqps": world * n_total / ms_w / 1e3}
+            del qw, rw, ow, dw
 
-    # ---- rank 0: roofline, secondary numbers, CPU baseline ------------------------------------------------------------
-    ms_per_step = total_ms_max / args.steps
-    value = world * n / (ms_per_step * 1e-3) / 1e6
-    peak, peak_src = load_peaks()
-    mv = None
-    mvp = os.path.join(ROOT, "profiles", "must_visit.json")
-    if os.path.exists(mvp):
-        mv = json.load(open(mvp))["configs"].get("torus708")
-    roofline = None
-    if mv is not None and n == N_QUERIES:
-        V, Lv = mv["silhouette_star_radius"]["V"], mv["silhouette_star_radius"]["L"]
-        io_q = 12 + 4 + 4                       # point + r_max in, distance out (flip omitted: NULL)
-        b_q = io_q + 64.0 * V + 192.0 * Lv      # B_q = IO_q + 64*V* + P*L*, P = 3 edges x 64 B
-        kernel_ms = trav_ms / max(trav_launches, 1)  # the traversal kernel alone (CUDA events on its stream, inside the timed region)
-        achieved = b_q * n / (kernel_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "snch::k_silhouette_coop<3, 0, 0, 1>", "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / statistics.mean(step_ms),
-                    "algorithmic_bytes_per_query": b_q, "must_visit_internal": V, "must_visit_leaves": Lv,
-                    "peak_source": peak_src,
-                    "note": "divergent gather over SNode 96 MB + LEdge 96 MB; the kernel is issue/L1-bound, not DRAM-bound: traffic << algorithmic "
-                            "bytes because records are re-read from L1/L2 (hit rates in profiles/)"}
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            roofline["traffic"] = tj.get("k_silhouette_coop_bytes_per_launch", tj.get("k_silhouette_bytes_per_launch"))
-
-    extra = {"build_ms": stats["build_ms"], "adjacency_ms": stats["adjacency_ms"], "arena_bytes": stats["arena_bytes"],
-             "replicate_ms": replicate_ms if world > 1 else 0.0, "scene_setup_wall_ms": (t1 - t0) * 1e3,
-             "finite_fraction": finite_frac, "step_ms_min": min(step_ms), "step_ms_max": max(step_ms)}
+    extra = {"build_ms": stats["build_ms"] if rank == 0 else None, "arena_bytes": stats["arena_bytes"], "finite_fraction": finite_frac,
+             "gathered_finite_fraction": gathered_finite, "step_ms_min": min(step_ms), "step_ms_max": max(step_ms),
+             "e2e_event_ms_per_step": e2e_event_ms / e2e_steps, "e2e_wall_ms_per_step": e2e_wall_ms / e2e_steps}
+    extra.update(rep_info)
+    if world == 1:
+        extra["replicate_ms"] = 0.0
+    if weak:
+        extra["weak_scaling"] = weak
     cpu_base = None
     if not args.no_extra:
+        # ---- per-kind throughput of THIS rank's shard on the C3 mesh, each with its own roofline entry (rank 0 reports)
         with torch.cuda.stream(stream):
             def timed(fn, reps=5):
                 fn()
@@ -537,74 +727,119 @@ def _run():
                 b.record(stream)
                 stream.synchronize()
                 return a.elapsed_time(b) / reps
-            d_d = torch.from_numpy(m.unit_directions(n, seed=77)).to(f"cuda:{dev}")
-            extra["closest_mqps"] = n / timed(lambda: scene.closest_point(q_d, stream=stream)) / 1e3
-            extra["silhouette_unbounded_mqps"] = n / timed(lambda: scene.closest_silhouette(q_d, stream=stream)) / 1e3
-            extra["ray_mqps"] = n / timed(lambda: scene.intersect(q_d, d_d, stream=stream)) / 1e3
+            d_h = m.unit_directions(n_total, seed=77)[lo_i:hi_i]
+            d_d = torch.from_numpy(d_h).to(f"cuda:{dev}")
+            scene.set_option("query.time_kernels", 1)
+            per_kind = {}
+            scene.counter("query.traversal_ms", reset=True)
+            t = timed(lambda: scene.closest_point(q_d, stream=stream))
+            per_kind["closest"] = t
+            e = mv.get("torus708", {}).get("closest")
+            if e:
+                extra["roofline_closest"] = kernel_roofline(
+                    scene, "closest", n, 12 + 8 + 64.0 * e["V"] + 64.0 * e["L"], e["V"], e["L"], peak, peak_src, t,
+                    "per-QUERY must-visit bytes: a 32-query packet fetches a node ONCE for all its lanes, so bytes actually requested per query are far "
+                    "lower (profiles/*ncu*closest*: L1 sectors per query) and this fraction can exceed 1; it is the contract's figure, not a bound")
+                attach_traffic(extra["roofline_closest"])
+            scene.counter("query.traversal_ms", reset=True)
+            per_kind["silhouette_unbounded"] = timed(lambda: scene.closest_silhouette(q_d, stream=stream))
+            per_kind["silhouette_star_radius_with_edge_and_point"] = timed(lambda: scene.closest_silhouette(q_d, r_max=rmax_d, stream=stream, with_edge=True))
+            scene.counter("query.traversal_ms", reset=True)
+            t = timed(lambda: scene.intersect(q_d, d_d, stream=stream))
+            per_kind["ray"] = t
+            e = mv.get("torus708", {}).get("ray")
+            if e:
+                extra["roofline_ray"] = kernel_roofline(scene, "ray", n, 12 + 12 + 16 + 1 + 64.0 * e["V"] + 64.0 * e["L"], e["V"], e["L"], peak, peak_src, t,
+                                                        "B_q = 41 B of ray in / hit out + 64 B per must-visit node + 64 B per must-test triangle")
+                attach_traffic(extra["roofline_ray"])
+            scene.counter("query.traversal_ms", reset=True)
+            scene.set_option("query.time_kernels", 0)
             sph = torch.cat([q_d, rmax_d[:, None]], dim=1).contiguous()
-            rnd = torch.from_numpy(m.uniforms(n, 3, seed=99)).to(f"cuda:{dev}")
-            extra["sample_in_sphere_mqps"] = n / timed(lambda: scene.sample_in_sphere(sph, rnd, stream=stream)) / 1e3
-            builds = []
-            for _ in range(5):
-                scene0 = scene if world == 1 else None
-                if scene0 is None:
-                    break
-                scene0.build_bvh(stream=stream)
-                builds.append(scene0.stats()["build_ms"])
-            if builds:
+            rnd = torch.from_numpy(m.uniforms(n_total, 3, seed=99)[lo_i:hi_i]).to(f"cuda:{dev}")
+            per_kind["sample_in_sphere"] = timed(lambda: scene.sample_in_sphere(sph, rnd, stream=stream))
+            for k, t in per_kind.items():
+                extra[f"{k}_mqps"] = world * n / job.max(t) / 1e3  # the ONE batch's throughput: total queries / slowest rank's shard time
+            del sph, rnd
+            if rank == 0:
+                builds = []
+                sc0 = scene if world == 1 else pkg.Scene3(v, f, device=dev).compute_silhouettes()
+                for _ in range(5):
+                    sc0.build_bvh(stream=stream)
+                    builds.append(sc0.stats()["build_ms"])
                 extra["build_ms"] = min(builds)
+                extra["build_launches"] = int(sc0.counter("build.launches"))
                 extra["build_roofline_frac"] = (334.0 * stats["num_objects"] / (min(builds) * 1e-3) / 1e9) / peak
-        for cfg in [c for c in args.also.split(",") if c]:
+                # adjacency (compute_silhouettes) warm: the second and third run of a fresh scene (the first pays module load + allocations)
+                sa = pkg.Scene3(v, f, device=dev)
+                adj = []
+                for _ in range(3):
+                    sa.compute_silhouettes()
+                    adj.append(sa.stats()["adjacency_ms"])
+                extra["adjacency_ms"], extra["adjacency_first_call_ms"] = min(adj[1:]), adj[0]
+                del sa
+        cfgs = [c for c in (args.configs + "," + args.also).split(",") if c]
+        for cfg in dict.fromkeys(cfgs):
             try:
-                extra[cfg] = other_config(cfg, pkg, m, dev, stream)
+                r = other_config(cfg, job, pkg, m, stream, peak, mv)
+                if rank == 0:
+                    extra[cfg] = r
             except Exception as ex:
+                if world > 1:
+                    raise  # a rank that skipped a collective would hang the others
                 extra[cfg] = {"error": repr(ex)}
-        # the reference's own CUDA path on this B200 (prebuilt from the unmodified headers; absent -> skipped)
-        try:
-            from oracle import RefScene, ref_available
-            if ref_available("cuda"):
-                with quiet_stdout():
-                    ns = 1 << 22
-                    ref = RefScene(v, f, "cuda")
-                    ref.time_construct(3)
-                    rc = {"construct_ms": ref.timings()["construct_ms"], "build_bvh_ms_incl_host": ref.timings()["build_bvh_ms"],
-                          "compute_silhouettes_host_ms": ref.timings()["silhouettes_ms"], "sample": f"first {ns} of the C3 queries"}
-                    d_h = m.unit_directions(ns, seed=77)
-                    ref.silhouette(q_h[:ns])
-                    ref.silhouette(q_h[:ns])
-                    rc["silhouette_unbounded_mqps"] = ns / ref.last_ms / 1e3
-                    ref.closest(q_h[:ns])
-                    ref.closest(q_h[:ns])
-                    rc["closest_mqps"] = ns / ref.last_ms / 1e3
-                    ref.ray(q_h[:ns], d_h)
-                    ref.ray(q_h[:ns], d_h)
-                    rc["ray_mqps"] = ns / ref.last_ms / 1e3
-                    rc["note"] = ("the reference has no r_max input (SURVEY Q5): its answer to the C3 workload is the unbounded "
-                                  "query followed by a filter, i.e. silhouette_unbounded_mqps is its C3 throughput")
-                    extra["reference_cuda"] = rc
-                    extra["speedup_vs_reference_cuda_c3"] = value / world / rc["silhouette_unbounded_mqps"]
-        except Exception as ex:  # baseline legs never break the bench line
-            extra["reference_cuda_error"] = repr(ex)
-        try:
-            cpu_base = cpu_silhouette_baseline(v, f, q_h, r_p.numpy())
-        except Exception as ex:
-            cpu_base = {"value": None, "unit": "M queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"}
+        if rank == 0:
+            # the reference's own CUDA path on this B200 (prebuilt from the unmodified headers; absent -> skipped)
+            try:
+                from oracle import RefScene, ref_available
+                if ref_available("cuda"):
+                    with quiet_stdout():
+                        ns = min(1 << 22, n)
+                        ref = RefScene(v, f, "cuda")
+                        ref.time_construct(3)
+                        rc = {"construct_ms": ref.timings()["construct_ms"], "build_bvh_ms_incl_host": ref.timings()["build_bvh_ms"],
+                              "compute_silhouettes_host_ms": ref.timings()["silhouettes_ms"], "sample": f"first {ns} of the C3 queries"}
+                        ref.silhouette(q_h[:ns])
+                        ref.silhouette(q_h[:ns])
+                        rc["silhouette_unbounded_mqps"] = ns / ref.last_ms / 1e3
+                        ref.closest(q_h[:ns])
+                        ref.closest(q_h[:ns])
+                        rc["closest_mqps"] = ns / ref.last_ms / 1e3
+                        ref.ray(q_h[:ns], d_h[:ns])
+                        ref.ray(q_h[:ns], d_h[:ns])
+                        rc["ray_mqps"] = ns / ref.last_ms / 1e3
+                        rc["note"] = ("the reference has no r_max input (SURVEY Q5): its answer to the C3 workload is the unbounded "
+                                      "query followed by a filter, i.e. silhouette_unbounded_mqps is its C3 throughput")
+                        extra["reference_cuda"] = rc
+                        extra["speedup_vs_reference_cuda_c3_per_gpu"] = (n_total / ms_per_step / 1e3 / world) / rc["silhouette_unbounded_mqps"]
+                        extra["ray_speedup_vs_reference_cuda_per_gpu"] = extra["ray_mqps"] / world / rc["ray_mqps"]
+            except Exception as ex:  # baseline legs never break the bench line
+                extra["reference_cuda_error"] = repr(ex)
+            try:
+                cs = _cpu_scene(v, f)
+                cpu_base = cpu_silhouette_baseline(v, f, q_h, rmax_d.cpu().numpy(), scene=cs)
+                extra["cpu_baseline_other"] = cpu_other_baselines(v, f, q_h, d_h, cs)
+            except Exception as ex:
+                cpu_base = {"value": None, "unit": "M queries/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"}
 
+    if rank != 0:
+        job.close()
+        return None
+    value = n_total / (ms_per_step * 1e-3) / 1e6
     line = {"metric": "M queries/sec (nearest-silhouette, star radii) @1M tris", "value": value, "unit": "M queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": n, "triangles": stats["num_objects"],
-                       "parallelism": f"replicated tree, query batch sharded x{world}",
-                       "l2": "inputs larger than L2 (268 MB of queries + 192 MB of tree records + 201 MB of ordering buffers per step vs 126 MB L2); no explicit flush",
-                       "step": "Morton ordering of the batch (bounds, keys, 3-pass onesweep radix sort) + persistent traversal kernel",
-                       "e2e": "snch_closest_silhouette_batch on pinned HOST buffers: H2D, kernels and D2H inside the call, pipelined in chunks "
-                              "of query.host_chunk = 8388608 queries over a copy-in stream, two compute streams and a copy-out stream"},
-            "e2e": {"value": world * n * e2e_steps / (e2e_ms_max * 1e-3) / 1e6, "unit": "M queries/s", "h2d_bytes_per_step": n * 16,
-                    "d2h_bytes_per_step": n * 4, "ms_per_step": e2e_ms_max / e2e_steps},
+            "config": {"workload": WORKLOAD, "queries_total": n_total, "queries_per_gpu_per_step": n, "triangles": stats["num_objects"],
+                       "parallelism": f"tree built on rank 0 and broadcast (replicated), ONE query batch sharded x{world} (contiguous shards)",
+                       "l2": "inputs larger than L2 (16 B/query of queries + radii, 192 MB of tree records, 12 B/query of ordering buffers per step vs "
+                             "126 MB L2); no explicit flush",
+                       "step": "Morton ordering of the shard (bounds, keys, 3-pass onesweep radix sort) + persistent traversal kernel + its tail launch",
+                       "e2e": "snch_closest_silhouette_batch on page-locked HOST buffers shared by the ranks: H2D, kernels and D2H inside the call "
+                              "(pipelined in chunks of query.host_chunk = 8388608 queries), results land in ONE host array; max(CUDA events, wall) per "
+                              "rank, max over ranks"},
+            "e2e": {"value": n_total * e2e_steps / (e2e_ms_max * 1e-3) / 1e6, "unit": "M queries/s", "h2d_bytes_per_step": n_total * 16,
+                    "d2h_bytes_per_step": n_total * 4, "ms_per_step": e2e_ms_max / e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_base, "extra": extra}
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    job.close()
     return line
 
 

@@ -185,12 +185,11 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
 /* Scheduling knobs of the batched kernels; results never depend on them (tests/test_gpu_queries.py sweeps them).
  *   "query.sort_min_n"  batches at least this large are visited in Morton order of the query points (default 16384; 0 = never)
  *   "query.sort_bits"   key bits of that ordering (8..30, default 24)
- *   "query.sort_rays"   ray batches: 0 = caller's order, 1 = Morton order of the origins (default), 2 = direction octant, then origin
+ *   "query.sort_rays"   ray batches: 0 = caller's order (default), 1 = Morton order of the origins, 2 = direction octant, then origin
  *   "query.cone_filter" silhouette normal-cone test: 0 = cone.cuh:168-212 verbatim; 1 = guard-banded sine-space evaluation on MUFU
  *                       approximations, the verbatim chain out of line for everything inside the band (default)
  *   "query.seed"        closest point: bit 0 = bound each query by the triangle that answered the lane's previous query (default 1);
  *                       bit 1 = switch the per-triangle lower bound off
- *   "query.sil_seed"    silhouette: queue the leaf that answered the lane's previous query as a pruning hint (default 1)
  *   "query.sil_tail"    silhouette: when a batch has been handed out, a warp with at most this many walking lanes passes them to a
  *                       one-query-per-warp finishing launch (default 4; 0 = never)
  *   "query.sort_radius" bounded silhouette batches: 0 = Morton order only, 1 = search-radius octave then Morton, 2 = the same with
@@ -199,7 +198,7 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *                       per warp (default 2097152; 0 = never)
  *   "query.wide_max_n_sil"  the same for silhouette batches (default 262144)
  *   "query.ray_kernel"  1 = reference-order ray walk with parked leaves (default), 0 = leaves tested where they are met
- *   "query.ray_flush" / "query.ray_refill"  parked / idle lanes of a warp that trigger the triangle tests / the next draw (8 / 4)
+ *   "query.ray_flush" / "query.ray_refill"  parked / idle lanes of a warp that trigger the triangle tests / the next draw (8 / 8)
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
  *   "build.refit_kernel" 1 = CTA-cooperative refit (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort
@@ -274,9 +273,33 @@ int snch_sample_in_sphere_batch2(const snch_scene2 *s, const float *circles_xyr,
                                  float *out_pdf, float *out_point_xy, snch_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Replication (multi-GPU): the built scene lives in ONE pointer-free arena.  Rank 0 exposes it, the caller
- * moves the bytes (ncclBroadcast / cudaMemcpyPeer / torch.distributed.broadcast) and every other rank adopts its copy.
+ * Replication (multi-GPU): the built scene lives in ONE pointer-free arena; a replica is a byte copy of it plus a
+ * pointer patch.  The reference is single-GPU (no counterpart); this is the exchange step of its north-star deployment —
+ * build on one GPU, broadcast over NVLink, every GPU traverses its shard of the query batch against its own copy.
+ *
+ *   one process per GPU  : snch_comm_* + snch_scene_broadcast — ncclBroadcast received directly into the replica's arena.
+ *                          NCCL is libnccl.so.2 itself, resolved on first use (SNCH_NCCL_LIB overrides the path); nothing else
+ *                          in this library needs it.  The 128-byte id from snch_comm_unique_id (rank 0) reaches the other ranks by
+ *                          whatever bootstrap the job has (MPI, a file, torch.distributed, ...); a job that already owns an
+ *                          ncclComm_t wraps it with snch_comm_adopt instead.
+ *   one process, n GPUs  : snch_scene_replicate_local — cudaMemcpyPeerAsync fan-out, peer access enabled where possible.
+ *   bring your own bytes : snch_scene_arena + snch_scene_adopt_arena.
+ * A replica answers every query and export like the original; it cannot be rebuilt (rebuild the original, then
+ * snch_scene_rebroadcast into the replicas' existing arenas: the warm form of the exchange).
  * ------------------------------------------------------------------------------------------------------------- */
+#define SNCH_COMM_ID_BYTES 128
+typedef struct snch_comm snch_comm;
+int snch_comm_unique_id(void *id_out, uint64_t bytes);                                   /* ncclGetUniqueId */
+int snch_comm_create(const void *id, uint64_t bytes, int rank, int world, int device, snch_comm **out); /* ncclCommInitRank (collective) */
+int snch_comm_adopt(void *nccl_comm, int rank, int world, int device, snch_comm **out);  /* wrap the caller's ncclComm_t (not destroyed here) */
+int snch_comm_destroy(snch_comm *c);
+/* collective over `comm`, asynchronous on `stream` until the final synchronisation.  Root: `scene` = the built scene, *out = NULL.
+ * Other ranks: `scene` = NULL, *out = the replica on comm's device. */
+int snch_scene_broadcast(const snch_scene *scene, int root, snch_comm *comm, snch_stream stream, snch_scene **out);
+/* collective: the root's (rebuilt) arena into the existing arenas of its replicas (same vertex / triangle / edge counts) */
+int snch_scene_rebroadcast(snch_scene *scene, int root, snch_comm *comm, snch_stream stream);
+/* replicas of `scene` on devices[0..n) of this process (out[i] on devices[i]; a device may be the scene's own) */
+int snch_scene_replicate_local(const snch_scene *scene, const int *devices, int n, snch_scene **out);
 int snch_scene_arena(const snch_scene *s, void **device_ptr, uint64_t *bytes);
 /* arena_copy: DEVICE pointer on `device` holding a byte-exact copy of another scene's arena (copied; caller keeps ownership) */
 int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, snch_stream stream, snch_scene **out);

@@ -7,7 +7,7 @@ this package without the built library, or calling it without a GPU, raises.
 The directory name contains a hyphen (it is the name the project was given); ``import snch_lbvh_b200`` works through
 the one-line shim module at the repository root.
 """
-from .binding import (Scene3, Scene2, SnchError, lib, lib_path, ABI_SYMBOLS, ExportKind)  # noqa: F401
+from .binding import (Scene3, Scene2, Comm, SnchError, lib, lib_path, ABI_SYMBOLS, ExportKind)  # noqa: F401
 from . import meshes  # noqa: F401
 
 scene3 = Scene3  # the reference spells it lbvh::scene<3>

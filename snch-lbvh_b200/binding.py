@@ -20,6 +20,8 @@ ABI_SYMBOLS = [
     "snch_closest_silhouette_batch", "snch_intersect_batch", "snch_sample_in_sphere_batch", "snch_scene_arena",
     "snch_scene_adopt_arena", "snch_scene_set_option", "snch_scene_counter", "snch_lbvh_build", "snch_scene_update_vertices",
     "snch_wost_step_batch", "snch_scene_save", "snch_scene_load", "snch_scene_last_kernel",
+    "snch_comm_unique_id", "snch_comm_create", "snch_comm_adopt", "snch_comm_destroy", "snch_scene_broadcast", "snch_scene_rebroadcast",
+    "snch_scene_replicate_local",
     "snch_scene2_create", "snch_scene2_destroy", "snch_scene2_compute_silhouettes", "snch_scene2_build", "snch_scene2_stats",
     "snch_scene2_device_repr", "snch_scene2_export", "snch_scene2_set_option", "snch_closest_point_batch2",
     "snch_closest_silhouette_batch2", "snch_intersect_batch2", "snch_sample_in_sphere_batch2",
@@ -128,6 +130,13 @@ def lib():
     L.snch_intersect_batch2.argtypes = [vp, vp, vp, vp, u64, vp, vp, C.c_int, vp]
     L.snch_sample_in_sphere_batch2.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp]
     L.snch_scene_last_kernel.argtypes = [vp]
+    L.snch_comm_unique_id.argtypes = [vp, u64]
+    L.snch_comm_create.argtypes = [vp, u64, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.snch_comm_adopt.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.snch_comm_destroy.argtypes = [vp]
+    L.snch_scene_broadcast.argtypes = [vp, C.c_int, vp, vp, C.POINTER(vp)]
+    L.snch_scene_rebroadcast.argtypes = [vp, C.c_int, vp, vp]
+    L.snch_scene_replicate_local.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     for name in ABI_SYMBOLS:
         if name not in ("snch_last_error", "snch_scene_last_kernel"):
             getattr(L, name).restype = C.c_int
@@ -395,6 +404,13 @@ class Scene3:
         with torch.cuda.device(self.device):
             return torch.as_tensor(_View(), device=f"cuda:{self.device}")
 
+    def replicate_local(self, devices):
+        """Replicas on other GPUs of THIS process (cudaMemcpyPeerAsync fan-out, include/snch_b200.h: snch_scene_replicate_local)."""
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        outs = (C.c_void_p * len(devices))()
+        _check(self._L.snch_scene_replicate_local(self._h, devs, len(devices), outs))
+        return [Scene3._from_handle(C.c_void_p(outs[i]), devices[i]) for i in range(len(devices))]
+
     @classmethod
     def adopt_arena(cls, arena_tensor, device: int, stream=None):
         """Create a replica on `device` from a byte-exact copy of another scene's arena (torch uint8 CUDA tensor)."""
@@ -402,6 +418,48 @@ class Scene3:
         _check(lib().snch_scene_adopt_arena(arena_tensor.data_ptr(), arena_tensor.numel(), int(device), _stream_ptr(stream),
                                             C.byref(h)))
         return cls._from_handle(h, device)
+
+
+class Comm:
+    """A communicator of the library's own (libnccl.so.2, no torch): ``Comm.unique_id()`` on rank 0, ship the 128 bytes to the
+    other ranks by any means, then ``Comm(id, rank, world, device)`` on every rank (collective).  ``broadcast(scene, root)``
+    returns the root's scene on the root and a replica elsewhere; ``rebroadcast`` refreshes existing replicas in place."""
+
+    ID_BYTES = 128
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self._L = lib()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        buf = C.create_string_buffer(bytes(unique_id), self.ID_BYTES)
+        h = C.c_void_p()
+        _check(self._L.snch_comm_create(buf, self.ID_BYTES, self.rank, self.world, self.device, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        _check(lib().snch_comm_unique_id(buf, Comm.ID_BYTES))
+        return buf.raw
+
+    def broadcast(self, scene, root: int = 0, stream=None):
+        out = C.c_void_p()
+        _check(self._L.snch_scene_broadcast(scene._h if scene is not None else None, int(root), self._h, _stream_ptr(stream), C.byref(out)))
+        return scene if self.rank == root else Scene3._from_handle(out, self.device)
+
+    def rebroadcast(self, scene, root: int = 0, stream=None):
+        _check(self._L.snch_scene_rebroadcast(scene._h, int(root), self._h, _stream_ptr(stream)))
+        return scene
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.snch_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Scene2:

@@ -817,7 +817,6 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.cone_filter") t.cone_filter = (int)value;
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.sort_radius") t.sort_radius = (int)value;
-    else if (k == "query.sil_seed") t.sil_seed = (int)value;
     else if (k == "query.sil_tail") t.sil_tail = (int)value;
     else if (k == "query.wide_max_n") t.wide_max_n = (int)value;
     else if (k == "query.wide_max_n_sil") t.wide_max_n_sil = (int)value;
@@ -853,17 +852,16 @@ int snch_scene_arena(const snch_scene *s, void **device_ptr, uint64_t *bytes)
     return SNCH_OK;
 }
 
-static int adopt_from(const void *src, bool src_is_host, uint64_t bytes, int device, cudaStream_t cst, snch_scene **out, const char *who)
+// Replica creation in two steps shared by adopt / load / broadcast / peer fan-out: adopt_begin validates the (untrusted)
+// header and allocates the arena on `device`; the caller fills it; adopt_end re-patches the embedded pointers.
+extern "C++"
+{
+namespace snch
+{
+int adopt_begin(const ArenaHeader &h, uint64_t bytes, int device, const char *who, snch_scene **out)
 {
     *out = nullptr;
     SNCH_CUDA(cudaSetDevice(device));
-    ArenaHeader h;
-    if (src_is_host) std::memcpy(&h, src, sizeof h);
-    else
-    {
-        SNCH_CUDA(cudaMemcpyAsync(&h, src, sizeof h, cudaMemcpyDeviceToHost, cst));
-        SNCH_CUDA(cudaStreamSynchronize(cst));
-    }
     if (h.magic != kArenaMagic || h.version != kArenaVersion || h.total_bytes != bytes)
     {
         set_error(std::string(who) + ": not a scene arena (magic/version/size mismatch)");
@@ -905,25 +903,50 @@ static int adopt_from(const void *src, bool src_is_host, uint64_t bytes, int dev
     }
     s->arena_bytes = bytes;
     s->hdr = h;
-    cudaError_t e = cudaMemcpyAsync(s->arena, src, bytes, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cst);
+    *out = s;
+    return SNCH_OK;
+}
+int adopt_end(snch_scene *s, cudaStream_t cst)
+{
+    resolve_view(s);
+    int st = patch_pointers(s, cst); // reference-layout structs embed raw pointers (scene.cuh:831-839)
+    if (st == SNCH_OK)
+    {
+        const cudaError_t e = cudaStreamSynchronize(cst);
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    if (st == SNCH_OK) s->built = true;
+    return st;
+}
+} // namespace snch
+} // extern "C++"
+
+static int adopt_from(const void *src, bool src_is_host, uint64_t bytes, int device, cudaStream_t cst, snch_scene **out, const char *who)
+{
+    *out = nullptr;
+    SNCH_CUDA(cudaSetDevice(device));
+    ArenaHeader h;
+    if (src_is_host) std::memcpy(&h, src, sizeof h);
+    else
+    {
+        SNCH_CUDA(cudaMemcpyAsync(&h, src, sizeof h, cudaMemcpyDeviceToHost, cst));
+        SNCH_CUDA(cudaStreamSynchronize(cst));
+    }
+    snch_scene *s = nullptr;
+    int st = adopt_begin(h, bytes, device, who, &s);
+    if (st != SNCH_OK) return st;
+    const cudaError_t e = cudaMemcpyAsync(s->arena, src, bytes, src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cst);
     if (e != cudaSuccess)
     {
         snch_scene_destroy(s);
         return cuda_fail(e, "arena copy");
     }
-    resolve_view(s);
-    int st = patch_pointers(s, cst); // reference-layout structs embed raw pointers (scene.cuh:831-839)
-    if (st == SNCH_OK)
-    {
-        e = cudaStreamSynchronize(cst);
-        if (e != cudaSuccess) st = cuda_fail(e, "cudaStreamSynchronize");
-    }
+    st = adopt_end(s, cst);
     if (st != SNCH_OK)
     {
         snch_scene_destroy(s);
         return st;
     }
-    s->built = true;
     *out = s;
     return SNCH_OK;
 }

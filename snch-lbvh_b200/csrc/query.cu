@@ -660,11 +660,6 @@ SNCH_DI float solo_silhouette(const SceneView &sv, const Stk st, int lane, V3 p,
 //     order or grouping of the tests, so results are identical to the sequential loop's;
 //   * the lowest kSStack levels of each lane's traversal stack live in shared memory (conflict-free: the bank depends
 //     on the lane only), deeper levels spill to local memory;
-//   * kSeed: a lane remembers the leaf that answered its previous query (its neighbour in the ordered batch) and queues that
-//     leaf as a HINT when it takes a new query.  A hint distance only tightens the pruning bound; the answer is still the
-//     minimum over edges the walk itself reaches, and if the walk ends without confirming the hint (no reached edge within
-//     it — the reference's cone chain does not lead to that leaf) the query is walked again from the answer found so far
-//     without a hint.  So the result is the unseeded one;
 //   * kEdge: the per-lane minimum is the 64-bit key (distance bits, LEdge slot), so the edge that attains the answer comes
 //     back with it (snch_closest_silhouette_batch out_edge / out_point); instantiated only when those outputs are asked for;
 //   * TAIL: once the batch has no more queries to hand out, a warp left with at most `tail_lanes` walking lanes stops
@@ -674,9 +669,8 @@ SNCH_DI float solo_silhouette(const SceneView &sv, const Stk st, int lane, V3 p,
 //     same predicate chain, same edge tests, same minimum (an edge found before the restart lies within the inclusive
 //     bound and is reached again).
 constexpr int kSStack = 12;
-constexpr int kLeafQueue = 128;  // >= kLeafFlushAt - 1 + 64 + 32 (every lane can add two leaves per step, plus one hint)
+constexpr int kLeafQueue = 96;   // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
 constexpr int kLeafFlushAt = 32;
-constexpr uint32_t kOwnerHint = 32u; // queue owner byte: lane | kOwnerHint for a hint entry
 template <bool kEdge> struct SilResult
 {
     using T = uint32_t;
@@ -693,14 +687,13 @@ template <> struct SilResult<true>
     SNCH_DI static float dist(T r) { return __uint_as_float((uint32_t)(r >> 32)); }
     SNCH_DI static uint32_t slot(T r) { return (uint32_t)r; }
 };
-template <int kFilter, bool kSeed, bool kEdge>
+template <int kFilter, bool kEdge>
 __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
                       float *__restrict__ out_point, unsigned long long *counter, int tail_lanes, uint32_t *__restrict__ tail_slot,
                       float *__restrict__ tail_bound)
 {
-    static_assert(!(kSeed && kEdge), "the hinted walk does not carry edge slots");
     using Res = SilResult<kEdge>;
     __shared__ StackEntry s_stk[kSStack][kQueryThreads];
     struct WarpQueue // one base address per warp: payloads, owner bytes and the fill count are immediate offsets from it
@@ -711,7 +704,6 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     };
     __shared__ WarpQueue s_wq[kQueryThreads / 32];
     __shared__ typename Res::T s_result[kQueryThreads];
-    __shared__ uint32_t s_hint[kSeed ? kQueryThreads : 1], s_seed[kSeed ? kQueryThreads : 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpQueue &wq = s_wq[wid];
     Feeder fd{0u, 0u, false};
@@ -720,17 +712,9 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     V3 p = V3{0.f, 0.f, 0.f};
     bool flip = false, found = false, busy = false, pend = false, tail = false;
     float best = INFINITY, best2 = INFINITY;
-    float ans = INFINITY;    // kSeed: smallest distance the walk itself has reached (best = min(ans, hint) is only the pruning bound)
-    uint32_t seed = kNone;   // kSeed: queue payload of the leaf that answered this lane's previous query
-    bool hinted = false;     // kSeed: a hint has lowered `best` below what the walk itself has reached
     uint32_t best_slot = kNone; // kEdge: LEdge slot of the edge that attains `best`
     uint32_t slot = kNone, node = kNone;
     s_result[threadIdx.x] = Res::kEmpty;
-    if (kSeed)
-    {
-        s_hint[threadIdx.x] = kNone;
-        s_seed[threadIdx.x] = kNone;
-    }
     if (lane == 0) wq.count = 0;
     __syncwarp();
     for (;;)
@@ -745,23 +729,12 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 qc -= take;
                 const bool mine = (uint32_t)lane < take;
                 const uint32_t payload = mine ? wq.payload[qc + lane] : 0u;
-                const uint32_t ow = mine ? (uint32_t)wq.owner[qc + lane] : (uint32_t)lane;
-                const int owner = (int)(ow & 31u);
-                const bool is_hint = kSeed && (ow & kOwnerHint) != 0;
+                const int owner = mine ? (int)wq.owner[qc + lane] : lane;
                 const V3 op = V3{__shfl_sync(kFull, p.x, owner), __shfl_sync(kFull, p.y, owner), __shfl_sync(kFull, p.z, owner)};
                 float ob = __shfl_sync(kFull, best, owner);
                 const bool oflip = __shfl_sync(kFull, (int)flip, owner) != 0;
                 uint32_t eslot = kNone;
-                if (leaf_silhouette(sv, payload >> 2, payload & 3u, op, oflip, ob, eslot))
-                {
-                    if (is_hint) atomicMin(&s_hint[(wid << 5) + owner], __float_as_uint(ob));
-                    else
-                    {
-                        const typename Res::T nb = Res::make(ob, eslot);
-                        const typename Res::T old = atomicMin(&s_result[(wid << 5) + owner], nb);
-                        if (kSeed && nb <= old) s_seed[(wid << 5) + owner] = payload; // (racy between two improving lanes: any of them is a usable seed)
-                    }
-                }
+                if (leaf_silhouette(sv, payload >> 2, payload & 3u, op, oflip, ob, eslot)) atomicMin(&s_result[(wid << 5) + owner], Res::make(ob, eslot));
                 __syncwarp();
             }
             const typename Res::T rb = s_result[threadIdx.x];
@@ -775,27 +748,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                     found = true;
                     if (kEdge) best_slot = Res::slot(rb);
                 }
-                if (kSeed && v <= ans)
-                {
-                    ans = v;
-                    seed = s_seed[threadIdx.x];
-                }
                 s_result[threadIdx.x] = Res::kEmpty;
-            }
-            if (kSeed)
-            {
-                const uint32_t hb = s_hint[threadIdx.x];
-                if (hb != kNone)
-                {
-                    const float v = __uint_as_float(hb);
-                    if (node != kNone && v < best)
-                    { // a hint that arrives after the walk has ended changes nothing: that walk used only confirmed bounds
-                        best = v;
-                        best2 = v * v;
-                        hinted = true;
-                    }
-                    s_hint[threadIdx.x] = kNone;
-                }
             }
             pend = false;
             if (lane == 0) wq.count = 0;
@@ -805,20 +758,9 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         // ---- 2. finished walks hand in their answer; idle lanes take the next query
         if (busy && node == kNone)
         {
-            if (kSeed && hinted && ans > best)
-            { // the hint was never confirmed by an edge the walk reached: walk again, bounded by what it did reach
-                best = found ? ans : (rmax ? __ldg(rmax + slot) : INFINITY);
-                best2 = best * best;
-                hinted = false;
-                sp = 0;
-                node = 0;
-            }
-            else
-            {
-                out_dist[slot] = found ? (kSeed ? ans : best) : INFINITY;
-                if (kEdge) write_silhouette_point(sv, slot, best_slot, p, found, out_edge, out_point);
-                busy = false;
-            }
+            out_dist[slot] = found ? best : INFINITY;
+            if (kEdge) write_silhouette_point(sv, slot, best_slot, p, found, out_edge, out_point);
+            busy = false;
         }
         const unsigned idle = __ballot_sync(kFull, !busy);
         if (idle)
@@ -835,25 +777,13 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
                 busy = true;
                 sp = 0;
                 node = 0;
-                if (kSeed)
-                {
-                    ans = INFINITY;
-                    hinted = false;
-                    if (seed != kNone)
-                    {
-                        const uint32_t pos = atomicAdd(&wq.count, 1u);
-                        wq.payload[pos] = seed;
-                        wq.owner[pos] = (uint8_t)((uint32_t)lane | kOwnerHint);
-                        pend = true;
-                    }
-                }
             }
             if (fd.exhausted)
             {
                 const int walking = __popc(__ballot_sync(kFull, busy));
                 if (walking == 0) break;
                 if (walking <= tail_lanes)
-                { // nothing left to hand out and few lanes still walk: drain the queue (top of the loop), then finish cooperatively
+                { // nothing left to hand out and few lanes still walk: drain the queue (top of the loop), then hand them to the tail launch
                     tail = true;
                     __syncwarp();
                     continue;
@@ -918,22 +848,19 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         __syncwarp(); // queue appends of this step are visible to the whole warp before the next count is read
     }
     if (!tail) return;
-    // ---- TAIL: the queue is drained and every confirmed result is folded into found / best (/ ans).  Lanes whose walk had
-    // already ended hand in; the queries still being walked go on the tail list with the bound found so far, and the launch
-    // that follows (k_silhouette_wide over that list) finishes each of them on 32 lanes.
-    const bool need = busy && (node != kNone || (kSeed && hinted && ans > best));
-    if (busy && !need)
+    // ---- TAIL: the queue is drained and every result is folded into found / best.  Lanes whose walk had already ended hand in;
+    // the queries still being walked go on the tail list with the bound found so far, and the launch that follows
+    // (k_silhouette_wide over that list) finishes each of them on 32 lanes.
+    if (busy && node == kNone)
     {
-        out_dist[slot] = found ? (kSeed ? ans : best) : INFINITY;
+        out_dist[slot] = found ? best : INFINITY;
         if (kEdge) write_silhouette_point(sv, slot, best_slot, p, found, out_edge, out_point);
     }
-    if (need)
+    else if (busy)
     {
-        float bound = best;
-        if (kSeed) bound = ans < INFINITY ? ans : (rmax ? __ldg(rmax + slot) : INFINITY); // only confirmed distances bound the restart
         const uint32_t at = (uint32_t)atomicAdd(counter + 1, 1ull); // < gridDim.x * blockDim.x entries by construction
         tail_slot[at] = slot;
-        tail_bound[at] = bound;
+        tail_bound[at] = best;
     }
 }
 
@@ -1111,7 +1038,7 @@ __global__ void __launch_bounds__(kQueryThreads)
 //     is then not run for one lane at a time in nearly every step).
 constexpr int kRStack = 12;
 template <bool kAnyHit>
-__global__ void __launch_bounds__(kQueryThreads)
+__global__ void __launch_bounds__(kQueryThreads, 10)
     k_intersect_parked(SceneView sv, const float *__restrict__ org, const float *__restrict__ dir, const float *__restrict__ tmaxv,
                        const uint32_t *__restrict__ perm, uint32_t n, snch_hit *__restrict__ hits, uint8_t *__restrict__ found_out,
                        unsigned long long *counter, int flush_lanes, int refill_lanes)
@@ -1125,35 +1052,10 @@ __global__ void __launch_bounds__(kQueryThreads)
     float max_dist = INFINITY, best_t = INFINITY, best_u = 0.f, best_v = 0.f;
     uint32_t best_prim = kNone, slot = kNone, node = kNone, pleaf = kNone;
     bool busy = false;
-    // next entry of this lane's stack that survives the pop-time rejection: an internal node to walk, a leaf to park on, or the end of the ray
-    auto advance = [&]()
-    {
-        node = kNone;
-        pleaf = kNone;
-        while (sp > 0)
-        {
-            --sp;
-            const StackEntry se = sp < kRStack ? s_stk[sp][threadIdx.x] : lstk[sp - kRStack];
-            if (se.key > best_t) continue;
-            if (se.node & kLeafFlag) pleaf = se.node & ~kLeafFlag;
-            else node = se.node;
-            return;
-        }
-        if (found_out) found_out[slot] = best_prim != kNone ? 1 : 0;
-        if (!kAnyHit && hits)
-        {
-            snch_hit h;
-            h.t = best_t;
-            h.u = best_u;
-            h.v = best_v;
-            h.prim = best_prim;
-            hits[slot] = h;
-        }
-        busy = false;
-    };
     for (;;)
     {
         // ---- 1. parked leaves
+        bool pop = false; // this lane needs the next entry of its stack (set by the leaf test above / the step below, served in 3b)
         const unsigned parked = __ballot_sync(kFull, pleaf != kNone);
         if (parked && (__popc(parked) >= flush_lanes || !__any_sync(kFull, node != kNone)))
         {
@@ -1164,24 +1066,23 @@ __global__ void __launch_bounds__(kQueryThreads)
                 ld256(tp, t0, t1);
                 ld256(reinterpret_cast<const char *>(tp) + 32, t2, t3);
                 float t, u, v;
-                bool done = false;
                 if (ray_triangle(V3{t0.x, t0.y, t0.z}, V3{t1.x, t1.y, t1.z}, V3{t2.x, t2.y, t2.z}, o, dv, &t, &u, &v) && t < max_dist && t < best_t)
                 {
                     best_t = t;
                     best_u = u;
                     best_v = v;
                     best_prim = __float_as_uint(t0.w);
-                    done = kAnyHit;
+                    if (kAnyHit) sp = 0;
                 }
-                if (done) sp = 0;
-                advance();
+                pleaf = kNone;
+                pop = true;
             }
         }
         // ---- 2. idle lanes take the next ray
         const unsigned idle = __ballot_sync(kFull, !busy);
         if (idle)
         {
-            if (!fd.exhausted && (__popc(idle) >= refill_lanes || !__any_sync(kFull, node != kNone)))
+            if (!fd.exhausted && (__popc(idle) >= refill_lanes || !__any_sync(kFull, node != kNone || pop)))
             {
                 const uint32_t s = feeder_take(fd, idle, !busy, lane, n, counter);
                 if (s != kNone)
@@ -1231,17 +1132,43 @@ __global__ void __launch_bounds__(kQueryThreads)
                 else lstk[sp - kRStack] = se;
                 ++sp;
             }
+            node = kNone;
             if (h0 || h1)
             {
                 const uint32_t r = h0 ? r0 : r1;
-                if (r & kLeafFlag)
-                {
-                    pleaf = r & ~kLeafFlag;
-                    node = kNone;
-                }
+                if (r & kLeafFlag) pleaf = r & ~kLeafFlag;
                 else node = r;
             }
-            else advance();
+            else pop = true;
+        }
+        // ---- 3b. next entry of the stack that survives the pop-time rejection: an internal node to walk, a leaf to park on, or
+        // the end of the ray — ONE site for the lanes coming from the leaf test and from a dead end, so they run it together
+        if (pop)
+        {
+            while (sp > 0)
+            {
+                --sp;
+                const StackEntry se = sp < kRStack ? s_stk[sp][threadIdx.x] : lstk[sp - kRStack];
+                if (se.key > best_t) continue;
+                if (se.node & kLeafFlag) pleaf = se.node & ~kLeafFlag;
+                else node = se.node;
+                pop = false;
+                break;
+            }
+            if (pop)
+            { // stack empty: the ray is done
+                if (found_out) found_out[slot] = best_prim != kNone ? 1 : 0;
+                if (!kAnyHit && hits)
+                {
+                    snch_hit h;
+                    h.t = best_t;
+                    h.u = best_u;
+                    h.v = best_v;
+                    h.prim = best_prim;
+                    hits[slot] = h;
+                }
+                busy = false;
+            }
         }
     }
 }
@@ -1480,17 +1407,13 @@ static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, c
             v, q, flip, rmax, perm, n, dist, edge, point, counter, nullptr, nullptr);
         return;
     }
-    const bool seeded = !kEdge && t.sil_seed != 0;
-    if (qc) qc->last_kernel = kEdge ? "k_silhouette_coop<edge>" : (seeded ? "k_silhouette_coop<seed>" : "k_silhouette_coop");
-    const unsigned grid = seeded ? persistent_grid(k_silhouette_coop<kFilter, true, false>, t, n) : persistent_grid(k_silhouette_coop<kFilter, false, kEdge>, t, n);
-    // the tail list holds at most one entry per resident lane (tail_scratch_bytes sizes it for the largest grid)
+    if (qc) qc->last_kernel = kEdge ? "k_silhouette_coop<edge>" : "k_silhouette_coop";
+    const unsigned grid = persistent_grid(k_silhouette_coop<kFilter, kEdge>, t, n);
+    // the tail list holds at most one entry per resident lane
     uint32_t *tail_slot = reinterpret_cast<uint32_t *>(tail);
     float *tail_bound = reinterpret_cast<float *>(tail + kTailEntries * 4);
     const int tl = (t.sil_tail > 0 && (uint64_t)grid * kQueryThreads <= kTailEntries) ? (t.sil_tail > 31 ? 31 : t.sil_tail) : 0;
-    if (seeded)
-        k_silhouette_coop<kFilter, true, false><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound);
-    else
-        k_silhouette_coop<kFilter, false, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound);
+    k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound);
     if (tl)
     { // finish the listed queries one per warp; its own work counter is counter[2], the list length counter[1]
         if (qc) qc->launches += 1;

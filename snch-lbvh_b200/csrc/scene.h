@@ -18,11 +18,10 @@ struct QueryTuning
     int sort_radius = 2;    // bounded silhouette batches: 1 = order by search-radius octave first, then Morton code;
                             // 2 = the same with the largest radii first (longest walks start first, the tail is made of cheap queries);
                             // 3, 4 = largest first with 2 / 4 classes per octave
-    int sort_rays = 1;      // ray batches: 0 = caller's order, 1 = Morton order of the origins, 2 = direction octant, then origin
+    int sort_rays = 0;      // ray batches: 0 = caller's order (default: at 1M triangles ordering costs more than it returns, profiles/r2b_variants.json),
+                            // 1 = Morton order of the origins, 2 = direction octant, then origin
     int cone_filter = 1;    // silhouette normal-cone test: 0 = the reference's libm chain verbatim, 1 = guard-banded sine-space filter on
                             // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
-    int sil_seed = 1;       // silhouette: queue the leaf that answered the lane's previous query as a pruning hint (results unchanged:
-                            // an unconfirmed hint makes the query walk again without one)
     int sil_tail = 4;       // silhouette: once the batch is handed out, a warp with at most this many walking lanes finishes them
                             // cooperatively, one query at a time on 32 lanes (0 = never)
     int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical
@@ -32,7 +31,7 @@ struct QueryTuning
                             // bit 1 = switch the per-triangle lower bound OFF (A/B)
     int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked), 0 = leaves tested inline (k_intersect)
     int ray_flush = 8;      // k_intersect_parked: parked lanes of a warp that trigger the triangle tests
-    int ray_refill = 4;     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
+    int ray_refill = 8;     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
                               // Measured on C3 (16.7M queries): 0 -> 60.5 ms, 8M -> 59.5, 4M -> 60.0, 2M -> 63.5, 1M -> 73.1: every extra
@@ -109,6 +108,10 @@ int cuda_fail(cudaError_t e, const char *what);
         cudaError_t e__ = (call);                                    \
         if (e__ != cudaSuccess) return snch::cuda_fail(e__, #call);  \
     } while (0)
+
+// capi.cu — replica creation: validate the header + allocate on `device`; (caller fills the arena); patch pointers
+int adopt_begin(const ArenaHeader &h, uint64_t bytes, int device, const char *who, snch_scene **out);
+int adopt_end(snch_scene *s, cudaStream_t stream);
 
 // adjacency.cu
 int compute_adjacency_device(snch_scene *s);

@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: one process per GPU, the tree is built once and replicated, query batches are
-sharded contiguously by rank, results are gathered to the host.  torch.distributed is used only as plumbing
-(NCCL broadcast of the arena over NVLink / NVSwitch; gloo in the CPU tests).
+sharded contiguously by rank, results are gathered to the host.  The exchange itself is the library's (C-ABI
+snch_comm_* / snch_scene_broadcast on libnccl.so.2); torch.distributed only bootstraps the communicator's id and gathers
+host-side results (gloo in the CPU tests).
 
 The path has exactly ONE exchange step — the broadcast of the pointer-free scene arena.  Queries never communicate.
 """
@@ -17,31 +18,36 @@ def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     return (n * rank) // world, (n * (rank + 1)) // world
 
 
-def replicate_scene(scene, rank: int, world: int, device: int, dist=None, src: int = 0):
-    """Rank `src` passes its built Scene3; every rank returns a Scene3 living on its own GPU.
-
-    The arena is broadcast as one uint8 tensor (ncclBroadcast under torch.distributed) and adopted with
-    snch_scene_adopt_arena, which re-patches the raw pointers embedded in the reference-layout structs."""
+def make_comm(rank: int, world: int, device: int, dist=None, src: int = 0):
+    """The library's own NCCL communicator (binding.Comm -> snch_comm_create: libnccl.so.2, no torch on the data path).
+    torch.distributed — any backend — is only the bootstrap that carries rank `src`'s 128-byte unique id to the others."""
     import torch
-    from .binding import Scene3
+    from .binding import Comm
 
-    if world == 1:
-        return scene
     if dist is None:
         import torch.distributed as dist  # noqa: PLW0642
-    size = torch.zeros(1, dtype=torch.int64, device=f"cuda:{device}")
+    dev = "cpu" if dist.get_backend() == "gloo" else f"cuda:{device}"
+    uid = torch.zeros(Comm.ID_BYTES, dtype=torch.uint8)
     if rank == src:
-        view = scene.arena_tensor()
-        size[0] = view.numel()
-    dist.broadcast(size, src=src)
-    nbytes = int(size.item())
-    if rank == src:
-        dist.broadcast(view, src=src)
+        uid = torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8).clone()
+    uid = uid.to(dev)
+    dist.broadcast(uid, src=src)
+    return Comm(bytes(uid.cpu().numpy().tobytes()), rank, world, device)
+
+
+def replicate_scene(scene, rank: int, world: int, device: int, dist=None, src: int = 0, comm=None):
+    """Rank `src` passes its built Scene3; every rank returns a Scene3 living on its own GPU.
+
+    The arena is broadcast by the library itself (snch_scene_broadcast: ncclBroadcast over NVLink / NVSwitch, received
+    directly into the replica's arena) and its embedded pointers are re-patched on arrival.  `comm`: a binding.Comm to
+    reuse (one is made — and kept on the returned scene as `.comm` — otherwise)."""
+    if world == 1:
         return scene
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}")
-    dist.broadcast(buf, src=src)
-    torch.cuda.current_stream().synchronize()
-    return Scene3.adopt_arena(buf, device=device)
+    if comm is None:
+        comm = make_comm(rank, world, device, dist, src)
+    out = comm.broadcast(scene if rank == src else None, root=src)
+    out.comm = comm
+    return out
 
 
 def sharded_query(query_fn, inputs: list, n: int, rank: int, world: int):

@@ -71,6 +71,10 @@ def test_product_never_touches_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or fn == "Makefile":
                 txt = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert not bad.search(txt), f"{fn} references the oracle"
+            if fn.endswith((".cu", ".cuh", ".h", ".cpp")):  # the one library resolved at run time is NCCL itself (replicate.cu)
+                txt = open(os.path.join(dirpath, fn), errors="replace").read()
+                for m in re.finditer(r"dlopen\(([^,]*),", txt):
+                    assert m.group(1).strip() in ("env", '"libnccl.so.2"'), f"{fn} dlopens {m.group(1)}"
     out = subprocess.check_output(["ldd", os.path.join(pk, "libsnch_b200.so")], text=True)
     assert "oracle" not in out and "snch_ref" not in out
 

@@ -52,18 +52,18 @@ def main():
             best = min(best, a.elapsed_time(b))
         return best, out
 
-    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 1, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0,
-                "query.sort_radius": 2, "query.sil_seed": 1, "query.sil_tail": 4, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
-                "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 4}
-    settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("no_seed", {"query.seed": 0}), ("sil_unseeded", {"query.sil_seed": 0}),
+    defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0,
+                "query.sort_radius": 2, "query.sil_tail": 4, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
+                "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 8}
+    settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("no_seed", {"query.seed": 0}),
                 ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
                 ("sil_tail31", {"query.sil_tail": 31}), ("radius_none", {"query.sort_radius": 0}), ("radius_asc", {"query.sort_radius": 1}),
                 ("sil_bps7", {"query.blocks_per_sm": 7}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
-                ("ray_v1", {"query.ray_kernel": 0}), ("ray_v1_unsorted", {"query.ray_kernel": 0, "query.sort_rays": 0}), ("ray_unsorted", {"query.sort_rays": 0}),
+                ("ray_v1", {"query.ray_kernel": 0}), ("ray_v1_sorted", {"query.ray_kernel": 0, "query.sort_rays": 1}), ("ray_sorted", {"query.sort_rays": 1}),
                 ("ray_octant", {"query.sort_rays": 2}), ("ray_flush1", {"query.ray_flush": 1}), ("ray_flush4", {"query.ray_flush": 4}),
                 ("ray_flush12", {"query.ray_flush": 12}), ("ray_flush16", {"query.ray_flush": 16}), ("ray_flush24", {"query.ray_flush": 24}),
-                ("ray_refill1", {"query.ray_refill": 1}), ("ray_refill2", {"query.ray_refill": 2}), ("ray_refill8", {"query.ray_refill": 8}),
-                ("ray_refill16", {"query.ray_refill": 16}), ("ray_f4_r2", {"query.ray_flush": 4, "query.ray_refill": 2}),
+                ("ray_refill1", {"query.ray_refill": 1}), ("ray_refill2", {"query.ray_refill": 2}), 
+                ("ray_refill4", {"query.ray_refill": 4}), ("ray_refill16", {"query.ray_refill": 16}), ("ray_f4_r2", {"query.ray_flush": 4, "query.ray_refill": 2}),
                 ("ray_f16_r8", {"query.ray_flush": 16, "query.ray_refill": 8}), ("ray_bps8", {"query.blocks_per_sm": 8}), ("ray_bps6", {"query.blocks_per_sm": 6}),
                 ("sort_bits_30", {"query.sort_bits": 30}), ("sort_bits_18", {"query.sort_bits": 18})]
     if args.sets != "all":
