@@ -5,7 +5,6 @@
 //   k_morton      30-bit Morton code of each leaf-box centroid, (key, index) pairs         [bvh.cuh:436-449]
 //   radix sort    stable LSD sort of 8-byte pairs (payload is NOT dragged along)           [bvh.cuh:452-454]
 //   k_hierarchy   Karras 2012 ranges/splits on the augmented key (morton<<32 | index)      [bvh.cuh:109-229,459-515]
-//   k_owned_count + scan   per-leaf silhouette-edge slots
 //   k_refit       leaf boxes/cones in sorted order, then ONE bottom-up climb that merges boxes AND normal cones and
 //                 emits the 64 B / 96 B two-child traversal records                       [bvh.cuh:520-604]
 // The augmented key reproduces the reference topology on both of its paths (unique 32-bit codes, or its 64-bit fallback
@@ -286,14 +285,6 @@ __global__ void __launch_bounds__(256) k_hierarchy(BuildCtx c)
     c.ranges[i] = make_uint2((uint32_t)first, (uint32_t)last);
 }
 
-__global__ void __launch_bounds__(256) k_owned_count(BuildCtx c)
-{
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= c.n) return;
-    const int3 o = c.objects[c.sorted_idx[k]].owned;
-    c.edge_off[k] = (uint32_t)(o.x != -1) + (uint32_t)(o.y != -1) + (uint32_t)(o.z != -1);
-}
-
 SNCH_DI void store_aabb(RefAabb *dst, Box b)
 {
     float2 *p = reinterpret_cast<float2 *>(dst);
@@ -374,11 +365,14 @@ SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
     cone.axis = V3{0.f, 0.f, 0.f};
     cone.half_angle = kPi;
     cone.radius = 0.f;
-    const uint32_t eoff = c.edge_off_packed ? c.edge_off[k] >> 2 : c.edge_off[k];
+    // LEdge is indexed by EDGE ID: the reference numbers edges in first-seen order and gives each to the first triangle (in
+    // input order) that touches it (scene.cuh:1135-1229), so the ids a triangle owns are consecutive — first owned id + s for
+    // its s-th owned edge (checked by tests/test_host_adjacency.py) — and a leaf's edges need no offset table or scan
+    const int owned[3] = {t.owned.x, t.owned.y, t.owned.z};
+    const uint32_t eoff = owned[0] >= 0 ? (uint32_t)owned[0] : 0u;
     uint32_t cnt = 0;
     bool all_two = true;
     V3 fn0[3], fn1[3];
-    const int owned[3] = {t.owned.x, t.owned.y, t.owned.z};
 #pragma unroll
     for (int s = 0; s < 3; ++s)
     {
@@ -406,7 +400,7 @@ SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
         const V3 u1 = has1 ? normalize(n1) : V3{0.f, 0.f, 0.f};
         fn0[s] = u0;
         fn1[s] = u1;
-        float4 *le = reinterpret_cast<float4 *>(c.ledge + eoff + cnt);
+        float4 *le = reinterpret_cast<float4 *>(c.ledge + owned[s]);
         const bool boundary = !(has0 && has1);
         le[0] = make_float4(ea.x, ea.y, ea.z, eb.x);
         le[1] = make_float4(eb.y, eb.z, boundary ? __int_as_float(0x7FC00000) : u0.x, u0.y);
@@ -571,7 +565,8 @@ SNCH_DI void sh_get(const RefitShared &sh, uint32_t id, Box &b, Cone &cn)
     cn.half_angle = sh.f[9][id];
     cn.radius = sh.f[10][id];
 }
-__global__ void __launch_bounds__(kRefitLeaves, 8) k_refit_coop(BuildCtx c)
+template <int kMinBlocks> // resident CTAs per SM the register budget is sized for: 8 (64 registers, a few spills) or 6 (80 registers, none)
+__global__ void __launch_bounds__(kRefitLeaves, kMinBlocks) k_refit_coop(BuildCtx c)
 {
     __shared__ RefitShared sh;
     constexpr uint32_t B = kRefitLeaves;
@@ -829,7 +824,6 @@ int build_device(snch_scene *s, cudaStream_t stream)
 
     // ---- scratch: sort ping-pong + sort/scan counters + flags + box + counters
     const uint64_t sort_elems = sort_scratch_elems(nT);
-    const uint64_t scan_elems = scan_scratch_elems(nT);
     uint64_t so = 0;
     auto stake = [&](uint64_t bytes)
     {
@@ -838,7 +832,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
         return o;
     };
     const uint64_t o_ktmp = stake((uint64_t)nT * 4), o_vtmp = stake((uint64_t)nT * 4);
-    const uint64_t o_sort = stake(sort_elems * 4), o_scan = stake(scan_elems * 4);
+    const uint64_t o_sort = stake(sort_elems * 4);
     const uint64_t o_flags = stake((uint64_t)nT * 4), o_esc = stake((uint64_t)nT * 4), o_box = stake(64), o_cnt = stake(64);
     if (s->scratch_bytes < so)
     {
@@ -857,7 +851,6 @@ int build_device(snch_scene *s, cudaStream_t stream)
     BuildCtx c;
     c.n = nT;
     c.n_edges = nE;
-    c.edge_off_packed = refit ? 1u : 0u;
     c.verts = (const float3 *)(b + h.off_vertices);
     c.edges = (const RefEdge *)(b + h.off_edges);
     c.objects = (const RefTriangle *)(b + h.off_objects);
@@ -903,14 +896,14 @@ int build_device(snch_scene *s, cudaStream_t stream)
         launches += 1 + radix_sort_pairs(c.morton, c.sorted_idx, (uint32_t *)(sc + o_ktmp), (uint32_t *)(sc + o_vtmp), nT, 30,
                                          (uint32_t *)(sc + o_sort), stream);
         if (nT > 1) k_hierarchy<<<(nT - 1 + 255) / 256, 256, 0, stream>>>(c);
-        k_owned_count<<<g256, 256, 0, stream>>>(c);
-        launches += (nT > 1 ? 1 : 0) + 1 + exclusive_scan_u32(c.edge_off, c.edge_off, nT, (uint32_t *)(sc + o_scan), stream);
+        launches += (nT > 1 ? 1 : 0);
     }
     if (s->opt_refit_kernel == 0) k_refit<<<(nT + 127) / 128, 128, 0, stream>>>(c);
     else
     {
         const unsigned ctas = (nT + kRefitLeaves - 1) / kRefitLeaves;
-        k_refit_coop<<<ctas, kRefitLeaves, 0, stream>>>(c);
+        if (s->opt_refit_kernel == 2) k_refit_coop<6><<<ctas, kRefitLeaves, 0, stream>>>(c);
+        else k_refit_coop<8><<<ctas, kRefitLeaves, 0, stream>>>(c);
         if (nT > 1)
         {
             k_refit_top<<<ctas < 8 ? 1 : ctas / 8, 128, 0, stream>>>(c); // one thread per escape of the pass above (~12 per CTA); grid-stride beyond

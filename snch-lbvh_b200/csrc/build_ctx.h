@@ -8,7 +8,6 @@ namespace snch
 struct BuildCtx
 {
     uint32_t n, n_edges;
-    uint32_t edge_off_packed; // refit-only: edge_off already holds (first_edge << 2 | count) from the previous build
     const float3 *verts;
     const RefEdge *edges;
     const RefTriangle *objects;

@@ -818,11 +818,13 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.seed") t.seed = (int)value;
     else if (k == "query.sort_radius") t.sort_radius = (int)value;
     else if (k == "query.sil_tail") t.sil_tail = (int)value;
+    else if (k == "query.sil_flush") t.sil_flush = (int)value;
     else if (k == "query.wide_max_n") t.wide_max_n = (int)value;
     else if (k == "query.wide_max_n_sil") t.wide_max_n_sil = (int)value;
     else if (k == "query.ray_kernel") t.ray_kernel = (int)value;
     else if (k == "query.ray_flush") t.ray_flush = (int)value;
     else if (k == "query.ray_refill") t.ray_refill = (int)value;
+    else if (k == "query.ray_prefetch") t.ray_prefetch = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;

@@ -670,7 +670,7 @@ SNCH_DI float solo_silhouette(const SceneView &sv, const Stk st, int lane, V3 p,
 //     bound and is reached again).
 constexpr int kSStack = 12;
 constexpr int kLeafQueue = 96;   // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
-constexpr int kLeafFlushAt = 32;
+constexpr int kLeafFlushAt = 32; // upper limit of "query.sil_flush"
 template <bool kEdge> struct SilResult
 {
     using T = uint32_t;
@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
                       float *__restrict__ out_point, unsigned long long *counter, int tail_lanes, uint32_t *__restrict__ tail_slot,
-                      float *__restrict__ tail_bound)
+                      float *__restrict__ tail_bound, uint32_t flush_at)
 {
     using Res = SilResult<kEdge>;
     __shared__ StackEntry s_stk[kSStack][kQueryThreads];
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     {
         // ---- 1. queued leaves
         uint32_t qc = wq.count;
-        if (qc >= kLeafFlushAt || tail || __any_sync(kFull, pend && node == kNone))
+        if (qc >= flush_at || tail || __any_sync(kFull, pend && node == kNone))
         {
             while (qc > 0)
             {
@@ -903,6 +903,15 @@ __global__ void __launch_bounds__(kQueryThreads)
     }
 }
 
+// A child that goes on the stack will be read when it is popped: asking L2 for its record now takes the DRAM / L2 latency
+// off that later step (rays are latency-bound: one dependent record fetch per step, profiles/r2b_ncu_prof_ray.json).
+SNCH_DI void prefetch_child(const SceneView &sv, uint32_t ref)
+{
+    const void *p = (ref & kLeafFlag) ? static_cast<const void *>(sv.ltri + (ref & ~kLeafFlag)) : static_cast<const void *>(sv.bnode + ref);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char *>(p) + 32));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // ray intersection (closest hit / any hit)                                               query.cuh:79-169
 // ---------------------------------------------------------------------------------------------------------------
@@ -1041,7 +1050,7 @@ template <bool kAnyHit>
 __global__ void __launch_bounds__(kQueryThreads, 10)
     k_intersect_parked(SceneView sv, const float *__restrict__ org, const float *__restrict__ dir, const float *__restrict__ tmaxv,
                        const uint32_t *__restrict__ perm, uint32_t n, snch_hit *__restrict__ hits, uint8_t *__restrict__ found_out,
-                       unsigned long long *counter, int flush_lanes, int refill_lanes)
+                       unsigned long long *counter, int flush_lanes, int refill_lanes, int prefetch)
 {
     __shared__ StackEntry s_stk[kRStack][kQueryThreads];
     const int lane = threadIdx.x & 31;
@@ -1131,6 +1140,7 @@ __global__ void __launch_bounds__(kQueryThreads, 10)
                 if (sp < kRStack) s_stk[sp][threadIdx.x] = se;
                 else lstk[sp - kRStack] = se;
                 ++sp;
+                if (prefetch) prefetch_child(sv, r1);
             }
             node = kNone;
             if (h0 || h1)
@@ -1413,7 +1423,8 @@ static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, c
     uint32_t *tail_slot = reinterpret_cast<uint32_t *>(tail);
     float *tail_bound = reinterpret_cast<float *>(tail + kTailEntries * 4);
     const int tl = (t.sil_tail > 0 && (uint64_t)grid * kQueryThreads <= kTailEntries) ? (t.sil_tail > 31 ? 31 : t.sil_tail) : 0;
-    k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound);
+    const uint32_t flush_at = (uint32_t)(t.sil_flush < 1 ? 1 : (t.sil_flush > kLeafFlushAt ? kLeafFlushAt : t.sil_flush));
+    k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound, flush_at);
     if (tl)
     { // finish the listed queries one per warp; its own work counter is counter[2], the list length counter[1]
         if (qc) qc->launches += 1;
@@ -1508,11 +1519,16 @@ static void launch_intersect_kernel(const SceneView &v, const QueryTuning &t, co
         return;
     }
     if (qc) qc->last_kernel = "k_intersect_parked";
-    const int fl = t.ray_flush < 1 ? 1 : t.ray_flush, rl = t.ray_refill < 1 ? 1 : t.ray_refill;
+    // a batch that does not fill the machine (one ray per lane, config C1) runs as long as its longest ray: nobody waits there —
+    // a parked leaf is tested at once and a finished lane draws at once
+    const bool small = n < (1u << 20);
+    const int fl = small ? 1 : (t.ray_flush < 1 ? 1 : t.ray_flush), rl = small ? 1 : (t.ray_refill < 1 ? 1 : t.ray_refill);
     if (any_hit)
-        k_intersect_parked<true><<<persistent_grid(k_intersect_parked<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
+        k_intersect_parked<true><<<persistent_grid(k_intersect_parked<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl,
+                                                                                                           t.ray_prefetch);
     else
-        k_intersect_parked<false><<<persistent_grid(k_intersect_parked<false>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
+        k_intersect_parked<false><<<persistent_grid(k_intersect_parked<false>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl,
+                                                                                                             t.ray_prefetch);
 }
 int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
                      uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)

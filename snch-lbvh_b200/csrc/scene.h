@@ -22,6 +22,7 @@ struct QueryTuning
                             // 1 = Morton order of the origins, 2 = direction octant, then origin
     int cone_filter = 1;    // silhouette normal-cone test: 0 = the reference's libm chain verbatim, 1 = guard-banded sine-space filter on
                             // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
+    int sil_flush = 32;     // silhouette: queued leaves of a warp that trigger their tests (1..32; fewer = bounds tighten sooner, tests run on fewer lanes)
     int sil_tail = 4;       // silhouette: once the batch is handed out, a warp with at most this many walking lanes finishes them
                             // cooperatively, one query at a time on 32 lanes (0 = never)
     int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical
@@ -31,7 +32,8 @@ struct QueryTuning
                             // bit 1 = switch the per-triangle lower bound OFF (A/B)
     int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked), 0 = leaves tested inline (k_intersect)
     int ray_flush = 8;      // k_intersect_parked: parked lanes of a warp that trigger the triangle tests
-    int ray_refill = 8;     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
+    int ray_refill = 8;
+    int ray_prefetch = 1;   // k_intersect_parked: ask L2 for the record of a child when it is pushed     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
                               // Measured on C3 (16.7M queries): 0 -> 60.5 ms, 8M -> 59.5, 4M -> 60.0, 2M -> 63.5, 1M -> 73.1: every extra
@@ -95,7 +97,7 @@ struct snch_scene
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0, opt_refit_only = 0;
-    int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds (v2), 0 = one climbing thread per leaf (v1)
+    int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds at 8 CTAs/SM, 2 = the same at 6 CTAs/SM (no spills), 0 = one climbing thread per leaf
 };
 
 namespace snch

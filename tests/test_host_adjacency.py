@@ -42,3 +42,23 @@ def test_non_manifold_and_shuffled_input(pkg, meshes):
     for a, b in zip((sc.export(pkg.ExportKind.EDGES), sc.export(pkg.ExportKind.TRI_EDGES), sc.export(pkg.ExportKind.TRI_OWNED)),
                     o.adjacency()):
         assert np.array_equal(a, b)
+
+
+def test_owned_edge_ids_are_consecutive(meshes):
+    """The traversal records index a leaf's silhouette edges by EDGE ID (build.cu refit_leaf): that relies on the reference's
+    numbering — edges are numbered in first-seen order and owned by the first triangle that touches them (scene.cuh:1135-1229),
+    so triangle i owns exactly the next cnt_i ids, in slot order.  Checked on the oracle's adjacency (bit-identical to the
+    product's, tests above) for closed, open, non-manifold, duplicated and degenerate input."""
+    import numpy as np
+    from oracle import OracleScene
+    v = np.random.default_rng(0).random((30, 3)).astype(np.float32)
+    nasty = np.array([[0, 1, 2], [0, 1, 3], [0, 1, 4], [1, 0, 5], [2, 2, 3], [0, 1, 2], [6, 7, 8], [8, 7, 6], [9, 9, 9]], np.int32)
+    cases = [meshes.tetrahedron(), meshes.icosphere(2), meshes.open_grid(6), meshes.bumpy_torus(24, 16), meshes.bumpy_torus(120, 90), (v, nasty)]
+    for vv, ff in cases:
+        _, _, owned = OracleScene(vv, ff).adjacency()
+        nxt = 0
+        for row in owned:
+            ids = [int(x) for x in row if x != -1]
+            assert list(row[:len(ids)]) == ids, "owned slots are not compacted to the front"
+            assert ids == list(range(nxt, nxt + len(ids))), "owned edge ids are not the next consecutive ids"
+            nxt += len(ids)

@@ -20,7 +20,7 @@ if has variants; then
   echo "variants exit $?"; cat "$OUT/variants.err" | cut -c1-600
 fi
 if has bench; then
-  timeout 1200 python bench.py --steps 10 --warmup 3 --also c1,c4,c5,2d > "$OUT/bench.json" 2> "$OUT/bench.err"
+  timeout 1200 python bench.py --steps 10 --warmup 3 --also 2d > "$OUT/bench.json" 2> "$OUT/bench.err"
   echo "bench exit $?"; tail -c 3500 "$OUT/bench.json"; tail -5 "$OUT/bench.err"
 fi
 if has ref; then
