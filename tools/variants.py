@@ -104,7 +104,19 @@ def main():
                                                            x.view(torch.int32) if x.dtype == torch.float32 else x)) for k, x in res.items()}
         table[name] = row
         print(name, json.dumps(row), file=sys.stderr, flush=True)
-    print(json.dumps({"queries": n, "triangles": len(f), "table": table}, indent=1))
+    # build: the refit kernel variants (identical arenas are asserted by tests/test_gpu_build.py; here only the time)
+    build = {}
+    if args.sets == "all" or "build" in args.sets.split(","):
+        for name, rk in (("refit_coop_8cta", 1), ("refit_coop_6cta", 2), ("refit_per_thread", 0)):
+            sc.set_option("build.refit_kernel", rk)
+            ts = []
+            for _ in range(6):
+                sc.build_bvh()
+                ts.append(sc.stats()["build_ms"])
+            build[name] = {"build_ms_min": min(ts), "build_ms_median": sorted(ts)[len(ts) // 2], "launches": int(sc.counter("build.launches"))}
+            print(name, json.dumps(build[name]), file=sys.stderr, flush=True)
+        sc.set_option("build.refit_kernel", 1)
+    print(json.dumps({"queries": n, "triangles": len(f), "table": table, "build": build}, indent=1))
 
 
 if __name__ == "__main__":
