@@ -190,7 +190,7 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *                       approximations, the verbatim chain out of line for everything inside the band (default)
  *   "query.seed"        closest point: bit 0 = bound each query by the triangle that answered the lane's previous query (default 1);
  *                       bit 1 = switch the per-triangle lower bound off
- *   "query.sil_flush"   silhouette: queued leaves of a warp that trigger their (one per lane) tests (1..32, default 32)
+ *   "query.sil_flush"   silhouette: queued leaves of a warp that trigger their (one per lane) tests (1..32, default 24)
  *   "query.sil_tail"    silhouette: when a batch has been handed out, a warp with at most this many walking lanes passes them to a
  *                       one-query-per-warp finishing launch (default 4; 0 = never)
  *   "query.sort_radius" bounded silhouette batches: 0 = Morton order only, 1 = search-radius octave then Morton, 2 = the same with
@@ -198,12 +198,12 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *   "query.wide_max_n"  closest point: batches smaller than this — or with fewer than 2 queries per triangle — are walked one query
  *                       per warp (default 2097152; 0 = never)
  *   "query.wide_max_n_sil"  the same for silhouette batches (default 262144)
- *   "query.ray_kernel"  1 = reference-order ray walk with parked leaves (default), 0 = leaves tested where they are met
+ *   "query.ray_kernel"  1 = reference-order ray walk with parked leaves for batches of 1M rays and more (default), 0 = leaves tested
+ *                       where they are met, for every batch; 2 = parked leaves for every batch
  *   "query.ray_flush" / "query.ray_refill"  parked / idle lanes of a warp that trigger the triangle tests / the next draw (8 / 8)
- *   "query.ray_prefetch" 1 = prefetch the record of a pushed child into L2 (default), 0 = off
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
- *   "build.refit_kernel" 1 = CTA-cooperative refit (default), 2 = the same with a larger register budget, 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort
+ *   "build.refit_kernel" 1 = CTA-cooperative refit (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort
  *                       (default), 0 = three-kernel passes; "adjacency.device" 1 = GPU silhouette adjacency (default when a device
  *                       is present), 0 = host passes
  * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel).

@@ -824,7 +824,6 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.ray_kernel") t.ray_kernel = (int)value;
     else if (k == "query.ray_flush") t.ray_flush = (int)value;
     else if (k == "query.ray_refill") t.ray_refill = (int)value;
-    else if (k == "query.ray_prefetch") t.ray_prefetch = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;

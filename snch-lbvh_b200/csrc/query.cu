@@ -903,15 +903,6 @@ __global__ void __launch_bounds__(kQueryThreads)
     }
 }
 
-// A child that goes on the stack will be read when it is popped: asking L2 for its record now takes the DRAM / L2 latency
-// off that later step (rays are latency-bound: one dependent record fetch per step, profiles/r2b_ncu_prof_ray.json).
-SNCH_DI void prefetch_child(const SceneView &sv, uint32_t ref)
-{
-    const void *p = (ref & kLeafFlag) ? static_cast<const void *>(sv.ltri + (ref & ~kLeafFlag)) : static_cast<const void *>(sv.bnode + ref);
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const char *>(p) + 32));
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // ray intersection (closest hit / any hit)                                               query.cuh:79-169
 // ---------------------------------------------------------------------------------------------------------------
@@ -1050,7 +1041,7 @@ template <bool kAnyHit>
 __global__ void __launch_bounds__(kQueryThreads, 10)
     k_intersect_parked(SceneView sv, const float *__restrict__ org, const float *__restrict__ dir, const float *__restrict__ tmaxv,
                        const uint32_t *__restrict__ perm, uint32_t n, snch_hit *__restrict__ hits, uint8_t *__restrict__ found_out,
-                       unsigned long long *counter, int flush_lanes, int refill_lanes, int prefetch)
+                       unsigned long long *counter, int flush_lanes, int refill_lanes)
 {
     __shared__ StackEntry s_stk[kRStack][kQueryThreads];
     const int lane = threadIdx.x & 31;
@@ -1140,7 +1131,6 @@ __global__ void __launch_bounds__(kQueryThreads, 10)
                 if (sp < kRStack) s_stk[sp][threadIdx.x] = se;
                 else lstk[sp - kRStack] = se;
                 ++sp;
-                if (prefetch) prefetch_child(sv, r1);
             }
             node = kNone;
             if (h0 || h1)
@@ -1511,7 +1501,10 @@ static void launch_intersect_kernel(const SceneView &v, const QueryTuning &t, co
                                     uint32_t n, snch_hit *hits, uint8_t *found, bool any_hit, unsigned long long *counter, cudaStream_t st,
                                     QueryCounters *qc)
 {
-    if (t.ray_kernel == 0)
+    // A batch that does not fill the machine (one ray per lane: config C1, 64K rays) runs as long as its longest ray; there the
+    // plain per-lane walk with leaves tested where they are met has the shortest step (0.087 vs 0.104 ms on C1), so it keeps
+    // small batches.  ("query.ray_kernel" = 0 / 2 selects it / the parked walk for every batch: the A/B of the knob tests.)
+    if (t.ray_kernel == 0 || (t.ray_kernel == 1 && n < (1u << 20)))
     {
         if (qc) qc->last_kernel = "k_intersect";
         if (any_hit) k_intersect<true><<<persistent_grid(k_intersect<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter);
@@ -1519,16 +1512,11 @@ static void launch_intersect_kernel(const SceneView &v, const QueryTuning &t, co
         return;
     }
     if (qc) qc->last_kernel = "k_intersect_parked";
-    // a batch that does not fill the machine (one ray per lane, config C1) runs as long as its longest ray: nobody waits there —
-    // a parked leaf is tested at once and a finished lane draws at once
-    const bool small = n < (1u << 20);
-    const int fl = small ? 1 : (t.ray_flush < 1 ? 1 : t.ray_flush), rl = small ? 1 : (t.ray_refill < 1 ? 1 : t.ray_refill);
+    const int fl = t.ray_flush < 1 ? 1 : t.ray_flush, rl = t.ray_refill < 1 ? 1 : t.ray_refill;
     if (any_hit)
-        k_intersect_parked<true><<<persistent_grid(k_intersect_parked<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl,
-                                                                                                           t.ray_prefetch);
+        k_intersect_parked<true><<<persistent_grid(k_intersect_parked<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
     else
-        k_intersect_parked<false><<<persistent_grid(k_intersect_parked<false>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl,
-                                                                                                             t.ray_prefetch);
+        k_intersect_parked<false><<<persistent_grid(k_intersect_parked<false>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
 }
 int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, const float *d, const float *tmax, uint64_t n, snch_hit *hits,
                      uint8_t *found, int any_hit, unsigned char *scratch, cudaStream_t st, QueryCounters *qc)

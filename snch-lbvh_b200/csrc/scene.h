@@ -22,7 +22,7 @@ struct QueryTuning
                             // 1 = Morton order of the origins, 2 = direction octant, then origin
     int cone_filter = 1;    // silhouette normal-cone test: 0 = the reference's libm chain verbatim, 1 = guard-banded sine-space filter on
                             // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
-    int sil_flush = 32;     // silhouette: queued leaves of a warp that trigger their tests (1..32; fewer = bounds tighten sooner, tests run on fewer lanes)
+    int sil_flush = 24;     // silhouette: queued leaves of a warp that trigger their tests (1..32; fewer = bounds tighten sooner, tests run on fewer lanes)
     int sil_tail = 4;       // silhouette: once the batch is handed out, a warp with at most this many walking lanes finishes them
                             // cooperatively, one query at a time on 32 lanes (0 = never)
     int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical
@@ -30,7 +30,8 @@ struct QueryTuning
     int wide_max_n_sil = 262144; // silhouette: the same for k_silhouette_wide (measured crossover 0.25-0.5M queries)
     int seed = 1;           // closest point: bit 0 = bound each query by the triangle that answered the lane's previous query;
                             // bit 1 = switch the per-triangle lower bound OFF (A/B)
-    int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked), 0 = leaves tested inline (k_intersect)
+    int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked; batches under 1M rays keep k_intersect),
+                            // 0 = leaves tested where they are met (k_intersect) for every batch, 2 = parked leaves for every batch
     int ray_flush = 8;      // k_intersect_parked: parked lanes of a warp that trigger the triangle tests
     int ray_refill = 8;
     int ray_prefetch = 1;   // k_intersect_parked: ask L2 for the record of a child when it is pushed     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
@@ -97,7 +98,7 @@ struct snch_scene
     // stats
     float build_ms = 0.f, adjacency_ms = 0.f;
     uint32_t opt_print_collision = 0, opt_refit_only = 0;
-    int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds at 8 CTAs/SM, 2 = the same at 6 CTAs/SM (no spills), 0 = one climbing thread per leaf
+    int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds (default), 0 = one climbing thread per leaf
 };
 
 namespace snch

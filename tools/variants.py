@@ -53,14 +53,14 @@ def main():
         return best, out
 
     defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0,
-                "query.sort_radius": 2, "query.sil_tail": 4, "query.sil_flush": 32, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
-                "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 8, "query.ray_prefetch": 1}
+                "query.sort_radius": 2, "query.sil_tail": 4, "query.sil_flush": 24, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
+                "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 8}
     settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("no_seed", {"query.seed": 0}),
-                ("sil_flush8", {"query.sil_flush": 8}), ("sil_flush16", {"query.sil_flush": 16}), ("sil_flush24", {"query.sil_flush": 24}), ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
+                ("sil_flush8", {"query.sil_flush": 8}), ("sil_flush16", {"query.sil_flush": 16}), ("sil_flush32", {"query.sil_flush": 32}), ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
                 ("sil_tail31", {"query.sil_tail": 31}), ("radius_none", {"query.sort_radius": 0}), ("radius_asc", {"query.sort_radius": 1}),
                 ("sil_bps7", {"query.blocks_per_sm": 7}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
                 ("ray_v1", {"query.ray_kernel": 0}), ("ray_v1_sorted", {"query.ray_kernel": 0, "query.sort_rays": 1}), ("ray_sorted", {"query.sort_rays": 1}),
-                ("ray_octant", {"query.sort_rays": 2}), ("ray_noprefetch", {"query.ray_prefetch": 0}), ("ray_flush1", {"query.ray_flush": 1}), ("ray_flush4", {"query.ray_flush": 4}),
+                ("ray_octant", {"query.sort_rays": 2}), ("ray_flush1", {"query.ray_flush": 1}), ("ray_flush4", {"query.ray_flush": 4}),
                 ("ray_flush12", {"query.ray_flush": 12}), ("ray_flush16", {"query.ray_flush": 16}), ("ray_flush24", {"query.ray_flush": 24}),
                 ("ray_refill1", {"query.ray_refill": 1}), ("ray_refill2", {"query.ray_refill": 2}), 
                 ("ray_refill4", {"query.ray_refill": 4}), ("ray_refill16", {"query.ray_refill": 16}), ("ray_f4_r2", {"query.ray_flush": 4, "query.ray_refill": 2}),
@@ -107,7 +107,7 @@ def main():
     # build: the refit kernel variants (identical arenas are asserted by tests/test_gpu_build.py; here only the time)
     build = {}
     if args.sets == "all" or "build" in args.sets.split(","):
-        for name, rk in (("refit_coop_8cta", 1), ("refit_coop_6cta", 2), ("refit_per_thread", 0)):
+        for name, rk in (("refit_coop", 1), ("refit_per_thread", 0)):
             sc.set_option("build.refit_kernel", rk)
             ts = []
             for _ in range(6):
