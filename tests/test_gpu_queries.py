@@ -69,9 +69,12 @@ def test_closest_silhouette_edge_and_point(scene, meshes, flip):
     check_silhouette_edges(q, dist, edge, pt, orc, flip, r_max=rmax)
 
 
-def test_rays_closest_hit(scene):
+@pytest.mark.parametrize("ray_kernel", [1, 2])  # 1: a batch this small takes k_intersect; 2: k_intersect_parked for every batch
+def test_rays_closest_hit(scene, ray_kernel):
     _, sc, orc, q, d = scene
+    sc.set_option("query.ray_kernel", ray_kernel)
     found, hits = sc.intersect(q, d)
+    sc.set_option("query.ray_kernel", 1)
     both = check_rays(found, hits, q, d, None, orc)
     # the reported primitive really is hit at the reported t (ties between triangles sharing an edge are legal, Q4)
     f_b, t_b, _, _ = orc.ray(q[both], d[both], brute=True)
@@ -81,13 +84,16 @@ def test_rays_closest_hit(scene):
     assert np.all(u >= 0) and np.all(v >= 0) and np.all(u + v <= 1 + 1e-6)
 
 
-def test_rays_tmax_and_any_hit(scene):
+@pytest.mark.parametrize("ray_kernel", [1, 2])
+def test_rays_tmax_and_any_hit(scene, ray_kernel):
     _, sc, orc, q, d = scene
     tm = np.full(len(q), 0.7, np.float32)
+    sc.set_option("query.ray_kernel", ray_kernel)
     found, hits = sc.intersect(q, d, t_max=tm)
     check_rays(found, hits, q, d, tm, orc)
     assert np.all(hits["t"][found.astype(bool)] < 0.7)
     any_found, _ = sc.intersect(q, d, t_max=tm, any_hit=True)
+    sc.set_option("query.ray_kernel", 1)
     assert np.array_equal(any_found.astype(bool), orc.ray(q, d, tm, any_hit=True, nthreads=8)[0].astype(bool))
     assert np.mean(any_found.astype(bool) == found.astype(bool)) > 0.9998  # (any-hit stops at the first hit in walk order: Q4 ties aside, same flag)
 
