@@ -423,6 +423,21 @@ def other_config(cfg, job, pkg, m, stream, peak, mv):
                 b_q = 12 + 12 + 16 + 1 + 64.0 * e["V"] + 64.0 * e["L"]
                 out["roofline"] = kernel_roofline(scene, "ray", n, b_q, e["V"], e["L"], peak, "measured", ms,
                                                   "B_q = 41 B of ray in / hit out + 64 B per must-visit node + 64 B per must-test triangle")
+            if job.rank == 0:
+                try:  # the reference's CUDA path on the same mesh and rays (a 2M-ray sample; kernel time from its own CUDA events)
+                    from oracle import RefScene, ref_available
+                    if ref_available("cuda"):
+                        with quiet_stdout():
+                            ns = min(1 << 21, n)
+                            ref = RefScene(v, f, "cuda")
+                            qh, dh = q[:ns].cpu().numpy(), d[:ns].cpu().numpy()
+                            ref.ray(qh, dh)
+                            ref.ray(qh, dh)
+                            out["reference_cuda_ray_mqps"] = ns / ref.last_ms / 1e3
+                            out["ray_speedup_vs_reference_cuda_per_gpu"] = out["ray_mqps"] / job.world / out["reference_cuda_ray_mqps"]
+                            del ref
+                except Exception as ex:
+                    out["reference_cuda_error"] = repr(ex)
         else:
             u = torch.from_numpy(m.uniforms(n, 3, seed=231 + job.rank)).to(dev)
             ms = timed_steps(job, stream, lambda: scene.wost_step(q, d, u, stream=stream), 2, 1)

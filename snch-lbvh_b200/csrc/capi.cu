@@ -308,9 +308,10 @@ int snch_scene3_create(const float *xyz, uint32_t n_verts, const int32_t *tri, u
         return SNCH_ERR_INVALID;
     }
     *out = nullptr;
-    if (n_tris > 0x7FFFFFFFu / 2)
-    {
-        set_error("snch_scene3_create: too many triangles for 32-bit node ids");
+    if (n_tris > (1u << 27))
+    { // child references keep bit 31 as the leaf flag and a leaf's edge payload is (first edge id << 2 | count): with at most
+      // 3 edges per triangle that bounds a scene at 2^27 = 134M triangles (a 76 GB arena)
+        set_error("snch_scene3_create: more than 2^27 triangles (32-bit child references / edge payloads)");
         return SNCH_ERR_INVALID;
     }
     for (uint64_t i = 0; i < (uint64_t)3 * n_tris; ++i)

@@ -408,6 +408,37 @@ int main(int argc, char **argv)
         std::printf("CHECK silhouette2d_vs_batched_mismatch_frac %.3e\n", mismatch_frac(host(o[1], n2), host(bs, n2), 1e-5));
         std::printf("CHECK ray2d_vs_batched_mismatch_frac %.3e\n", mismatch_frac(host(o[2], n2), bt, 1e-5));
     }
+    { // replication behind the C-ABI from C++ (snch_scene_replicate_local): a replica on this device and, when the box has one,
+      // on a second GPU answers a batched query bit-identically
+        int ndev = 0;
+        CUDA_OK(cudaGetDeviceCount(&ndev));
+        const int devs[2] = {0, 1};
+        const int nrep = ndev > 1 ? 2 : 1;
+        snch_scene *reps[2] = {nullptr, nullptr};
+        if (snch_scene_replicate_local(sc.native_handle(), devs, nrep, reps) != 0)
+        {
+            std::printf("replicate failed: %s\n", snch_last_error());
+            return 1;
+        }
+        size_t diff = 0;
+        std::vector<float> want(n);
+        CUDA_OK(cudaMemcpy(want.data(), bsil, n * 4, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < nrep; ++r)
+        {
+            std::vector<float> got(n);
+            std::vector<float3> hq(q.begin(), q.end());
+            // host pointers: the library stages them on the replica's own device
+            if (snch_closest_silhouette_batch(reps[r], &hq[0].x, nullptr, nullptr, (uint64_t)n, got.data(), nullptr, nullptr, nullptr) != 0)
+            {
+                std::printf("replica query failed: %s\n", snch_last_error());
+                return 1;
+            }
+            for (int i = 0; i < n; ++i) diff += std::memcmp(&got[i], &want[i], 4) != 0;
+            snch_scene_destroy(reps[r]);
+        }
+        CUDA_OK(cudaSetDevice(0));
+        std::printf("CHECK replicas %d\nCHECK replica_silhouette_diff %zu\n", nrep, diff);
+    }
     std::printf("DROPIN_OK\n");
     return 0;
 }

@@ -47,6 +47,8 @@ def test_cpp_dropin_api(meshes, tmp_path, mesh):
     assert c["generic_node_diff"] == 0 and c["generic_aabb_diff"] == 0
     assert c["generic_cone_bad"] <= 1e-3 * c["nodes"]
     # 2-D scene through the same headers
+    # snch_scene_replicate_local from C++: the replicas answer bit-identically
+    assert c["replicas"] >= 1 and c["replica_silhouette_diff"] == 0
     assert c["seg2d"] == 449 and c["nodes2d"] == 2 * 449 - 1
     assert c["closest2d_vs_brute_worst_rel"] <= 1e-5 and c["ray2d_vs_brute_mismatch_frac"] <= 1e-3
     assert c["silhouette2d_vs_brute_mismatch_frac"] <= 2e-2  # cone pruning is only approximately conservative in the reference too

@@ -30,6 +30,8 @@ KEYS = [
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__sass_average_branch_targets_threads_uniform.pct",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
 ]
 
 
@@ -85,6 +87,14 @@ def full(src, out):
         import re
         short = re.sub(r"<.*", "", d["kernel"].split("::")[-1]).replace("void ", "").strip()
         traffic[short + "_bytes_per_launch"] = tb
+        # per-kernel entry bench.py scales to its own launch: dram bytes, the batch size of the capture (SNCH_NCU_QUERIES, default
+        # the 16.7M-query bench batch) and the L1 global-load sectors per query (what the kernel actually pulls through L1)
+        nq = int(os.environ.get("SNCH_NCU_QUERIES", str(1 << 24)))
+        ent = {"dram_bytes": tb, "queries": nq, "source": os.path.basename(out)}
+        sk = "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"
+        if sk in d:
+            ent["l1_global_load_sectors_per_query"] = d[sk][0] / nq
+        traffic[short] = ent
         print(name, {k: v for k, v in d.items() if k in ("kernel", "gpu__time_duration.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
                                                            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct")}, "dram bytes", tb)
     if traffic:

@@ -56,7 +56,7 @@ def main():
                 "query.sort_radius": 2, "query.sil_tail": 4, "query.sil_flush": 24, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
                 "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 8}
     settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("no_seed", {"query.seed": 0}),
-                ("sil_flush8", {"query.sil_flush": 8}), ("sil_flush16", {"query.sil_flush": 16}), ("sil_flush32", {"query.sil_flush": 32}), ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
+                ("sil_flush8", {"query.sil_flush": 8}), ("sil_flush16", {"query.sil_flush": 16}), ("sil_flush32", {"query.sil_flush": 32}), ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail4", {"query.sil_tail": 4}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
                 ("sil_tail31", {"query.sil_tail": 31}), ("radius_none", {"query.sort_radius": 0}), ("radius_asc", {"query.sort_radius": 1}),
                 ("sil_bps7", {"query.blocks_per_sm": 7}), ("no_sort", {"query.sort_min_n": 0}), ("no_cone_filter", {"query.cone_filter": 0}),
                 ("ray_v1", {"query.ray_kernel": 0}), ("ray_v1_sorted", {"query.ray_kernel": 0, "query.sort_rays": 1}), ("ray_sorted", {"query.sort_rays": 1}),
