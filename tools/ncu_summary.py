@@ -81,7 +81,7 @@ def full(src, out):
             res.append(d)
         name = os.path.basename(rep)[:-8]
         json.dump(res, open(f"{out}_ncu_{name}.json", "w"), indent=1)
-        d = res[-1]
+        d = max(res, key=lambda r: r.get("gpu__time_duration.sum", [0.0, ""])[0] * {"ms": 1e3, "us": 1.0, "ns": 1e-3, "s": 1e6}.get(r.get("gpu__time_duration.sum", [0, "us"])[1], 1.0))  # the full-size launch of the capture
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
         tb = sum(d[k][0] * scale[d[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in d)
         import re
