@@ -52,6 +52,7 @@ struct Feeder
 {
     uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
     bool exhausted;     // the global counter ran past n
+    uint32_t chunk = 0; // queries per draw (0 = chunk_for(n))
 };
 constexpr uint64_t kScratchHeader = 256; // work counters (u64 x 8: [0] batch, [1] tail list length, [2] tail work) + query box (6 ordered ints at +64)
 constexpr uint64_t kTailEntries = 1u << 18; // tail list of the silhouette kernel: one (slot, bound) pair per resident lane at most
@@ -62,14 +63,15 @@ SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane,
 {
     if (f.next == f.end && !f.exhausted)
     {
+        const uint32_t ch = f.chunk ? f.chunk : chunk_for(n);
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)chunk_for(n));
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)ch);
         base = __shfl_sync(kFull, base, 0);
         if (base >= n) f.exhausted = true;
         else
         {
             f.next = (uint32_t)base;
-            f.end = (uint32_t)min((unsigned long long)n, base + chunk_for(n));
+            f.end = (uint32_t)min((unsigned long long)n, base + ch);
         }
     }
     const uint32_t avail = f.end - f.next;
