@@ -23,12 +23,10 @@ def main():
     _, dcp = sc.closest_point(q_all)
     r_all = (dcp * s_all).contiguous()
     stream = torch.cuda.current_stream()
-    settings = [("default", {}), ("tail0", {"query.sil_tail": 0}), ("tail8", {"query.sil_tail": 8}), ("tail12", {"query.sil_tail": 12}),
-                ("tail16", {"query.sil_tail": 16}), ("tail8_chunk32", {"query.sil_tail": 8, "query.sil_chunk": 32}),
-                ("tail8_chunk16", {"query.sil_tail": 8, "query.sil_chunk": 16}), ("tail8_bps6", {"query.sil_tail": 8, "query.blocks_per_sm": 6}),
-                ("tail8_bps4", {"query.sil_tail": 8, "query.blocks_per_sm": 4}), ("tail8_noradius", {"query.sil_tail": 8, "query.sort_radius": 0}),
-                ("tail8_bits30", {"query.sil_tail": 8, "query.sort_bits": 30})]
-    defaults = {"query.sil_tail": 4, "query.sil_chunk": 0, "query.blocks_per_sm": 0, "query.sort_radius": 2, "query.sort_bits": 24}
+    settings = [("default", {}), ("fixed_chunks", {"query.sil_guided": 0}), ("fixed_chunk16", {"query.sil_guided": 0, "query.sil_chunk": 16}),
+                ("guided_chunk32", {"query.sil_chunk": 32}), ("tail0", {"query.sil_tail": 0}), ("tail4", {"query.sil_tail": 4}), ("tail12", {"query.sil_tail": 12}),
+                ("tail16", {"query.sil_tail": 16})]
+    defaults = {"query.sil_tail": 8, "query.sil_chunk": 0, "query.sil_guided": 1, "query.blocks_per_sm": 0, "query.sort_radius": 2, "query.sort_bits": 24}
     out = {}
     for n in (1 << 24, 1 << 23, 1 << 22, 1 << 21):
         q, r = q_all[:n].contiguous(), r_all[:n].contiguous()
@@ -52,10 +50,26 @@ def main():
             sc.set_option("query.time_kernels", 0)
             row[name] = {"step_ms": best, "traversal_ms_mean": kern, "mqps": n / best / 1e3, "ideal_ms_from_16M": None}
             print(n, name, json.dumps(row[name]), file=sys.stderr, flush=True)
+        dd = torch.from_numpy(m.unit_directions(n, seed=77)).cuda()
+        for k, val in defaults.items():
+            sc.set_option(k, val)
+        for kind, fn in (("closest", lambda: sc.closest_point(q)), ("ray", lambda: sc.intersect(q, dd))):
+            fn()
+            torch.cuda.synchronize()
+            best = 1e30
+            for _ in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                fn()
+                b.record(stream)
+                torch.cuda.synchronize()
+                best = min(best, a.elapsed_time(b))
+            row[kind] = {"step_ms": best, "mqps": n / best / 1e3, "ideal_ms_from_16M": None}
+            print(n, kind, json.dumps(row[kind]), file=sys.stderr, flush=True)
         out[str(n)] = row
-    base = out[str(1 << 24)]["default"]["step_ms"]
     for n, row in out.items():
         for name in row:
+            base = out[str(1 << 24)][name if name in ("closest", "ray") else "default"]["step_ms"]
             row[name]["ideal_ms_from_16M"] = base * int(n) / (1 << 24)
     print(json.dumps(out, indent=1))
 
