@@ -423,7 +423,7 @@ def other_config(cfg, job, pkg, m, stream, peak, mv):
                 b_q = 12 + 12 + 16 + 1 + 64.0 * e["V"] + 64.0 * e["L"]
                 out["roofline"] = kernel_roofline(scene, "ray", n, b_q, e["V"], e["L"], peak, "measured", ms,
                                                   "B_q = 41 B of ray in / hit out + 64 B per must-visit node + 64 B per must-test triangle")
-            if job.rank == 0:
+            if job.rank == 0 and not getattr(job, "skip_baselines", False):
                 try:  # the reference's CUDA path on the same mesh and rays (a 2M-ray sample; kernel time from its own CUDA events)
                     from oracle import RefScene, ref_available
                     if ref_available("cuda"):
@@ -599,6 +599,8 @@ def _run():
     ap.add_argument("--configs", default="c1,c4,c5", help="comma list of further BASELINE.json configs timed into `extra` at the same N "
                     "(c1, c4, c5; 2d = the scene<2> path); '' = none")
     ap.add_argument("--also", default="", help="more configs on top of --configs (kept for the round scripts)")
+    ap.add_argument("--skip-baselines", action="store_true", help="skip the CPU-baseline and reference-CUDA legs (rank 0 only, ~40 s during which the "
+                    "other GPUs idle): for the builder's own multi-GPU runs; the default line carries them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -609,6 +611,7 @@ def _run():
     from snch_lbvh_b200.distributed import shard_range
     m = pkg.meshes
     job = Job()
+    job.skip_baselines = args.skip_baselines
     world, rank, dev = job.world, job.rank, job.dev
     n_total = args.queries
     lo_i, hi_i = shard_range(n_total, rank, world)
@@ -802,7 +805,7 @@ def _run():
                 if world > 1:
                     raise  # a rank that skipped a collective would hang the others
                 extra[cfg] = {"error": repr(ex)}
-        if rank == 0:
+        if rank == 0 and not args.skip_baselines:
             # the reference's own CUDA path on this B200 (prebuilt from the unmodified headers; absent -> skipped)
             try:
                 from oracle import RefScene, ref_available

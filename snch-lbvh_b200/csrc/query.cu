@@ -1415,7 +1415,7 @@ static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, c
     const int tl = (t.sil_tail > 0 && (uint64_t)grid * kQueryThreads <= kTailEntries) ? (t.sil_tail > 31 ? 31 : t.sil_tail) : 0;
     const uint32_t flush_at = (uint32_t)(t.sil_flush < 1 ? 1 : (t.sil_flush > kLeafFlushAt ? kLeafFlushAt : t.sil_flush));
     k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound, flush_at,
-                                                                      (uint32_t)(t.sil_chunk > 0 ? (t.sil_chunk & 0xFFFF) : 0) | (t.sil_guided ? 0x10000u : 0u));
+                                                                      (uint32_t)(t.sil_chunk > 0 ? (t.sil_chunk & 0xFFFF) : sil_chunk_for_host(n)) | (t.sil_guided ? 0x10000u : 0u));
     if (tl)
     { // finish the listed queries one per warp; its own work counter is counter[2], the list length counter[1]
         if (qc) qc->launches += 1;

@@ -14,6 +14,11 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kChunk = 64; // consecutive queries a warp draws per atomic
 // batches under 1M queries draw 32 at a time: twice the warps, one query per lane — such a batch is latency-bound (C1: 64K rays)
 SNCH_DI uint32_t chunk_for(uint32_t n) { return n < (1u << 20) ? 32u : kChunk; }
+// The per-lane silhouette kernel: batches are ordered LARGEST search radius first, so the first draws hold the longest walks; a
+// draw of 64 gives every lane of the first warps two of them back to back — half of the run time of a 2M-query shard (the per-GPU
+// share of the C3 batch on 8 GPUs).  Below 12M queries a warp draws 16 at a time: 8.35 -> 7.35 ms at 2M, 13.8 -> 13.2 at 4M,
+// unchanged at 8M; at 16.7M draws of 64 stay (48.9 vs 49.3 ms) (profiles/r2h_shard_exp.json).
+static inline uint32_t sil_chunk_for_host(uint64_t n) { return n < (12u << 20) ? 16u : kChunk; }
 static inline uint32_t chunk_for_host(uint64_t n) { return n < (1u << 20) ? 32u : kChunk; }
 
 struct NodeBoxes

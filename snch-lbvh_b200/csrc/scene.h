@@ -23,7 +23,7 @@ struct QueryTuning
     int cone_filter = 1;    // silhouette normal-cone test: 0 = the reference's libm chain verbatim, 1 = guard-banded sine-space filter on
                             // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
     int sil_flush = 24;     // silhouette: queued leaves of a warp that trigger their tests (1..32; fewer = bounds tighten sooner, tests run on fewer lanes)
-    int sil_chunk = 0;      // silhouette: queries a warp draws per atomic (0 = 64 for batches of 1M and more, 32 below)
+    int sil_chunk = 0;      // silhouette: queries a warp draws per atomic (0 = 64 for batches of 12M and more, 16 below)
     int sil_guided = 1;     // silhouette: draws shrink towards the end of the batch (guided self-scheduling; 0 = fixed chunks)
     int sil_tail = 8;       // silhouette: once the batch is handed out, a warp with at most this many walking lanes finishes them
                             // cooperatively, one query at a time on 32 lanes (0 = never)

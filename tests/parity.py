@@ -127,14 +127,28 @@ def check_silhouette_edges(q, dist, edge, point, orc, flip=False, r_max=None):
 
 
 def check_rays(found, hits, q, d, tmax, orc):
-    """Hit flags, t, (u, v) and the triangle BIT-IDENTICAL to the oracle's walk (the kernels visit leaves in the reference's
-    order under its pop-time rejection)."""
+    """Hit flags and t BIT-IDENTICAL to the oracle's walk; the triangle and (u, v) too, except on exact ties (Q4: two
+    triangles sharing an edge are hit at the same t — the kernel that tests leaves where it meets them reaches them in another
+    order than the reference's stack): there the returned triangle must attain that t, recomputed here in double precision."""
     found = np.asarray(found).astype(bool)
     f_o, t_o, uv_o, p_o = orc.ray(q, d, tmax, nthreads=8)
     f_o = f_o.astype(bool)
     assert np.array_equal(found, f_o), f"ray hit flags differ on {np.count_nonzero(found != f_o)} of {len(found)} rays"
     assert np.array_equal(bits(hits["t"]), bits(t_o)), f"ray t differs on {np.count_nonzero(bits(hits['t']) != bits(t_o))} rays"
-    assert np.array_equal(hits["prim"], p_o), f"ray triangle differs on {np.count_nonzero(hits['prim'] != p_o)} rays"
-    assert np.array_equal(bits(hits["u"]), bits(uv_o[:, 0])) and np.array_equal(bits(hits["v"]), bits(uv_o[:, 1])), "ray (u, v) differ"
+    prim = np.asarray(hits["prim"]).astype(np.uint32)
+    same = prim == p_o
+    assert np.array_equal(bits(hits["u"])[same], bits(uv_o[:, 0])[same]) and np.array_equal(bits(hits["v"])[same], bits(uv_o[:, 1])[same]), "ray (u, v) differ"
+    tie = np.nonzero(~same)[0]
+    assert len(tie) <= max(1, len(found) // 1000), f"ray triangle differs on {len(tie)} rays"
+    if len(tie):
+        tri = orc.verts[orc.tris[prim[tie]]].astype(np.float64)
+        o64, d64 = np.asarray(q, np.float64)[tie], np.asarray(d, np.float64)[tie]
+        e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+        h = np.cross(d64, e2)
+        det = np.einsum("ij,ij->i", e1, h)
+        sv = o64 - tri[:, 0]
+        qv = np.cross(sv, e1)
+        t64 = np.einsum("ij,ij->i", e2, qv) / det
+        assert rel_close(t64, t_o[tie], 1e-5, 1e-6).all(), "a differing ray triangle does not attain the hit distance"
     assert np.all(np.isinf(np.asarray(hits["t"])[~found]))
     return found
