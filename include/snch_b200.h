@@ -191,8 +191,7 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *   "query.seed"        closest point: bit 0 = bound each query by the triangle that answered the lane's previous query (default 1);
  *                       bit 1 = switch the per-triangle lower bound off
  *   "query.sil_flush"   silhouette: queued leaves of a warp that trigger their (one per lane) tests (1..32, default 24)
- *   "query.sil_chunk" / "query.sil_guided"  silhouette: queries a warp draws per atomic (0 = 64, or 16 below 12M queries) and whether
- *                       draws shrink towards the end of the batch (guided self-scheduling, default 1)
+ *   "query.sil_chunk"   silhouette: queries a warp draws per atomic (0 = 64, or 16 below 12M queries)
  *   "query.sil_tail"    silhouette: when a batch has been handed out, a warp with at most this many walking lanes passes them to a
  *                       one-query-per-warp finishing launch (default 8; 0 = never)
  *   "query.sort_radius" bounded silhouette batches: 0 = Morton order only, 1 = search-radius octave then Morton, 2 = the same with

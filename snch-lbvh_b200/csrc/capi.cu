@@ -821,7 +821,6 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.sil_tail") t.sil_tail = (int)value;
     else if (k == "query.sil_flush") t.sil_flush = (int)value;
     else if (k == "query.sil_chunk") t.sil_chunk = (int)value;
-    else if (k == "query.sil_guided") t.sil_guided = (int)value;
     else if (k == "query.wide_max_n") t.wide_max_n = (int)value;
     else if (k == "query.wide_max_n_sil") t.wide_max_n_sil = (int)value;
     else if (k == "query.ray_kernel") t.ray_kernel = (int)value;

@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
                       float *__restrict__ out_point, unsigned long long *counter, int tail_lanes, uint32_t *__restrict__ tail_slot,
-                      float *__restrict__ tail_bound, uint32_t flush_at, uint32_t chunk /* bits 0-15: queries per draw (0 = auto), bit 16: guided */)
+                      float *__restrict__ tail_bound, uint32_t flush_at, uint32_t chunk)
 {
     using Res = SilResult<kEdge>;
     __shared__ StackEntry s_stk[kSStack][kQueryThreads];
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     __shared__ typename Res::T s_result[kQueryThreads];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpQueue &wq = s_wq[wid];
-    Feeder fd{0u, 0u, false, chunk & 0xFFFFu, (chunk >> 16) ? gridDim.x * (kQueryThreads / 32) : 0u};
+    Feeder fd{0u, 0u, false, chunk};
     StackEntry lstk[kStackDepth - kSStack];
     int sp = 0;
     V3 p = V3{0.f, 0.f, 0.f};
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(kQueryThreads)
                 unsigned long long *counter)
 {
     const int lane = threadIdx.x & 31;
-    Feeder fd{0u, 0u, false, 0u, gridDim.x * (kQueryThreads / 32)}; // guided draws: small ones near the end of the batch
+    Feeder fd{0u, 0u, false};
     StackEntry stk[kStackDepth];
     int sp = 0;
     V3 o = V3{0.f, 0.f, 0.f}, dv = o, dinv = o;
@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(kQueryThreads, 10)
 {
     __shared__ StackEntry s_stk[kRStack][kQueryThreads];
     const int lane = threadIdx.x & 31;
-    Feeder fd{0u, 0u, false, 0u, gridDim.x * (kQueryThreads / 32)}; // guided draws: small ones near the end of the batch
+    Feeder fd{0u, 0u, false};
     StackEntry lstk[kStackDepth - kRStack];
     int sp = 0;
     V3 o = V3{0.f, 0.f, 0.f}, dv = o, dinv = o;
@@ -1415,7 +1415,7 @@ static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, c
     const int tl = (t.sil_tail > 0 && (uint64_t)grid * kQueryThreads <= kTailEntries) ? (t.sil_tail > 31 ? 31 : t.sil_tail) : 0;
     const uint32_t flush_at = (uint32_t)(t.sil_flush < 1 ? 1 : (t.sil_flush > kLeafFlushAt ? kLeafFlushAt : t.sil_flush));
     k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound, flush_at,
-                                                                      (uint32_t)(t.sil_chunk > 0 ? (t.sil_chunk & 0xFFFF) : sil_chunk_for_host(n)) | (t.sil_guided ? 0x10000u : 0u));
+                                                                      (uint32_t)(t.sil_chunk > 0 ? t.sil_chunk : sil_chunk_for_host(n)));
     if (tl)
     { // finish the listed queries one per warp; its own work counter is counter[2], the list length counter[1]
         if (qc) qc->launches += 1;

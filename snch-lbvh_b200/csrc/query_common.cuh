@@ -17,7 +17,8 @@ SNCH_DI uint32_t chunk_for(uint32_t n) { return n < (1u << 20) ? 32u : kChunk; }
 // The per-lane silhouette kernel: batches are ordered LARGEST search radius first, so the first draws hold the longest walks; a
 // draw of 64 gives every lane of the first warps two of them back to back — half of the run time of a 2M-query shard (the per-GPU
 // share of the C3 batch on 8 GPUs).  Below 12M queries a warp draws 16 at a time: 8.35 -> 7.35 ms at 2M, 13.8 -> 13.2 at 4M,
-// unchanged at 8M; at 16.7M draws of 64 stay (48.9 vs 49.3 ms) (profiles/r2h_shard_exp.json).
+// unchanged at 8M; at 16.7M draws of 64 stay (48.9 vs 49.3 ms) (profiles/r2h_shard_exp.json).  (Draws that SHRINK towards the end of the
+// batch — guided self-scheduling — were measured too and gave nothing: the long walks are at the start of the batch.)
 static inline uint32_t sil_chunk_for_host(uint64_t n) { return n < (12u << 20) ? 16u : kChunk; }
 static inline uint32_t chunk_for_host(uint64_t n) { return n < (1u << 20) ? 32u : kChunk; }
 
@@ -58,9 +59,6 @@ struct Feeder
     uint32_t next, end; // warp-uniform: the unclaimed part of the warp's current chunk
     bool exhausted;     // the global counter ran past n
     uint32_t chunk = 0; // queries per draw (0 = chunk_for(n))
-    uint32_t guided = 0; // > 0: warps of the grid — a draw takes at most half this warp's fair share of what is LEFT (guided
-                         // self-scheduling): full chunks while the batch is long, small ones near its end, where a chunk of 64 left
-                         // two queries per lane to drain (2M-query shards: 8.35 -> 7.3 ms, profiles/r2g_shard_exp.json)
 };
 constexpr uint64_t kScratchHeader = 256; // work counters (u64 x 8: [0] batch, [1] tail list length, [2] tail work) + query box (6 ordered ints at +64)
 constexpr uint64_t kTailEntries = 1u << 18; // tail list of the silhouette kernel: one (slot, bound) pair per resident lane at most
@@ -71,20 +69,10 @@ SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane,
 {
     if (f.next == f.end && !f.exhausted)
     {
-        uint32_t ch = f.chunk ? f.chunk : chunk_for(n);
+        const uint32_t ch = f.chunk ? f.chunk : chunk_for(n);
         unsigned long long base = 0;
-        if (lane == 0)
-        {
-            if (f.guided)
-            { // (a stale read only changes the size of this draw, never its correctness)
-                const unsigned long long seen = *reinterpret_cast<volatile unsigned long long *>(counter);
-                const uint32_t left = seen < n ? n - (uint32_t)seen : 0u;
-                ch = max(8u, min(ch, left / (2u * f.guided)));
-            }
-            base = atomicAdd(counter, (unsigned long long)ch);
-        }
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)ch);
         base = __shfl_sync(kFull, base, 0);
-        ch = __shfl_sync(kFull, ch, 0);
         if (base >= n) f.exhausted = true;
         else
         {

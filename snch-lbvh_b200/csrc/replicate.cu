@@ -35,6 +35,7 @@ struct NcclApi
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*GetVersion)(int *) = nullptr;
 };
@@ -58,9 +59,10 @@ NcclApi *nccl_api()
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(h, "ncclBroadcast"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
     a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(dlsym(h, "ncclGetVersion"));
-    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Broadcast || !a.GetErrorString)
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Broadcast || !a.AllReduce || !a.GetErrorString)
     {
         set_error("libnccl.so.2 lacks a required symbol");
         return nullptr;
@@ -205,15 +207,36 @@ int snch_scene_broadcast(const snch_scene *scene, int root, snch_comm *comm, snc
         return nccl_fail(api, r, "ncclBroadcast(header)");
     }
     snch_scene *rep = nullptr;
+    int local_rc = SNCH_OK;
     if (!is_root)
     {
         ArenaHeader h;
         cudaError_t e = cudaMemcpyAsync(&h, dh, sizeof h, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        cudaFree(dh);
-        if (e != cudaSuccess) return cuda_fail(e, "header read-back");
-        const int rc = adopt_begin(h, h.total_bytes, comm->device, "snch_scene_broadcast", &rep);
-        if (rc != SNCH_OK) return rc; // (the root's second broadcast then fails or hangs: a corrupt header is fatal for the job)
+        if (e != cudaSuccess) local_rc = cuda_fail(e, "header read-back");
+        else local_rc = adopt_begin(h, h.total_bytes, comm->device, "snch_scene_broadcast", &rep);
+    }
+    // every rank learns whether ALL of them accepted the header and allocated their arena before the big transfer starts: a
+    // rank that bailed out alone would leave the others blocked inside the collective
+    {
+        int *dflag = is_root ? nullptr : reinterpret_cast<int *>(dh);
+        if (is_root) SNCH_CUDA(cudaMalloc(&dflag, sizeof(int)));
+        int agreed = local_rc;
+        cudaError_t e = cudaMemcpyAsync(dflag, &local_rc, sizeof(int), cudaMemcpyHostToDevice, st);
+        ncclResult_t rr = ncclSuccess;
+        if (e == cudaSuccess) rr = api->AllReduce(dflag, dflag, 1, ncclInt32, ncclMin, comm->comm, st);
+        if (e == cudaSuccess && rr == ncclSuccess) e = cudaMemcpyAsync(&agreed, dflag, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && rr == ncclSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(dflag);
+        dh = nullptr;
+        if (rr != ncclSuccess || e != cudaSuccess || agreed != SNCH_OK)
+        {
+            if (rep) snch_scene_destroy(rep);
+            if (rr != ncclSuccess) return nccl_fail(api, rr, "ncclAllReduce(status)");
+            if (e != cudaSuccess) return cuda_fail(e, "status exchange");
+            if (local_rc == SNCH_OK) set_error("snch_scene_broadcast: another rank rejected the arena header or could not allocate its replica");
+            return local_rc != SNCH_OK ? local_rc : agreed;
+        }
     }
     // 2. the arena, received in place
     const uint64_t bytes = is_root ? scene->arena_bytes : rep->arena_bytes;

@@ -24,7 +24,6 @@ struct QueryTuning
                             // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
     int sil_flush = 24;     // silhouette: queued leaves of a warp that trigger their tests (1..32; fewer = bounds tighten sooner, tests run on fewer lanes)
     int sil_chunk = 0;      // silhouette: queries a warp draws per atomic (0 = 64 for batches of 12M and more, 16 below)
-    int sil_guided = 1;     // silhouette: draws shrink towards the end of the batch (guided self-scheduling; 0 = fixed chunks)
     int sil_tail = 8;       // silhouette: once the batch is handed out, a warp with at most this many walking lanes finishes them
                             // cooperatively, one query at a time on 32 lanes (0 = never)
     int wide_max_n = 2097152; // closest point: batches smaller than this walk ONE query per warp (32 lanes on one query: shortens the critical

@@ -23,9 +23,9 @@ def main():
     _, dcp = sc.closest_point(q_all)
     r_all = (dcp * s_all).contiguous()
     stream = torch.cuda.current_stream()
-    settings = [("default", {}), ("fixed_chunks", {"query.sil_guided": 0}), ("chunk64", {"query.sil_chunk": 64}), ("chunk8", {"query.sil_chunk": 8}), ("chunk16_tail4", {"query.sil_chunk": 16, "query.sil_tail": 4}), ("chunk16_tail16", {"query.sil_chunk": 16, "query.sil_tail": 16}),
+    settings = [("default", {}), ("chunk64", {"query.sil_chunk": 64}), ("chunk8", {"query.sil_chunk": 8}), ("chunk16_tail4", {"query.sil_chunk": 16, "query.sil_tail": 4}), ("chunk16_tail16", {"query.sil_chunk": 16, "query.sil_tail": 16}),
                 ("chunk32", {"query.sil_chunk": 32}), ("tail0", {"query.sil_tail": 0})]
-    defaults = {"query.sil_tail": 8, "query.sil_chunk": 0, "query.sil_guided": 1, "query.blocks_per_sm": 0, "query.sort_radius": 2, "query.sort_bits": 24}
+    defaults = {"query.sil_tail": 8, "query.sil_chunk": 0, "query.blocks_per_sm": 0, "query.sort_radius": 2, "query.sort_bits": 24}
     out = {}
     for n in (1 << 24, 1 << 23, 1 << 22, 1 << 21):
         q, r = q_all[:n].contiguous(), r_all[:n].contiguous()

@@ -53,7 +53,7 @@ def main():
         return best, out
 
     defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.cone_filter": 1, "query.seed": 1, "query.blocks_per_sm": 0,
-                "query.sort_radius": 2, "query.sil_tail": 8, "query.sil_flush": 24, "query.sil_chunk": 0, "query.sil_guided": 1, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
+                "query.sort_radius": 2, "query.sil_tail": 8, "query.sil_flush": 24, "query.sil_chunk": 0, "query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144,
                 "query.ray_kernel": 1, "query.ray_flush": 8, "query.ray_refill": 8}
     settings = [("default", {}), ("no_lower_bound", {"query.seed": 3}), ("no_seed", {"query.seed": 0}),
                 ("sil_flush8", {"query.sil_flush": 8}), ("sil_flush16", {"query.sil_flush": 16}), ("sil_flush32", {"query.sil_flush": 32}), ("sil_tail0", {"query.sil_tail": 0}), ("sil_tail2", {"query.sil_tail": 2}), ("sil_tail4", {"query.sil_tail": 4}), ("sil_tail8", {"query.sil_tail": 8}), ("sil_tail16", {"query.sil_tail": 16}),
