@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(kQueryThreads)
             { // both needed: enter the child most lanes are nearer to, keep the other with the lanes that want it
                 const unsigned near1 = __ballot_sync(kFull, (w0 && w1) ? (m1 < m0) : w1);
                 const bool first1 = 2 * __popc(near1) > __popc(b0 | b1);
-                stk[sp] = first1 ? make_uint2(r0, b0) : make_uint2(r1, b1);
+                if (lane == 0) stk[sp] = first1 ? make_uint2(r0, b0) : make_uint2(r1, b1); // (warp-uniform value: one writer)
+                __syncwarp();
                 ++sp;
                 node = first1 ? r1 : r0;
                 mask = first1 ? b1 : b0;
@@ -371,6 +372,7 @@ __global__ void __launch_bounds__(kQueryThreads)
                 if (sp == 0) break;
                 --sp;
                 const uint2 e = stk[sp];
+                __syncwarp(); // every lane has read the entry before a later push may overwrite the slot
                 node = e.x;
                 mask = e.y;
             }
@@ -723,6 +725,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         uint32_t qc = wq.count;
         if (qc >= flush_at || tail || __any_sync(kFull, pend && node == kNone))
         {
+            __syncwarp(); // every lane has read the count before lane 0 resets it below
             while (qc > 0)
             {
                 const uint32_t take = qc < 32u ? qc : 32u;
