@@ -566,7 +566,8 @@ SNCH_DI void sh_get(const RefitShared &sh, uint32_t id, Box &b, Cone &cn)
     cn.radius = sh.f[10][id];
 }
 // (8 resident CTAs at 64 registers with 56 B of spills beat 6 CTAs at 76 registers without: 0.488 vs 0.497 ms, profiles/r2e_variants.json)
-__global__ void __launch_bounds__(kRefitLeaves, 8) k_refit_coop(BuildCtx c)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kRefitLeaves, kMinBlocks) k_refit_coop(BuildCtx c)
 {
     __shared__ RefitShared sh;
     constexpr uint32_t B = kRefitLeaves;
@@ -902,7 +903,9 @@ int build_device(snch_scene *s, cudaStream_t stream)
     else
     {
         const unsigned ctas = (nT + kRefitLeaves - 1) / kRefitLeaves;
-        k_refit_coop<<<ctas, kRefitLeaves, 0, stream>>>(c);
+        if (s->opt_refit_kernel == 2) k_refit_coop<10><<<ctas, kRefitLeaves, 0, stream>>>(c);
+        else if (s->opt_refit_kernel == 3) k_refit_coop<12><<<ctas, kRefitLeaves, 0, stream>>>(c);
+        else k_refit_coop<8><<<ctas, kRefitLeaves, 0, stream>>>(c);
         if (nT > 1)
         {
             k_refit_top<<<ctas < 8 ? 1 : ctas / 8, 128, 0, stream>>>(c); // one thread per escape of the pass above (~12 per CTA); grid-stride beyond
