@@ -565,9 +565,10 @@ SNCH_DI void sh_get(const RefitShared &sh, uint32_t id, Box &b, Cone &cn)
     cn.half_angle = sh.f[9][id];
     cn.radius = sh.f[10][id];
 }
-// (8 resident CTAs at 64 registers with 56 B of spills beat 6 CTAs at 76 registers without: 0.488 vs 0.497 ms, profiles/r2e_variants.json)
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kRefitLeaves, kMinBlocks) k_refit_coop(BuildCtx c)
+// Register budget, measured (build ms @1M triangles): 6 CTAs/SM at 76 registers, no spills 0.497; **8 CTAs at 64 registers, 56 B of
+// spills 0.488**; 10 CTAs at 48 registers, 308 B 0.566; 12 CTAs at 40 registers, 476 B 0.768.  The kernel's time is (waves of CTAs) x
+// (rounds) x (latency of one cone merge on one thread), so it wants residency — until the spills of the merge eat it.
+__global__ void __launch_bounds__(kRefitLeaves, 8) k_refit_coop(BuildCtx c)
 {
     __shared__ RefitShared sh;
     constexpr uint32_t B = kRefitLeaves;
@@ -903,9 +904,7 @@ int build_device(snch_scene *s, cudaStream_t stream)
     else
     {
         const unsigned ctas = (nT + kRefitLeaves - 1) / kRefitLeaves;
-        if (s->opt_refit_kernel == 2) k_refit_coop<10><<<ctas, kRefitLeaves, 0, stream>>>(c);
-        else if (s->opt_refit_kernel == 3) k_refit_coop<12><<<ctas, kRefitLeaves, 0, stream>>>(c);
-        else k_refit_coop<8><<<ctas, kRefitLeaves, 0, stream>>>(c);
+        k_refit_coop<<<ctas, kRefitLeaves, 0, stream>>>(c);
         if (nT > 1)
         {
             k_refit_top<<<ctas < 8 ? 1 : ctas / 8, 128, 0, stream>>>(c); // one thread per escape of the pass above (~12 per CTA); grid-stride beyond

@@ -107,7 +107,7 @@ def main():
     # build: the refit kernel variants (identical arenas are asserted by tests/test_gpu_build.py; here only the time)
     build = {}
     if args.sets == "all" or "build" in args.sets.split(","):
-        for name, rk in (("refit_coop", 1), ("refit_coop_10cta", 2), ("refit_coop_12cta", 3), ("refit_per_thread", 0)):
+        for name, rk in (("refit_coop", 1), ("refit_per_thread", 0)):
             sc.set_option("build.refit_kernel", rk)
             ts = []
             for _ in range(6):
