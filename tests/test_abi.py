@@ -95,3 +95,24 @@ def test_cpp_dropin_headers_compile(tmp_path):
     out = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "include"), "-c", str(src),
                           "-o", str(tmp_path / "tu.o")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_replication_entry_points_reject_bad_arguments(pkg):
+    """The replication part of the C-ABI validates its arguments before it touches CUDA or NCCL (so this runs on a CPU box)."""
+    L = pkg.lib()
+    out = C.c_void_p()
+    buf = C.create_string_buffer(128)
+    assert L.snch_comm_unique_id(buf, 16) == -1 and b"SNCH_COMM_ID_BYTES" in L.snch_last_error()
+    assert L.snch_comm_create(buf, 128, 3, 2, 0, C.byref(out)) == -1          # rank outside the world
+    assert L.snch_comm_create(buf, 64, 0, 2, 0, C.byref(out)) == -1           # id buffer too short
+    assert L.snch_comm_adopt(None, 0, 1, 0, C.byref(out)) == -1
+    assert L.snch_comm_destroy(None) == 0
+    assert L.snch_scene_broadcast(None, 0, None, None, C.byref(out)) == -1
+    v, f = pkg.meshes.tetrahedron()
+    sc = pkg.Scene3(v, f).compute_silhouettes()                                 # not built
+    devs = (C.c_int * 1)(0)
+    reps = (C.c_void_p * 1)()
+    assert L.snch_scene_replicate_local(sc._h, devs, 1, reps) == -2 and L.snch_last_error() == b"BVH is not built yet."
+    assert L.snch_scene_last_kernel(None) == b"" and L.snch_scene_last_kernel(sc._h) == b""
+    with pytest.raises(pkg.SnchError):
+        sc.set_option("query.sil_seed", 1)                                      # a knob removed in round 2 is an error, not a no-op
