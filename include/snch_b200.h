@@ -205,7 +205,8 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
  *   "build.refit_kernel" 1 = CTA-cooperative refit (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort
- *                       (default), 0 = three-kernel passes; "adjacency.device" 1 = GPU silhouette adjacency (default when a device
+ *                       (default), 0 = three-kernel passes; "sort.lookback" predecessor tiles a tile reads per round trip of its
+ *                       look-back (8, default) or 1; "adjacency.device" 1 = GPU silhouette adjacency (default when a device
  *                       is present), 0 = host passes
  * The reference has no counterpart (its queries are per-thread device functions scheduled by the caller's kernel).
  *   "query.time_kernels" bracket every traversal kernel with CUDA events on the launching stream (default 0; see snch_scene_counter) */

@@ -831,6 +831,7 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;
     else if (k == "build.refit_kernel") s->opt_refit_kernel = (int)value;
+    else if (k == "sort.lookback") set_sort_lookback((int)value); // process-wide: 1 = one predecessor tile per L2 round trip, else 8
     else if (k == "sort.onesweep") set_sort_onesweep((int)value); // process-wide (A/B of the two radix sorts)
     else
     {

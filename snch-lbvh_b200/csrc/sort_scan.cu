@@ -212,6 +212,7 @@ static int radix_sort_pairs_multipass(uint32_t *keys, uint32_t *vals, uint32_t *
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kOsAgg = 1u << 30, kOsPrefix = 2u << 30, kOsValue = (1u << 30) - 1u;
 constexpr int kOsMaxPasses = 4;
+constexpr int kOsWindow = 8;
 
 __global__ void __launch_bounds__(kSortThreads)
     k_os_hist(const uint32_t *__restrict__ keys, uint64_t n, int first_bit, int passes, uint32_t *__restrict__ ghist)
@@ -293,11 +294,15 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
     return incl - v + before;
 }
 
+static int g_sort_onesweep = 1, g_sort_lookback = 8;
+void set_sort_onesweep(int on) { g_sort_onesweep = on; }
+void set_sort_lookback(int window) { g_sort_lookback = window; }
+
 // kItems keys per thread: 16 (4096-key tiles) for large inputs, 8 when that would leave SMs without a tile
 template <int kItems>
 __global__ void __launch_bounds__(kSortThreads)
     k_os_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout, uint32_t *__restrict__ vout,
-              uint64_t n, int shift, const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *tile_counter)
+              uint64_t n, int shift, const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *tile_counter, int lookback)
 {
     constexpr int kWarps = kSortThreads / 32;
     constexpr int kTile = kSortThreads * kItems;
@@ -355,15 +360,38 @@ __global__ void __launch_bounds__(kSortThreads)
         const uint32_t dstart = block_exclusive_scan_256(cnt, s_warp_sums);          // where digit d starts inside the tile
         const uint32_t gdigit = block_exclusive_scan_256(ghist[d], s_warp_sums);     // where digit d starts in the output
         uint32_t excl = 0;
-        for (int64_t t = (int64_t)tile - 1; t >= 0; --t)
+        if (lookback <= 1)
         {
-            uint32_t v;
-            do
+            for (int64_t t = (int64_t)tile - 1; t >= 0; --t)
             {
-                v = status[(uint64_t)t * kSortBins + d];
-            } while ((v & ~kOsValue) == 0);
-            excl += v & kOsValue;
-            if (v & kOsPrefix) break;
+                uint32_t v;
+                do
+                {
+                    v = status[(uint64_t)t * kSortBins + d];
+                } while ((v & ~kOsValue) == 0);
+                excl += v & kOsValue;
+                if (v & kOsPrefix) break;
+            }
+        }
+        else
+        { // kOsWindow predecessors are read at once (independent loads in flight), then consumed in order: the walk back to
+          // the nearest published prefix costs one L2 round trip per window instead of one per tile
+            bool done = tile == 0;
+            for (int64_t t = (int64_t)tile - 1; !done; t -= kOsWindow)
+            {
+                uint32_t v[kOsWindow];
+#pragma unroll
+                for (int j = 0; j < kOsWindow; ++j) v[j] = t - j >= 0 ? status[(uint64_t)(t - j) * kSortBins + d] : (2u << 30) /* prefix of nothing */;
+#pragma unroll
+                for (int j = 0; j < kOsWindow; ++j)
+                {
+                    if (done) continue;
+                    uint32_t x = v[j];
+                    while ((x & ~kOsValue) == 0) x = status[(uint64_t)(t - j) * kSortBins + d];
+                    excl += x & kOsValue;
+                    done = (x & kOsPrefix) != 0;
+                }
+            }
         }
         *mine = (excl + cnt) | kOsPrefix;
         s_dstart[d] = dstart;
@@ -393,8 +421,6 @@ __global__ void __launch_bounds__(kSortThreads)
     }
 }
 
-static int g_sort_onesweep = 1;
-void set_sort_onesweep(int on) { g_sort_onesweep = on; }
 
 int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp, uint64_t n, int bits,
                      uint32_t *scratch, cudaStream_t stream, int first_bit)
@@ -418,10 +444,10 @@ int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_
     {
         if (small_tiles)
             k_os_pass<kSortItems / 2><<<tiles, kSortThreads, 0, stream>>>(sk, sv, dk, dv, n, first_bit + 8 * p, ghist + p * kSortBins,
-                                                                        status + (uint64_t)p * tiles * kSortBins, counters + p);
+                                                                        status + (uint64_t)p * tiles * kSortBins, counters + p, g_sort_lookback);
         else
             k_os_pass<kSortItems><<<tiles, kSortThreads, 0, stream>>>(sk, sv, dk, dv, n, first_bit + 8 * p, ghist + p * kSortBins,
-                                                                    status + (uint64_t)p * tiles * kSortBins, counters + p);
+                                                                    status + (uint64_t)p * tiles * kSortBins, counters + p, g_sort_lookback);
         uint32_t *t = sk;
         sk = dk;
         dk = t;

@@ -54,5 +54,6 @@ int radix_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_
 
 // process-wide switch between the onesweep and the multi-kernel sort (snch_scene_set_option "sort.onesweep")
 void set_sort_onesweep(int on);
+void set_sort_lookback(int window); // 1 = serial look-back, else windows of 8 tiles
 
 } // namespace snch

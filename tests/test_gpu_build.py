@@ -81,7 +81,8 @@ def test_rebuild_is_deterministic(pkg, meshes):
 @pytest.mark.parametrize("name", ["tet", "one", "ico2", "grid6", "grid40", "torus97x61", "flat", "dups", "torus300", "torus708"])
 def test_refit_kernels_produce_identical_arenas(pkg, meshes, name):
     """"build.refit_kernel": the block-cooperative refit (v2, rounds in shared memory) and the per-thread climb (v1) apply the
-    same merges to the same children; "sort.onesweep": both radix sorts are stable.  The whole arena — reference-layout
+    same merges to the same children; "sort.onesweep" / "sort.lookback": both radix sorts are stable and the look-back window
+    changes no offset.  The whole arena — reference-layout
     arrays and traversal records — is bit-identical for every combination."""
     if name == "one":
         v, f = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), np.array([[0, 1, 2]], np.int32)
@@ -91,11 +92,12 @@ def test_refit_kernels_produce_identical_arenas(pkg, meshes, name):
     arenas = []
     import torch
     try:
-        for kern, onesweep in ((0, 0), (1, 1), (1, 0), (1, 1)):  # "sort.onesweep" is process-wide: restored below
-            sc.set_option("build.refit_kernel", kern).set_option("sort.onesweep", onesweep).build_bvh()
+        # "sort.onesweep" / "sort.lookback" are process-wide: restored below
+        for kern, onesweep, lookback in ((0, 0, 8), (1, 1, 8), (1, 0, 8), (1, 1, 1)):
+            sc.set_option("build.refit_kernel", kern).set_option("sort.onesweep", onesweep).set_option("sort.lookback", lookback).build_bvh()
             arenas.append(sc.arena_tensor().clone())
     finally:
-        sc.set_option("build.refit_kernel", 1).set_option("sort.onesweep", 1)
+        sc.set_option("build.refit_kernel", 1).set_option("sort.onesweep", 1).set_option("sort.lookback", 8)
     for a in arenas[1:]:
         assert a.shape == arenas[0].shape
         assert torch.equal(arenas[0], a), f"{int((arenas[0] != a).sum())} arena bytes differ between refit kernels / radix sorts"
