@@ -219,7 +219,9 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value);
  *   "query.launches"            kernels launched by the *_batch calls (ordering + traversal)
  *   "query.traversal_launches"  traversal kernels among them
  *   "query.traversal_ms"        device time of the traversal kernels alone; needs "query.time_kernels" = 1 (synchronises the last one)
- *   "build.launches"            kernels of the last snch_scene_build */
+ *   "build.launches"            kernels of the last snch_scene_build
+ *   "adjacency.device_ms"       device time (upload + kernels, CUDA events) of the last GPU snch_scene_compute_silhouettes;
+ *                               snch_build_stats.adjacency_ms is the host's wall clock around it, allocations included */
 int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset);
 /* name of the traversal kernel the last *_batch call on this scene launched (static string; what bench.py puts in roofline.kernel) */
 const char *snch_scene_last_kernel(const snch_scene *s);

@@ -118,7 +118,7 @@ void free_adjacency(snch_scene *s)
 }
 
 // Leaves tri / tri_edges / tri_owned / edges4 in one device allocation owned by the scene (s->adj); build_device()
-// assembles the reference-layout structs from it and releases it.  One host synchronisation (the edge count).
+// assembles the reference-layout structs from it and releases it.  One host synchronisation, at the end.
 int compute_adjacency_device(snch_scene *s)
 {
     const auto t0 = std::chrono::steady_clock::now();
@@ -153,18 +153,30 @@ int compute_adjacency_device(snch_scene *s)
     const uint64_t o_key = take(m64 * 4), o_val = take(m64 * 4), o_ktmp = take(m64 * 4), o_vtmp = take(m64 * 4);
     const uint64_t o_head = take(m64 * 4), o_eid = take(m64 * 4), o_sort = take(sort_elems * 4), o_scan = take(scan_elems * 4);
     const uint64_t tmp_bytes = off;
-    unsigned char *tmp = nullptr, *tri_buf = nullptr;
-    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess || cudaMalloc(&tri_buf, m64 * 4) != cudaSuccess)
+    // the persistent arrays are sized for the worst case (every half-edge its own edge) so that no allocation falls between
+    // the kernels; build_device() releases them as soon as the arena holds the topology
+    uint64_t poff = 0;
+    auto ptake = [&](uint64_t bytes)
+    {
+        const uint64_t o = poff;
+        poff = align_up(poff + bytes, 256);
+        return o;
+    };
+    const uint64_t p_tri = ptake(m64 * 4), p_te = ptake(m64 * 4), p_to = ptake(m64 * 4), p_e4 = ptake(m64 * 16);
+    unsigned char *tmp = nullptr, *tri_buf = nullptr, *adj = nullptr;
+    if (cudaMalloc(&tmp, tmp_bytes) != cudaSuccess || cudaMalloc(&tri_buf, m64 * 4) != cudaSuccess || cudaMalloc(&adj, poff) != cudaSuccess)
     {
         cudaGetLastError();
         if (tmp) cudaFree(tmp);
-        set_error("cudaMalloc of the adjacency scratch failed");
+        if (tri_buf) cudaFree(tri_buf);
+        set_error("cudaMalloc of the adjacency arrays failed");
         return SNCH_ERR_OOM;
     }
     auto fail = [&](cudaError_t e, const char *what)
     {
         cudaFree(tmp);
         cudaFree(tri_buf);
+        cudaFree(adj);
         return cuda_fail(e, what);
     };
 #define ADJ_CUDA(call)                                   \
@@ -179,6 +191,20 @@ int compute_adjacency_device(snch_scene *s)
     uint32_t *head = (uint32_t *)(tmp + o_head), *eid = (uint32_t *)(tmp + o_eid);
     uint32_t *sort_scr = (uint32_t *)(tmp + o_sort), *scan_scr = (uint32_t *)(tmp + o_scan);
 
+    // device-side time of the pass (upload, two sorts, scan, fills) between two events: adjacency_ms is the host's wall clock and
+    // also pays three cudaMalloc and two cudaFree, which the driver answers in anything from 0.1 to 100+ ms
+    struct EventPair
+    {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair()
+        {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } ev;
+    ADJ_CUDA(cudaEventCreate(&ev.a));
+    ADJ_CUDA(cudaEventCreate(&ev.b));
+    ADJ_CUDA(cudaEventRecord(ev.a, st));
     ADJ_CUDA(cudaMemcpyAsync(tri, s->h_tri.data(), m64 * 4, cudaMemcpyHostToDevice, st));
     int bits = 1;
     while (bits < 32 && (1ull << bits) < (uint64_t)s->n_verts) ++bits;
@@ -193,40 +219,24 @@ int compute_adjacency_device(snch_scene *s)
     uint32_t last[2] = {0, 0};
     ADJ_CUDA(cudaMemcpyAsync(&last[0], eid + (m - 1), 4, cudaMemcpyDeviceToHost, st));
     ADJ_CUDA(cudaMemcpyAsync(&last[1], head + (m - 1), 4, cudaMemcpyDeviceToHost, st));
-    ADJ_CUDA(cudaStreamSynchronize(st));
-    const uint32_t E = last[0] + last[1];
-
-    uint64_t poff = 0;
-    auto ptake = [&](uint64_t bytes)
-    {
-        const uint64_t o = poff;
-        poff = align_up(poff + bytes, 256);
-        return o;
-    };
-    const uint64_t p_tri = ptake(m64 * 4), p_te = ptake(m64 * 4), p_to = ptake(m64 * 4), p_e4 = ptake((uint64_t)E * 16);
-    unsigned char *adj = nullptr;
-    if (cudaMalloc(&adj, poff) != cudaSuccess)
-    {
-        cudaGetLastError();
-        cudaFree(tmp);
-        cudaFree(tri_buf);
-        set_error("cudaMalloc of the adjacency arrays failed");
-        return SNCH_ERR_OOM;
-    }
-    s->adj = adj;
-    s->adj_tri = (int32_t *)(adj + p_tri);
-    s->adj_tri_edges = (int32_t *)(adj + p_te);
-    s->adj_tri_owned = (int32_t *)(adj + p_to);
-    s->adj_edges4 = (int4 *)(adj + p_e4);
-    ADJ_CUDA(cudaMemcpyAsync(s->adj_tri, tri, m64 * 4, cudaMemcpyDeviceToDevice, st));
-    k_fill_edges<<<g, 256, 0, st>>>(tri, m, val, head, eid, s->adj_edges4, s->adj_tri_edges);
-    k_owned<<<(n + 255) / 256, 256, 0, st>>>(n, head, eid, s->adj_tri_owned);
+    int32_t *adj_tri = (int32_t *)(adj + p_tri), *adj_tri_edges = (int32_t *)(adj + p_te), *adj_tri_owned = (int32_t *)(adj + p_to);
+    int4 *adj_edges4 = (int4 *)(adj + p_e4);
+    ADJ_CUDA(cudaMemcpyAsync(adj_tri, tri, m64 * 4, cudaMemcpyDeviceToDevice, st));
+    k_fill_edges<<<g, 256, 0, st>>>(tri, m, val, head, eid, adj_edges4, adj_tri_edges);
+    k_owned<<<(n + 255) / 256, 256, 0, st>>>(n, head, eid, adj_tri_owned);
     ADJ_CUDA(cudaGetLastError());
+    ADJ_CUDA(cudaEventRecord(ev.b, st));
     ADJ_CUDA(cudaStreamSynchronize(st));
+    ADJ_CUDA(cudaEventElapsedTime(&s->adjacency_device_ms, ev.a, ev.b));
 #undef ADJ_CUDA
+    s->adj = adj;
+    s->adj_tri = adj_tri;
+    s->adj_tri_edges = adj_tri_edges;
+    s->adj_tri_owned = adj_tri_owned;
+    s->adj_edges4 = adj_edges4;
     cudaFree(tmp);
     cudaFree(tri_buf);
-    s->n_edges = E;
+    s->n_edges = last[0] + last[1];
     s->silhouettes_done = true;
     s->adjacency_on_device = true;
     s->adjacency_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();

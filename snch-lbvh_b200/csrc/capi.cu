@@ -788,6 +788,7 @@ int snch_scene_counter(snch_scene *s, const char *name, double *value, int reset
         *value = c.traversal_ms;
     }
     else if (k == "build.launches") *value = (double)s->build_launches;
+    else if (k == "adjacency.device_ms") *value = (double)s->adjacency_device_ms;
     else
     {
         set_error("snch_scene_counter: unknown counter '" + k + "'");

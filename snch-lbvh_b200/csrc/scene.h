@@ -97,7 +97,7 @@ struct snch_scene
     snch::QueryCounters counters;
     uint64_t build_launches = 0;
     // stats
-    float build_ms = 0.f, adjacency_ms = 0.f;
+    float build_ms = 0.f, adjacency_ms = 0.f, adjacency_device_ms = 0.f; // adjacency: host wall clock / CUDA events around the device work
     uint32_t opt_print_collision = 0, opt_refit_only = 0;
     int opt_refit_kernel = 1; // "build.refit_kernel": 1 = block-cooperative rounds (default), 0 = one climbing thread per leaf
 };
