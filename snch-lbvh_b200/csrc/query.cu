@@ -668,8 +668,11 @@ SNCH_DI float solo_silhouette(const SceneView &sv, const Stk st, int lane, V3 p,
 //     walking them one lane each: it drains its queue and puts those queries, with the bound each has found so far, on a
 //     list that the next launch (k_silhouette_wide) finishes ONE QUERY PER WARP from the root.  The few queries that open
 //     thousands of nodes (a point in the hole of the torus) were a fixed ~8 ms single-lane tail of every unbounded batch;
-//     same predicate chain, same edge tests, same minimum (an edge found before the restart lies within the inclusive
-//     bound and is reached again).
+//     same predicate chain, same edge tests, same minimum.  The edge found before the restart travels with the entry
+//     (tail_prev): its distance is the restart's inclusive bound, but far from the origin the ROUNDED distance to an edge
+//     can be smaller than the rounded distance to the box that holds it, so the restart is not certain to reach it again
+//     (tests/test_gpu_fuzz.py seed 7: coordinates near 1000); when the restart finds nothing within the bound, that edge
+//     is the answer.
 constexpr int kSStack = 12;
 constexpr int kLeafQueue = 96;   // >= kLeafFlushAt - 1 + 64 (every lane can add two leaves per step)
 constexpr int kLeafFlushAt = 32; // upper limit of "query.sil_flush"
@@ -694,7 +697,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
     k_silhouette_coop(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
                       float *__restrict__ out_point, unsigned long long *counter, int tail_lanes, uint32_t *__restrict__ tail_slot,
-                      float *__restrict__ tail_bound, uint32_t flush_at, uint32_t chunk)
+                      float *__restrict__ tail_bound, uint32_t *__restrict__ tail_prev, uint32_t flush_at, uint32_t chunk)
 {
     using Res = SilResult<kEdge>;
     __shared__ StackEntry s_stk[kSStack][kQueryThreads];
@@ -864,6 +867,7 @@ __global__ void __launch_bounds__(kQueryThreads, 8)
         const uint32_t at = (uint32_t)atomicAdd(counter + 1, 1ull); // < gridDim.x * blockDim.x entries by construction
         tail_slot[at] = slot;
         tail_bound[at] = best;
+        tail_prev[at] = found ? (kEdge ? best_slot : 0u) : kNone; // the LEdge slot that attains `best`, if an edge has been found
     }
 }
 
@@ -875,12 +879,13 @@ __global__ void __launch_bounds__(kQueryThreads)
     k_silhouette_wide(SceneView sv, const float *__restrict__ q, const uint8_t *__restrict__ flipv, const float *__restrict__ rmax,
                       const uint32_t *__restrict__ perm, uint32_t n, float *__restrict__ out_dist, uint32_t *__restrict__ out_edge,
                       float *__restrict__ out_point, unsigned long long *counter, const unsigned long long *__restrict__ list_n,
-                      const float *__restrict__ list_bound)
+                      const float *__restrict__ list_bound, const uint32_t *__restrict__ list_prev)
 {
     __shared__ StackEntry s_solo[kQueryThreads / 32][kSoloStackSil];
     const int lane = threadIdx.x & 31;
     const FlatStack solo{s_solo[threadIdx.x >> 5]};
-    // list mode (the tail of k_silhouette_coop): `perm` is the list, *list_n its length, list_bound[i] the bound of entry i
+    // list mode (the tail of k_silhouette_coop): `perm` is the list, *list_n its length, list_bound[i] the bound of entry i and
+    // list_prev[i] the edge that set it (kNone: the bound is still the query's own radius)
     if (list_n) n = (uint32_t)*list_n;
     const unsigned long long kRun = list_n ? 1 : 4;
     for (;;)
@@ -896,7 +901,16 @@ __global__ void __launch_bounds__(kQueryThreads)
             const bool flip = flipv ? (__ldg(flipv + slot) != 0) : false;
             const float r = list_n ? __ldg(list_bound + s) : (rmax ? __ldg(rmax + slot) : INFINITY);
             uint32_t eslot = kNone;
-            const float ans = solo_silhouette<kFilter, kEdge, kSoloStackSil>(sv, solo, lane, p, flip, r, eslot);
+            float ans = solo_silhouette<kFilter, kEdge, kSoloStackSil>(sv, solo, lane, p, flip, r, eslot);
+            if (list_n && !(ans < INFINITY))
+            {
+                const uint32_t prev = __ldg(list_prev + s);
+                if (prev != kNone)
+                {
+                    ans = r;
+                    eslot = prev;
+                }
+            }
             if (lane == 0)
             {
                 out_dist[slot] = ans;
@@ -1407,7 +1421,7 @@ static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, c
     {
         if (qc) qc->last_kernel = kEdge ? "k_silhouette_wide<edge>" : "k_silhouette_wide";
         k_silhouette_wide<kFilter, kEdge><<<persistent_grid(k_silhouette_wide<kFilter, kEdge>, t, n < (1u << 26) ? n * 16 : n), kQueryThreads, 0, st>>>(
-            v, q, flip, rmax, perm, n, dist, edge, point, counter, nullptr, nullptr);
+            v, q, flip, rmax, perm, n, dist, edge, point, counter, nullptr, nullptr, nullptr);
         return;
     }
     if (qc) qc->last_kernel = kEdge ? "k_silhouette_coop<edge>" : "k_silhouette_coop";
@@ -1415,15 +1429,16 @@ static void launch_silhouette_kernel(const SceneView &v, const QueryTuning &t, c
     // the tail list holds at most one entry per resident lane
     uint32_t *tail_slot = reinterpret_cast<uint32_t *>(tail);
     float *tail_bound = reinterpret_cast<float *>(tail + kTailEntries * 4);
+    uint32_t *tail_prev = reinterpret_cast<uint32_t *>(tail + kTailEntries * 8);
     const int tl = (t.sil_tail > 0 && (uint64_t)grid * kQueryThreads <= kTailEntries) ? (t.sil_tail > 31 ? 31 : t.sil_tail) : 0;
     const uint32_t flush_at = (uint32_t)(t.sil_flush < 1 ? 1 : (t.sil_flush > kLeafFlushAt ? kLeafFlushAt : t.sil_flush));
-    k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound, flush_at,
+    k_silhouette_coop<kFilter, kEdge><<<grid, kQueryThreads, 0, st>>>(v, q, flip, rmax, perm, n, dist, edge, point, counter, tl, tail_slot, tail_bound, tail_prev, flush_at,
                                                                       (uint32_t)(t.sil_chunk > 0 ? t.sil_chunk : sil_chunk_for_host(n)));
     if (tl)
     { // finish the listed queries one per warp; its own work counter is counter[2], the list length counter[1]
         if (qc) qc->launches += 1;
         k_silhouette_wide<kFilter, kEdge><<<grid < 592 ? grid : 592, kQueryThreads, 0, st>>>(v, q, flip, rmax, tail_slot, 0u, dist, edge, point, counter + 2, counter + 1,
-                                                                                          tail_bound);
+                                                                                          tail_bound, tail_prev);
     }
 }
 static void launch_silhouette_lanes(const SceneView &v, const QueryTuning &t, const float *q, const uint8_t *flip, const float *rmax,

@@ -61,8 +61,8 @@ struct Feeder
     uint32_t chunk = 0; // queries per draw (0 = chunk_for(n))
 };
 constexpr uint64_t kScratchHeader = 256; // work counters (u64 x 8: [0] batch, [1] tail list length, [2] tail work) + query box (6 ordered ints at +64)
-constexpr uint64_t kTailEntries = 1u << 18; // tail list of the silhouette kernel: one (slot, bound) pair per resident lane at most
-constexpr uint64_t kTailBytes = kTailEntries * 8;
+constexpr uint64_t kTailEntries = 1u << 18; // tail list of the silhouette kernel: one (slot, bound, edge found so far) triple per resident lane at most
+constexpr uint64_t kTailBytes = kTailEntries * 12;
 // Gives every idle lane (bit set in `idle`) the next query slot of the warp's chunk; draws a new chunk when needed.
 // Returns the slot for this lane or kNone.  Warp-convergent call.
 SNCH_DI uint32_t feeder_take(Feeder &f, unsigned idle, bool lane_idle, int lane, uint32_t n, unsigned long long *counter)

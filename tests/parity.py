@@ -62,7 +62,10 @@ def check_cones(cones, cones_o, taint, taint_o, rtol=REL_TOL, atol=2e-6):
                                                                       f"{absd.max()} at angles {cones_o[ok, 3][~strict][:5]}")
     assert rel_close(cones[ok, 4], cones_o[ok, 4], rtol, atol).all(), "cone radii differ"
     # axes: compare as vectors (unit length, or the zero default of boundary leaves)
+    nan, nan_o = np.isnan(cones[ok, :3]).any(axis=1), np.isnan(cones_o[ok, :3]).any(axis=1)
+    assert np.array_equal(nan, nan_o), "cone axes: NaN sets differ"  # (opposite normals cancel: normalize(0), in both)
     dax = np.linalg.norm(cones[ok, :3].astype(np.float64) - cones_o[ok, :3].astype(np.float64), axis=1)
+    dax = np.where(nan_o, 0.0, dax)
     assert (dax <= 1e-3).all() and np.mean(dax <= 1e-4) >= 1 - 1e-4 and np.mean(dax <= 2e-5) >= 0.99, f"cone axes differ (max {dax.max()})"  # same conditioning as above
     # tainted nodes: the product defines half_angle = pi and radii are still comparable
     t = taint_o & valid_o
@@ -126,7 +129,7 @@ def check_silhouette_edges(q, dist, edge, point, orc, flip=False, r_max=None):
     return float(same.mean()) if fin.any() else 1.0
 
 
-def check_rays(found, hits, q, d, tmax, orc):
+def check_rays(found, hits, q, d, tmax, orc, max_tie_frac=1e-3):
     """Hit flags and t BIT-IDENTICAL to the oracle's walk; the triangle and (u, v) too, except on exact ties (Q4: two
     triangles sharing an edge are hit at the same t — the kernel that tests leaves where it meets them reaches them in another
     order than the reference's stack): there the returned triangle must attain that t, recomputed here in double precision."""
@@ -139,7 +142,7 @@ def check_rays(found, hits, q, d, tmax, orc):
     same = prim == p_o
     assert np.array_equal(bits(hits["u"])[same], bits(uv_o[:, 0])[same]) and np.array_equal(bits(hits["v"])[same], bits(uv_o[:, 1])[same]), "ray (u, v) differ"
     tie = np.nonzero(~same)[0]
-    assert len(tie) <= max(1, len(found) // 1000), f"ray triangle differs on {len(tie)} rays"
+    assert len(tie) <= max(1, int(len(found) * max_tie_frac)), f"ray triangle differs on {len(tie)} rays"  # (soups of duplicated triangles: any)
     if len(tie):
         tri = orc.verts[orc.tris[prim[tie]]].astype(np.float64)
         o64, d64 = np.asarray(q, np.float64)[tie], np.asarray(d, np.float64)[tie]

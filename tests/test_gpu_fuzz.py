@@ -1,0 +1,147 @@
+"""Seeded fuzz of the whole path on the GPU against the CPU oracle: random triangle SOUPS — non-manifold edges shared by many
+triangles, duplicated triangles, inconsistent orientation, boundary edges, self-intersections, slivers, far-from-origin
+and tiny coordinates — the inputs the structured meshes of the other tests never produce.  Build arrays, adjacency and every
+query kind must match the oracle the same way they do on the structured meshes (bit for bit where parity.py says so)."""
+import numpy as np
+import pytest
+
+from oracle import OracleScene
+from parity import bits, check_build_vs_oracle, check_closest, check_rays, check_silhouette, check_silhouette_edges
+
+pytestmark = pytest.mark.gpu
+
+# (seed, vertices, triangles, offset, scale, sliver): few vertices and many triangles = heavily non-manifold
+CASES = [
+    (1, 4, 7, 0.0, 1.0, False),
+    (2, 6, 40, 0.0, 1.0, False),
+    (3, 12, 100, 0.0, 1.0, False),
+    (4, 50, 60, 0.0, 1.0, False),
+    (5, 200, 1000, 0.0, 1.0, False),
+    (6, 30, 3000, 0.0, 1.0, False),
+    (7, 300, 500, 1000.0, 1.0, False),   # far from the origin: absolute rounding of every coordinate-sized quantity
+    (8, 300, 500, 0.0, 1e-3, False),     # tiny geometry
+    (9, 100, 400, 0.0, 1.0, True),       # slivers: one coordinate squeezed by 1e-4
+    (10, 2000, 20000, 0.0, 1.0, False),  # enough triangles for several sort tiles and refit CTAs
+]
+
+
+def soup(seed, nv, nt, offset, scale, sliver):
+    rng = np.random.default_rng(seed)
+    v = rng.random((nv, 3))
+    if sliver:
+        v[:, 2] *= 1e-4
+    v = (v * scale + offset).astype(np.float32)
+    f = rng.integers(0, nv, (nt, 3))
+    for _ in range(64):  # no repeated vertex inside a triangle (exactly degenerate input is test_gpu_adjacency's business)
+        bad = (f[:, 0] == f[:, 1]) | (f[:, 1] == f[:, 2]) | (f[:, 0] == f[:, 2])
+        if not bad.any():
+            break
+        f[bad] = rng.integers(0, nv, (int(bad.sum()), 3))
+    f = f[~((f[:, 0] == f[:, 1]) | (f[:, 1] == f[:, 2]) | (f[:, 0] == f[:, 2]))]
+    if nt >= 40:
+        f = np.concatenate([f, f[:5], f[:3, ::-1]])  # exact duplicates, and the same triangles with the opposite orientation
+    return v, f.astype(np.int32)
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: f"seed{c[0]}_v{c[1]}_t{c[2]}")
+def fuzz_scene(request, pkg, meshes):
+    v, f = soup(*request.param)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    orc = OracleScene(v, f)
+    lo, hi = meshes.mesh_bounds(v)
+    n = 6000
+    q = meshes.points_in_box(n, lo, hi, 1.5, seed=1000 + request.param[0])
+    d = meshes.unit_directions(n, seed=2000 + request.param[0])
+    return sc, orc, q, d, pkg
+
+
+def test_fuzz_build(fuzz_scene):
+    sc, orc, _, _, pkg = fuzz_scene
+    check_build_vs_oracle(sc, orc, pkg)
+
+
+def test_fuzz_closest(fuzz_scene):
+    sc, orc, q, _, _ = fuzz_scene
+    idx, dist = sc.closest_point(q)
+    check_closest(q, idx, dist, orc)
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_fuzz_silhouette(fuzz_scene, meshes, flip):
+    sc, orc, q, _, _ = fuzz_scene
+    dist = sc.closest_silhouette(q, flip=flip)
+    check_silhouette(dist, orc.silhouette(q, flip, nthreads=8))
+    rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(len(q))).astype(np.float32)
+    dist_r, edge, pt = sc.closest_silhouette(q, flip=flip, r_max=rmax, with_edge=True)
+    check_silhouette(dist_r, orc.silhouette(q, flip, r_max=rmax, nthreads=8))
+    check_silhouette_edges(q, dist_r, edge, pt, orc, flip, r_max=rmax)
+    assert np.array_equal(bits(dist_r), bits(np.where(dist <= rmax, dist, np.inf).astype(np.float32)))
+
+
+@pytest.mark.parametrize("ray_kernel", [1, 2])
+def test_fuzz_rays(fuzz_scene, ray_kernel):
+    sc, orc, q, d, _ = fuzz_scene
+    sc.set_option("query.ray_kernel", ray_kernel)
+    found, hits = sc.intersect(q, d)
+    tm = np.full(len(q), 0.4, np.float32)
+    found_t, hits_t = sc.intersect(q, d, t_max=tm)
+    sc.set_option("query.ray_kernel", 1)
+    # duplicated / coplanar overlapping triangles are hit at exactly the same t: which of them is reported is a tie (Q4) —
+    # every differing triangle is still verified in double precision to attain the bit-identical t
+    check_rays(found, hits, q, d, None, orc, max_tie_frac=1.0)
+    check_rays(found_t, hits_t, q, d, tm, orc, max_tie_frac=1.0)
+
+
+def test_fuzz_sample(fuzz_scene, meshes):
+    sc, orc, q, _, _ = fuzz_scene
+    _, dcp = orc.closest(q, nthreads=8)
+    sph = np.concatenate([q, (dcp * 1.5 + 0.05 * float(dcp.max()))[:, None]], axis=1).astype(np.float32)
+    rnd = meshes.uniforms(len(q), 3, seed=43)
+    idx, pdf, pt = sc.sample_in_sphere(sph, rnd)
+    idx_o, pdf_o = orc.sample(sph, rnd[:, 0].copy())
+    assert np.array_equal(idx, idx_o), f"sampled primitive differs on {np.count_nonzero(idx != idx_o)} of {len(idx)}"
+    hit = idx >= 0
+    assert np.array_equal(bits(pdf[hit]), bits(pdf_o[hit])), "sampling pdf differs"
+    pt_o = orc.sample_on_object(idx, rnd[:, 1].copy(), rnd[:, 2].copy())
+    assert np.array_equal(bits(pt[hit]), bits(pt_o[hit])), "sampled point differs"
+
+
+def test_fuzz_wost_step(fuzz_scene, meshes):
+    """the fused wavefront step equals its four stages on these inputs too"""
+    sc, _, q, d, _ = fuzz_scene
+    rnd = meshes.uniforms(len(q), 3, seed=44)
+    r = sc.wost_step(q, d, rnd)
+    idx, dist = sc.closest_point(q)
+    assert np.array_equal(bits(r["closest_distance"]), bits(dist))
+    sd = sc.closest_silhouette(q, r_max=dist)
+    assert np.array_equal(bits(r["silhouette_distance"]), bits(sd))
+    star = np.minimum(dist, sd)
+    assert np.array_equal(bits(r["star_radius"]), bits(star))
+    found, hits = sc.intersect(q, d, t_max=star)
+    assert np.array_equal(r["found"].astype(bool), found.astype(bool))
+    assert np.array_equal(bits(r["hits"]["t"]), bits(hits["t"]))
+
+
+def test_fuzz_large_batch_kernels(fuzz_scene, meshes):
+    """A 6 000-query batch takes the one-query-per-warp kernels; the kernels of the 16M-query batches (packets, per-lane walks
+    with the warp leaf queue and its tail launch, parked rays) must give the same bits on the same soups."""
+    sc, orc, q, d, _ = fuzz_scene
+    _, dist = sc.closest_point(q)
+    rmax = (dist * meshes.star_radius_scale(len(q))).astype(np.float32)
+    ref = [dist, sc.closest_silhouette(q), sc.closest_silhouette(q, flip=True), sc.closest_silhouette(q, r_max=rmax)]
+    ref_e = sc.closest_silhouette(q, r_max=rmax, with_edge=True)
+    kernels = set()
+    try:
+        sc.set_option("query.wide_max_n", 0).set_option("query.wide_max_n_sil", 0).set_option("query.sort_min_n", 1)
+        got = [sc.closest_point(q)[1]]
+        kernels.add(sc.last_kernel())
+        got += [sc.closest_silhouette(q), sc.closest_silhouette(q, flip=True), sc.closest_silhouette(q, r_max=rmax)]
+        kernels.add(sc.last_kernel())
+        got_e = sc.closest_silhouette(q, r_max=rmax, with_edge=True)
+    finally:
+        sc.set_option("query.wide_max_n", 2097152).set_option("query.wide_max_n_sil", 262144).set_option("query.sort_min_n", 16384)
+    assert {"k_closest_packet", "k_silhouette_coop"} <= kernels, kernels
+    for a, b in zip(ref, got):
+        assert np.array_equal(bits(a), bits(b))
+    assert np.array_equal(bits(ref_e[0]), bits(got_e[0]))
+    check_silhouette_edges(q, got_e[0], got_e[1], got_e[2], orc, False, r_max=rmax)
