@@ -396,7 +396,7 @@ public:
         SNCH_LBVH_HOST_DEVICE float operator()(const float2 &x, const float2 &y) const noexcept
         {
             const float r = detail::max_of(length(detail::sub(x, y)), 1e-2f);
-            return detail::abs_of(::logf(r) / (detail::pi<float>() * 2.0f));
+            return detail::abs_of(detail::log_of(r) / (detail::pi<float>() * 2.0f));
         }
     };
     struct sample_on_object

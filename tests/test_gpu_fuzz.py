@@ -145,3 +145,67 @@ def test_fuzz_large_batch_kernels(fuzz_scene, meshes):
         assert np.array_equal(bits(a), bits(b))
     assert np.array_equal(bits(ref_e[0]), bits(got_e[0]))
     check_silhouette_edges(q, got_e[0], got_e[1], got_e[2], orc, False, r_max=rmax)
+
+
+# ---- 2-D: random segment soups (vertices of any valence, duplicated and reversed segments, crossings) -------------------------
+# (seed, vertices, segments, offset, scale)
+CASES2 = [
+    (1, 4, 5, 0.0, 1.0),
+    (2, 8, 40, 0.0, 1.0),
+    (3, 100, 300, 0.0, 1.0),
+    (4, 300, 500, 1000.0, 1.0),  # far from the origin
+    (5, 300, 500, 0.0, 1e-3),    # tiny geometry
+    (6, 3000, 20000, 0.0, 1.0),
+]
+
+
+def soup2(seed, nv, ns, offset, scale):
+    rng = np.random.default_rng(seed)
+    v = (rng.random((nv, 2)) * scale + offset).astype(np.float32)
+    s = rng.integers(0, nv, (ns, 2))
+    s = s[s[:, 0] != s[:, 1]]
+    if ns >= 40:
+        s = np.concatenate([s, s[:5], s[:3, ::-1]])
+    return v, s.astype(np.int32)
+
+
+@pytest.mark.parametrize("case", CASES2, ids=lambda c: f"seed{c[0]}_v{c[1]}_s{c[2]}")
+def test_fuzz_2d(pkg, meshes, case):
+    """Every product of a 2-D scene against the 2-D oracle, bit for bit, with the one-query-per-warp kernels (the default for a
+    batch this small) and with the per-lane kernels of the large batches."""
+    from oracle import OracleScene2
+    v, s = soup2(*case)
+    sc = pkg.Scene2(v, s).compute_silhouettes().build_bvh()
+    orc = OracleScene2(v, s)
+    nodes, aabbs, _, _ = orc.tree()
+    assert np.array_equal(sc.export(pkg.ExportKind.NODES), nodes) and np.array_equal(bits(sc.export(pkg.ExportKind.AABBS)), bits(aabbs))
+    n = 6000
+    q = meshes.points_in_box2(n, v.min(0), v.max(0), 1.3, seed=3000 + case[0])
+    d = meshes.unit_directions2(n, seed=4000 + case[0])
+    _, odist = orc.closest(q)
+    rmax = (odist * meshes.star_radius_scale(n)).astype(np.float32)
+    osil = [orc.silhouette(q, False), orc.silhouette(q, True), orc.silhouette(q, False, rmax)]
+    of, ot, _, _ = orc.ray(q, d)
+    tm = np.full(n, 0.4 * case[4], np.float32)
+    of_t, ot_t, _, _ = orc.ray(q, d, tm)
+    sph = np.concatenate([q, (odist * 1.5 + 0.05 * float(odist.max()))[:, None]], axis=1).astype(np.float32)
+    u = meshes.uniforms(n, 2, seed=45)
+    oi, opdf = orc.sample(sph, u[:, 0].copy())
+    for wide in (131072, 0):
+        sc.set_option("query.wide_max_n", wide).set_option("query.sort_min_n", 16384 if wide else 1)
+        _, dist = sc.closest_point(q)
+        assert np.array_equal(bits(dist), bits(odist)), f"closest distance (wide_max_n={wide})"
+        sil = [sc.closest_silhouette(q), sc.closest_silhouette(q, flip=True), sc.closest_silhouette(q, r_max=rmax)]
+        for a, b in zip(sil, osil):
+            assert np.array_equal(bits(a), bits(b)), f"silhouette distance (wide_max_n={wide})"
+        dv, vid, pt = sc.closest_silhouette(q, r_max=rmax, with_vertex=True)
+        assert np.array_equal(bits(dv), bits(osil[2]))
+        fin = np.isfinite(dv)
+        assert np.all(vid[~fin] == 0xFFFFFFFF)
+        assert np.allclose(np.linalg.norm(pt[fin].astype(np.float64) - q[fin], axis=1), dv[fin], rtol=1e-5, atol=1e-6 * case[4] + 1e-7 * abs(case[3]))
+        found, hits = sc.intersect(q, d)
+        assert np.array_equal(found.astype(bool), of.astype(bool)) and np.array_equal(bits(hits["t"]), bits(ot)), f"rays (wide_max_n={wide})"
+        found_t, hits_t = sc.intersect(q, d, t_max=tm)
+        assert np.array_equal(found_t.astype(bool), of_t.astype(bool)) and np.array_equal(bits(hits_t["t"]), bits(ot_t))
+        si, pdf, _ = sc.sample_in_sphere(sph, u)
+        assert np.array_equal(si, oi) and np.array_equal(bits(pdf), bits(opdf)), f"sample (wide_max_n={wide})"

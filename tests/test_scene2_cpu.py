@@ -110,6 +110,35 @@ def test_oracle2_is_the_reference(pkg):
         assert np.array_equal(oi, ri) and np.array_equal(op.view(np.uint32), rp.view(np.uint32))
 
 
+def test_oracle2_is_the_reference_on_soups(pkg):
+    """... and on the random segment soups of test_gpu_fuzz.py (vertices of any valence, duplicates, far / tiny coordinates)."""
+    if not ref_available("cpu"):
+        pytest.skip("oracle/_ref/libsnch_ref_cpu.so not built (needs /root/reference)")
+    from oracle import OracleScene2, RefScene2
+    from test_gpu_fuzz import CASES2, soup2
+    m = pkg.meshes
+    for case in CASES2[:5]:
+        v, s = soup2(*case)
+        o, r = OracleScene2(v, s), RefScene2(v, s, "cpu")
+        on, oa, oc, q1 = o.tree()
+        rn, ra, rc = r.tree()
+        assert np.array_equal(on, rn) and np.array_equal(oa.view(np.uint32), ra.view(np.uint32))
+        _same_cones(oc, rc, q1)
+        q = m.points_in_box2(2000, v.min(0), v.max(0), 1.3, seed=3000 + case[0])
+        d = m.unit_directions2(2000, seed=4000 + case[0])
+        (oi, od), (ri, rd) = o.closest(q), r.closest(q)
+        assert np.array_equal(od.view(np.uint32), rd.view(np.uint32))
+        if not q1.any():  # (a Q1 node's half-angle is whatever the reference's stack held)
+            for fl in (False, True):
+                assert np.array_equal(o.silhouette(q, fl).view(np.uint32), r.silhouette(q, fl).view(np.uint32))
+        (of, ot, _, _), (rf, rt, _, _) = o.ray(q, d), r.ray(q, d)
+        assert np.array_equal(of, rf) and np.array_equal(ot.view(np.uint32), rt.view(np.uint32))
+        sph = np.concatenate([q, (od * 1.5 + 0.05 * float(od.max()))[:, None]], 1).astype(np.float32)
+        u = m.uniforms(2000, seed=5)
+        (oi, op), (ri, rp) = o.sample(sph, u), r.sample(sph, u)
+        assert np.array_equal(oi, ri) and np.array_equal(op.view(np.uint32), rp.view(np.uint32))
+
+
 def test_argument_errors_2d(pkg):
     v = np.zeros((3, 2), np.float32)
     with pytest.raises(pkg.SnchError) as e:
