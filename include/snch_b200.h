@@ -316,6 +316,12 @@ int snch_scene_adopt_arena(const void *arena_copy, uint64_t bytes, int device, s
 int snch_scene_save(const snch_scene *s, const char *path);
 int snch_scene_load(const char *path, int device, snch_stream stream, snch_scene **out);
 
+/* Self-test of the device math: out[i] = f(x[i]) evaluated ON THE DEVICE by the routine the build uses where the reference's
+ * CPU build calls its libm (include/snch_lbvh/core/host_libm.cuh): which = 0 acosf, 1 sinf, 2 cosf, 3 logf.  Host pointers.
+ * The cone refit (core/cone.cuh:34-66, 288-302, 427-480) and scene<2>::green_weight (scene.cuh:606-613) are bit-identical to
+ * the reference's CPU build because these are; tests/test_gpu_host_libm.py compares them with the host's libm. */
+int snch_selftest_host_libm(int which, const float *x, uint64_t n, float *out, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,15 +23,15 @@ namespace detail
 {
 template <typename T> SNCH_LBVH_CALLABLE T pi() noexcept { return T(3.14159265358979323846); }
 template <typename T> SNCH_LBVH_CALLABLE T half_pi() noexcept { return T(1.57079632679489661923); }
-SNCH_LBVH_CALLABLE float acos_of(float x) noexcept { return ::acosf(x); }
+SNCH_LBVH_CALLABLE float acos_of(float x) noexcept { return acosf_host(x); } // glibc's bits on the device too (host_libm.cuh)
 SNCH_LBVH_CALLABLE double acos_of(double x) noexcept { return ::acos(x); }
 SNCH_LBVH_CALLABLE float asin_of(float x) noexcept { return ::asinf(x); }
 SNCH_LBVH_CALLABLE double asin_of(double x) noexcept { return ::asin(x); }
 SNCH_LBVH_CALLABLE float atan2_of(float y, float x) noexcept { return ::atan2f(y, x); }
 SNCH_LBVH_CALLABLE double atan2_of(double y, double x) noexcept { return ::atan2(y, x); }
-SNCH_LBVH_CALLABLE float cos_of(float x) noexcept { return ::cosf(x); }
+SNCH_LBVH_CALLABLE float cos_of(float x) noexcept { return cosf_host(x); }
 SNCH_LBVH_CALLABLE double cos_of(double x) noexcept { return ::cos(x); }
-SNCH_LBVH_CALLABLE float sin_of(float x) noexcept { return ::sinf(x); }
+SNCH_LBVH_CALLABLE float sin_of(float x) noexcept { return sinf_host(x); }
 SNCH_LBVH_CALLABLE double sin_of(double x) noexcept { return ::sin(x); }
 // angle between two unit vectors, dot clamped into acos' domain
 template <typename V> SNCH_LBVH_CALLABLE scalar_of<V> angle_between(const V &a, const V &b) noexcept

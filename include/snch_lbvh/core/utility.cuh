@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 #include <vector_types.h>
 
+#include "host_libm.cuh"
+
 #ifdef __CUDACC__
 #define SNCH_LBVH_DEVICE __device__
 #define SNCH_LBVH_HOST __host__
@@ -80,40 +82,7 @@ template <typename V, typename F> SNCH_LBVH_CALLABLE V map2(const V &a, const V 
 SNCH_LBVH_CALLABLE float sqrt_of(float x) noexcept { return ::sqrtf(x); }
 SNCH_LBVH_CALLABLE double sqrt_of(double x) noexcept { return ::sqrt(x); }
 SNCH_LBVH_CALLABLE float abs_of(float x) noexcept { return ::fabsf(x); }
-// Natural logarithm with the HOST libm's bits on the device.  scene<2>::green_weight is |ln r| / 2 pi and feeds the sampling
-// pdf; CUDA's logf and glibc's differ in the last place on a fifth of the arguments.  glibc's logf (2.28 and later,
-// sysdeps/ieee754/flt-32/e_logf.c — the algorithm of ARM's optimized routines) is a 16-entry table and a cubic evaluated in
-// double and rounded once; the restatement below gave glibc 2.39's result on every positive normal float (2 130 706 432
-// arguments, with and without contracted multiply-adds: the contraction never reaches the rounded float).  Zero, subnormal,
-// negative, infinite and NaN arguments keep the device libm (green_weight clamps its argument at 1e-2).
-SNCH_LBVH_CALLABLE float log_of(float x) noexcept
-{
-#ifdef __CUDA_ARCH__
-    const unsigned int ix = __float_as_uint(x);
-    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) return ::logf(x);
-    if (ix == 0x3f800000u) return 0.0f;
-    constexpr unsigned long long tab[32] = {
-        0x3ff661ec79f8f3beull, 0xbfd57bf7808caadeull, 0x3ff571ed4aaf883dull, 0xbfd2bef0a7c06ddbull, 0x3ff49539f0f010b0ull, 0xbfd01eae7f513a67ull,
-        0x3ff3c995b0b80385ull, 0xbfcb31d8a68224e9ull, 0x3ff30d190c8864a5ull, 0xbfc6574f0ac07758ull, 0x3ff25e227b0b8ea0ull, 0xbfc1aa2bc79c8100ull,
-        0x3ff1bb4a4a1a343full, 0xbfba4e76ce8c0e5eull, 0x3ff12358f08ae5baull, 0xbfb1973c5a611cccull, 0x3ff0953f419900a7ull, 0xbfa252f438e10c1eull,
-        0x3ff0000000000000ull, 0x0000000000000000ull, 0x3fee608cfd9a47acull, 0x3faaa5aa5df25984ull, 0x3feca4b31f026aa0ull, 0x3fbc5e53aa362eb4ull,
-        0x3feb2036576afce6ull, 0x3fc526e57720db08ull, 0x3fe9c2d163a1aa2dull, 0x3fcbc2860d224770ull, 0x3fe886e6037841edull, 0x3fd1058bc8a07ee1ull,
-        0x3fe767dcf5534862ull, 0x3fd4043057b6ee09ull}; // {1 / c, ln c} for the sixteen subintervals of [0.7, 1.4)
-    const unsigned int tmp = ix - 0x3f330000u;
-    const int i = (int)((tmp >> 19) & 15u), k = (int)tmp >> 23;
-    const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
-    const double r = __dsub_rn(__dmul_rn(z, __longlong_as_double((long long)tab[2 * i])), 1.0);
-    const double y0 = __dadd_rn(__longlong_as_double((long long)tab[2 * i + 1]), __dmul_rn((double)k, __longlong_as_double(0x3fe62e42fefa39efll)));
-    const double r2 = __dmul_rn(r, r);
-    double y = __dadd_rn(__dmul_rn(__longlong_as_double(0x3fd5575b0be00b6all), r), __longlong_as_double((long long)0xbfdffffef20a4123ull));
-    y = __dadd_rn(__dmul_rn(__longlong_as_double((long long)0xbfd00ea348b88334ull), r2), y);
-    y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
-    return (float)y;
-#else
-    return ::logf(x);
-#endif
-}
-SNCH_LBVH_CALLABLE double abs_of(double x) noexcept { return ::fabs(x); }
+SNCH_LBVH_CALLABLE float log_of(float x) noexcept { return logf_host(x); } // glibc's bits on the device too (host_libm.cuh)
 // std::min / std::max semantics (return the first argument on ties and when a NaN is involved the way `b < a ? b : a` does)
 template <typename T> SNCH_LBVH_CALLABLE T min_of(T a, T b) noexcept { return (b < a) ? b : a; }
 template <typename T> SNCH_LBVH_CALLABLE T max_of(T a, T b) noexcept { return (a < b) ? b : a; }

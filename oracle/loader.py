@@ -69,6 +69,7 @@ def oracle_lib():
     L.orc_closest_must_visit.argtypes = [vp, _f32p, C.c_long, dp, dp]
     L.orc_silhouette_must_visit.argtypes = [vp, _f32p, C.c_long, C.c_int, C.c_void_p, dp, dp]
     L.orc_ray_must_visit.argtypes = [vp, _f32p, _f32p, _f32p, C.c_long, dp, dp]
+    L.orc_host_libm.argtypes = [C.c_int, _f32p, C.c_long, _f32p]
     L.orc_morton3.argtypes = [C.c_float, C.c_float, C.c_float]
     L.orc_morton3.restype = C.c_uint32
     L.orc_expand_bits.argtypes = [C.c_uint32]
@@ -317,6 +318,14 @@ class OracleScene2:
         idx, pdf = np.zeros(len(sph), np.int32), np.zeros(len(sph), np.float32)
         self.L.orc2_sample(self.h, sph, u, len(sph), idx, pdf)
         return idx, pdf
+
+
+def host_libm(which: int, x) -> np.ndarray:
+    """acosf (0) / sinf (1) / cosf (2) / logf (3) of the HOST's libm, element-wise"""
+    x = _f32(x)
+    out = np.empty_like(x)
+    oracle_lib().orc_host_libm(which, x, x.size, out)
+    return out
 
 
 def ref_available(kind: str = "cpu") -> bool:

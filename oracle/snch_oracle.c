@@ -1281,3 +1281,13 @@ void orc_ray_must_visit(const orc_scene *s, const float *org, const float *dir, 
     *mean_internal = n ? (double)vi / (double)n : 0;
     *mean_leaves = n ? (double)vl / (double)n : 0;
 }
+
+/* the HOST libm, for tests/test_gpu_host_libm.py: which = 0 acosf, 1 sinf, 2 cosf, 3 logf */
+void orc_host_libm(int which, const float *x, long n, float *out)
+{
+    for (long i = 0; i < n; ++i)
+    {
+        volatile float v = x[i];
+        out[i] = which == 0 ? acosf(v) : which == 1 ? sinf(v) : which == 2 ? cosf(v) : logf(v);
+    }
+}

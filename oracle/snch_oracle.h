@@ -51,6 +51,7 @@ void orc_closest_brute(const orc_scene *s, const float *q, long n, uint32_t *idx
 void orc_ray_brute(const orc_scene *s, const float *org, const float *dir, const float *tmax, long n, int *found, float *t,
                    uint32_t *prim, int nthreads);
 /* distance from q to triangle `idx` with the reference's distance_calculator (tie-aware index checks) */
+void orc_host_libm(int which, const float *x, long n, float *out); /* the host's acosf / sinf / cosf / logf */
 void orc_point_triangle_distance(const orc_scene *s, const float *q, const uint32_t *idx, long n, float *dist);
 
 /* must-visit statistics for the roofline: mean internal nodes / leaves any exact traversal must open */

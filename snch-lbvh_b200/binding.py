@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "snch_scene2_create", "snch_scene2_destroy", "snch_scene2_compute_silhouettes", "snch_scene2_build", "snch_scene2_stats",
     "snch_scene2_device_repr", "snch_scene2_export", "snch_scene2_set_option", "snch_closest_point_batch2",
     "snch_closest_silhouette_batch2", "snch_intersect_batch2", "snch_sample_in_sphere_batch2",
+    "snch_selftest_host_libm",
 ]
 
 

@@ -421,8 +421,8 @@ SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
             for (int s = 0; s < 3; ++s)
             {
                 if (owned[s] == -1) continue;
-                cone.half_angle = std_max(cone.half_angle, acosf(std_max(-1.0f, std_min(1.0f, dot(cone.axis, fn0[s])))));
-                cone.half_angle = std_max(cone.half_angle, acosf(std_max(-1.0f, std_min(1.0f, dot(cone.axis, fn1[s])))));
+                cone.half_angle = std_max(cone.half_angle, lbvh::detail::acosf_host(std_max(-1.0f, std_min(1.0f, dot(cone.axis, fn0[s])))));
+                cone.half_angle = std_max(cone.half_angle, lbvh::detail::acosf_host(std_max(-1.0f, std_min(1.0f, dot(cone.axis, fn1[s])))));
             }
         }
     }

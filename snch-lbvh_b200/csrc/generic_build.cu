@@ -245,3 +245,55 @@ extern "C" int snch_lbvh_build(int dim, uint32_t n, const void *leaf_aabbs, cons
                     : build_generic<3>(n, leaf_aabbs, leaf_cones, morton_codes, nodes, aabbs, cones, sorted_index_out, morton_sorted_out,
                                        collision_out, (cudaStream_t)stream);
 }
+
+// ---- self-test of the device restatements of the host libm (include/snch_lbvh/core/host_libm.cuh) ------------------------
+namespace snch
+{
+namespace
+{
+__global__ void k_selftest_libm(int which, const float *__restrict__ x, uint64_t n, float *__restrict__ out)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        const float v = x[i];
+        out[i] = which == 0 ? lbvh::detail::acosf_host(v) : which == 1 ? lbvh::detail::sinf_host(v) : which == 2 ? lbvh::detail::cosf_host(v) : lbvh::detail::logf_host(v);
+    }
+}
+} // namespace
+} // namespace snch
+
+extern "C" int snch_selftest_host_libm(int which, const float *x, uint64_t n, float *out, int device)
+{
+    using namespace snch;
+    if (which < 0 || which > 3 || (n && (!x || !out)))
+    {
+        set_error("snch_selftest_host_libm: which must be 0..3 and the arrays non-null");
+        return SNCH_ERR_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+    {
+        cudaGetLastError();
+        set_error("no CUDA device available (this library has no CPU fallback)");
+        return SNCH_ERR_CUDA;
+    }
+    if (n == 0) return SNCH_OK;
+    int prev = 0;
+    SNCH_CUDA(cudaGetDevice(&prev));
+    SNCH_CUDA(cudaSetDevice(device));
+    float *dx = nullptr, *dy = nullptr;
+    cudaError_t e = cudaMalloc(&dx, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dy, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+    {
+        k_selftest_libm<<<1184, 256>>>(which, dx, n, dy);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dy, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dy);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "snch_selftest_host_libm");
+    return SNCH_OK;
+}

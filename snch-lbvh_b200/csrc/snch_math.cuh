@@ -9,6 +9,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/snch_lbvh/core/host_libm.cuh" // glibc's acosf / sinf / cosf bits on the device (cone refit: parity with the reference's CPU build)
+
 namespace snch
 {
 
@@ -172,7 +174,7 @@ SNCH_DI bool cone_overlap(V3 axis, float half_angle, float radius, V3 o, V3 lo, 
 }
 SNCH_DI V3 rotate_towards(V3 u, V3 v, float theta) // cone.cuh:288-302 (Rodrigues)
 {
-    const float ct = cosf(theta), st = sinf(theta);
+    const float ct = lbvh::detail::cosf_host(theta), st = lbvh::detail::sinf_host(theta);
     const V3 w = normalize(cross(u, v));
     const V3 o = V3{(1.0f - ct) * w.x, (1.0f - ct) * w.y, (1.0f - ct) * w.z};
     const float r00 = ct + o.x * w.x, r01 = o.y * w.x - st * w.z, r02 = o.z * w.x + st * w.y;
@@ -204,7 +206,7 @@ SNCH_DI Cone cone_merge(Cone ca, Cone cb, V3 oa, V3 ob, V3 on, bool *q1)
             ha = hb;
             hb = th;
         }
-        const float theta = acosf(std_max(-1.0f, std_min(1.0f, dot(axis_a, axis_b))));
+        const float theta = lbvh::detail::acosf_host(std_max(-1.0f, std_min(1.0f, dot(axis_a, axis_b))));
         if (std_min(theta + hb, kPi) <= ha)
         {
             r.axis = axis_a;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import OracleScene
-from parity import bits, check_build_vs_oracle, check_closest, check_rays, check_silhouette, check_silhouette_edges
+from parity import bits, check_build_vs_oracle, check_closest, check_rays, check_silhouette, check_silhouette_edges, same_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -177,8 +177,11 @@ def test_fuzz_2d(pkg, meshes, case):
     v, s = soup2(*case)
     sc = pkg.Scene2(v, s).compute_silhouettes().build_bvh()
     orc = OracleScene2(v, s)
-    nodes, aabbs, _, _ = orc.tree()
+    nodes, aabbs, cones, q1 = orc.tree()
     assert np.array_equal(sc.export(pkg.ExportKind.NODES), nodes) and np.array_equal(bits(sc.export(pkg.ExportKind.AABBS)), bits(aabbs))
+    mine = sc.export(pkg.ExportKind.CONES)
+    keep = (cones[:, 2] >= 0) & ~q1.astype(bool)
+    assert np.array_equal(mine[:, 2] >= 0, cones[:, 2] >= 0) and same_bits(mine[keep], cones[keep]).all(), "2-D cones differ from the oracle's"
     n = 6000
     q = meshes.points_in_box2(n, v.min(0), v.max(0), 1.3, seed=3000 + case[0])
     d = meshes.unit_directions2(n, seed=4000 + case[0])
