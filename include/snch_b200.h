@@ -203,6 +203,10 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *                       where they are met, for every batch; 2 = parked leaves for every batch
  *   "query.ray_flush" / "query.ray_refill"  parked / idle lanes of a warp that trigger the triangle tests / the next draw (8 / 8)
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
+ *   "query.host_first"  host-pointer batches that are split: queries of the first chunk, whose H2D copy nothing overlaps
+ *                       (default 0 = an eighth of the batch within [512K, 2M]; -1 = like the other chunks)
+ *   "query.host_split_min"  host-pointer batches of at least this many queries are split even when they fit one chunk
+ *                       (default 3145728; 0 = only batches larger than "query.host_chunk")
  *   "query.blocks_per_sm" cap on resident CTAs per SM of the persistent kernels (default 0 = occupancy limit)
  *   "build.refit_kernel" 1 = CTA-cooperative refit (default), 0 = per-thread climb; "sort.onesweep" 1 = onesweep radix sort
  *                       (default), 0 = three-kernel passes; "sort.lookback" predecessor tiles a tile reads per round trip of its

@@ -171,9 +171,36 @@ struct Stager
     {
         if (status != SNCH_OK) return status;
         chunk = chunk_queries ? chunk_queries : m;
-        if ((m + chunk - 1) / chunk > (uint64_t)kMaxChunks) chunk = (m + kMaxChunks - 1) / kMaxChunks;
+        if ((m + chunk - 1) / chunk > (uint64_t)(kMaxChunks - 1)) chunk = (m + kMaxChunks - 2) / (kMaxChunks - 1);
         chunk = (chunk + 31) & ~31ull; // keep every chunk's staged arrays 32 B aligned (float3 x 32, byte x 32)
-        n_chunks = (int)((m + chunk - 1) / chunk);
+        // Chunk schedule: nothing overlaps the first chunk's H2D copy, so a batch of at least "query.host_split_min" queries
+        // starts with a SHORT chunk ("query.host_first": 0 = an eighth of the batch within [512K, 2M], -1 = like the others)
+        // and the rest is cut into equal parts of at most `chunk` queries.  Measured on C3 (profiles/r2x_e2e_chunks.json):
+        // 16.7M queries 53.1 -> 51.8 ms, 8.4M 28.2 -> 26.9, 4.2M 14.8 -> 14.3; a 2M batch gains nothing from a split.
+        uint64_t starts[kMaxChunks + 1];
+        n_chunks = 0;
+        starts[0] = 0;
+        uint64_t first = chunk;
+        if (s->tuning.host_first > 0) first = (uint64_t)s->tuning.host_first;
+        else if (s->tuning.host_first == 0)
+        {
+            first = m / 8;
+            first = first < (1ull << 19) ? (1ull << 19) : (first > (1ull << 21) ? (1ull << 21) : first);
+        }
+        first = ((first < chunk ? first : chunk) + 31) & ~31ull;
+        const bool split_small = s->tuning.host_first >= 0 && s->tuning.host_split_min > 0 && m >= (uint64_t)s->tuning.host_split_min && m > 2 * first;
+        if (chunk_queries && (m > chunk || split_small))
+        {
+            const uint64_t rest = m - first, parts = (rest + chunk - 1) / chunk;
+            const uint64_t each = ((rest + parts - 1) / parts + 31) & ~31ull;
+            starts[++n_chunks] = first;
+            while (starts[n_chunks] < m)
+            {
+                starts[n_chunks + 1] = starts[n_chunks] + each < m ? starts[n_chunks] + each : m;
+                ++n_chunks;
+            }
+        }
+        else starts[n_chunks = 1] = m;
         if (n_chunks <= 1)
         { // small batch: everything on the caller's stream
             for (int i = 0; i < n_arrs; ++i)
@@ -206,7 +233,7 @@ struct Stager
         cudaEvent_t h2d_done[kMaxChunks];
         for (int c = 0; c < n_chunks; ++c)
         {
-            const uint64_t o = (uint64_t)c * chunk, cnt = m - o < chunk ? m - o : chunk;
+            const uint64_t o = starts[c], cnt = starts[c + 1] - o;
             for (int i = 0; i < n_arrs; ++i)
                 if (arrs[i].src)
                 {
@@ -219,7 +246,7 @@ struct Stager
         }
         for (int c = 0; c < n_chunks; ++c)
         {
-            const uint64_t o = (uint64_t)c * chunk, cnt = m - o < chunk ? m - o : chunk;
+            const uint64_t o = starts[c], cnt = starts[c + 1] - o;
             cudaStream_t cs = lanes[c & 1];
             if ((e = cudaStreamWaitEvent(cs, h2d_done[c], 0)) != cudaSuccess) return fail(e, "cudaStreamWaitEvent");
             const int rc = launch(o, cnt, cs, c & 1);
@@ -259,7 +286,7 @@ static uint64_t host_chunk(const snch_scene *s, uint64_t m)
 {
     uint64_t c = s->tuning.host_chunk > 0 ? (uint64_t)s->tuning.host_chunk : m;
     if (c > m) c = m;
-    if ((m + c - 1) / c > (uint64_t)Stager::kMaxChunks) c = (m + Stager::kMaxChunks - 1) / Stager::kMaxChunks;
+    if ((m + c - 1) / c > (uint64_t)(Stager::kMaxChunks - 1)) c = (m + Stager::kMaxChunks - 2) / (Stager::kMaxChunks - 1);
     return (c + 31) & ~31ull;
 }
 
@@ -829,6 +856,8 @@ int snch_scene_set_option(snch_scene *s, const char *name, int64_t value)
     else if (k == "query.ray_refill") t.ray_refill = (int)value;
     else if (k == "query.blocks_per_sm") t.blocks_per_sm = (int)value;
     else if (k == "query.host_chunk") t.host_chunk = (int)(value < 0 ? 0 : value);
+    else if (k == "query.host_first") t.host_first = (int)(value < 0 ? -1 : value);
+    else if (k == "query.host_split_min") t.host_split_min = (int)(value < 0 ? 0 : value);
     else if (k == "query.time_kernels") s->counters.time_kernels = (int)value;
     else if (k == "adjacency.device") s->adjacency_mode = (int)value;
     else if (k == "build.refit_kernel") s->opt_refit_kernel = (int)value;

@@ -37,6 +37,10 @@ struct QueryTuning
     int ray_refill = 8;
     int ray_prefetch = 1;   // k_intersect_parked: ask L2 for the record of a child when it is pushed     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays
     int blocks_per_sm = 0;  // cap on resident CTAs per SM of the persistent kernels (0 = occupancy limit)
+    int host_first = 0;       // host-pointer batches that are split: queries of the FIRST chunk (nothing overlaps its H2D copy);
+                              // 0 = an eighth of the batch within [512K, 2M], -1 = like the other chunks
+    int host_split_min = 3 << 20; // host-pointer batches of at least this many queries are split (short first chunk + the rest) even
+                              // when they fit one chunk; 0 = only batches larger than "query.host_chunk" are split
     int host_chunk = 1 << 23; // host-pointer batches: queries per pipeline chunk (H2D / kernels / D2H overlap); 0 = one chunk.
                               // Measured on C3 (16.7M queries): 0 -> 60.5 ms, 8M -> 59.5, 4M -> 60.0, 2M -> 63.5, 1M -> 73.1: every extra
                               // launch pays its own tail and orders a sparser batch, so chunks stay large

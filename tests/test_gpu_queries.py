@@ -216,7 +216,7 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
     rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(n)).astype(np.float32)
     # the baseline forces the per-lane / packet kernels (the wide ones would take a batch this small); variants re-enable them
     defaults = {"query.sort_min_n": 16384, "query.sort_bits": 24, "query.sort_rays": 0, "query.cone_filter": 1, "query.seed": 1,
-                "query.blocks_per_sm": 0, "query.host_chunk": 1 << 23, "query.sort_radius": 0, "query.sil_tail": 8, "query.sil_flush": 24, "query.sil_chunk": 0,
+                "query.blocks_per_sm": 0, "query.host_chunk": 1 << 23, "query.host_first": 0, "query.host_split_min": 3 << 20, "query.sort_radius": 0, "query.sil_tail": 8, "query.sil_flush": 24, "query.sil_chunk": 0,
                 "query.wide_max_n": 0, "query.wide_max_n_sil": 0, "query.ray_kernel": 2, "query.ray_flush": 8, "query.ray_refill": 8}
 
     def run():
@@ -246,6 +246,8 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
                 {"query.ray_flush": 1, "query.ray_refill": 1}, {"query.ray_flush": 32, "query.ray_refill": 32}, {"query.ray_flush": 16, "query.sort_rays": 1},
                 {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
                 {"query.host_chunk": 7001}, {"query.host_chunk": 0}, {"query.host_chunk": 500, "query.sort_min_n": 0},  # host-pointer pipeline
+                {"query.host_first": 1000, "query.host_split_min": 1}, {"query.host_first": 20000, "query.host_split_min": 1, "query.host_chunk": 17000},
+                {"query.host_first": -1, "query.host_chunk": 25000}, {"query.host_first": 1, "query.host_chunk": 3000},
                 {"query.sort_min_n": 0, "query.cone_filter": 0, "query.seed": 0, "query.sil_tail": 0, "query.ray_kernel": 0}]
     for kv in variants:
         for k, val in {**defaults, **kv}.items():
