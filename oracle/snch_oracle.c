@@ -1291,3 +1291,80 @@ void orc_host_libm(int which, const float *x, long n, float *out)
         out[i] = which == 0 ? acosf(v) : which == 1 ? sinf(v) : which == 2 ? cosf(v) : logf(v);
     }
 }
+
+/* What a NEAR-FIRST walk with immediate leaf tests visits (tools/visit_sim.py): the nearer surviving child first, the other on
+ * the stack with its box distance, rejected at pop time against the bound of that moment — the GPU kernels' order when a
+ * leaf's edges are tested the moment the leaf is reached.  Same answer as the reference's walk; only the counts are reported:
+ * internal nodes opened, leaves tested.  `defer` > 0 models the kernels' leaf queue: a leaf's result only tightens the bound
+ * after `defer` further nodes have been opened. */
+static long g_need_axis;
+long orc_need_axis_count(int reset) { const long v = g_need_axis; if (reset) g_need_axis = 0; return v; }
+void orc_silhouette_nearfirst_visits(const orc_scene *s, const float *q, long n, int flip, const float *r_max, int defer, double *mean_internal,
+                                     double *mean_leaves)
+{
+    long vi = 0, vl = 0;
+    for (long i = 0; i < n && s->nT > 1; ++i)
+    {
+        const f3 p = mk3(q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+        float best = r_max ? r_max[i] : INFINITY;
+        float pend_d[64];
+        long pend_at[64];
+        int np = 0;
+        long opened = 0;
+        stack_entry st[STACK_CAP];
+        int sp = 0;
+        uint32_t node = 0;
+        for (;;)
+        {
+            /* deferred results that are due */
+            int k = 0;
+            for (int j = 0; j < np; ++j)
+            {
+                if (pend_at[j] <= opened) { if (pend_d[j] <= best) best = pend_d[j]; }
+                else { pend_d[k] = pend_d[j]; pend_at[k] = pend_at[j]; ++k; }
+            }
+            np = k;
+            ++vi; ++opened;
+            const uint32_t ch[2] = {s->nodes[node].left, s->nodes[node].right};
+            float md[2];
+            int hit[2], need_axis = 0;
+            for (int c = 0; c < 2; ++c)
+            {
+                md[c] = box_mindist(s->aabbs[ch[c]], p);
+                hit[c] = md[c] <= best * best && cone_valid(&s->cones[ch[c]]) && cone_overlap(&s->cones[ch[c]], p, s->aabbs[ch[c]], md[c]);
+                /* would this child's test have read the cone's axis / radius?  (cone.cuh:174: wide cones and points inside the box pass at once) */
+                if (md[c] <= best * best && cone_valid(&s->cones[ch[c]]) && s->cones[ch[c]].half_angle < ORC_PI_2_F && !(md[c] < FLT_EPSILON)) need_axis = 1;
+            }
+            g_need_axis += need_axis;
+            const int first = md[1] < md[0] ? 1 : 0;
+            uint32_t next = LEAF_NONE;
+            for (int t = 0; t < 2; ++t)
+            {
+                const int c = t == 0 ? first : 1 - first;
+                if (!hit[c]) continue;
+                const uint32_t obj = s->nodes[ch[c]].object;
+                if (obj != LEAF_NONE)
+                {
+                    ++vl;
+                    float d = INFINITY;
+                    if (tri_closest_silhouette(s, (int)obj, p, best * best, &d, flip, 0.0f, NULL, NULL) && d <= best)
+                    {
+                        if (defer <= 0 || np >= 64) best = d;
+                        else { pend_d[np] = d; pend_at[np] = opened + defer; ++np; }
+                    }
+                }
+                else if (next == LEAF_NONE) next = ch[c];
+                else { st[sp].node = ch[c]; st[sp].key = md[c]; ++sp; }
+            }
+            while (next == LEAF_NONE && sp > 0)
+            {
+                --sp;
+                if (st[sp].key <= best * best) next = st[sp].node;
+            }
+            if (next == LEAF_NONE) break;
+            node = next;
+        }
+    }
+    *mean_internal = n ? (double)vi / (double)n : 0;
+    *mean_leaves = n ? (double)vl / (double)n : 0;
+}
