@@ -124,7 +124,9 @@ int snch_closest_point_batch(const snch_scene *s, const float *points_xyz, uint6
 
 /* query_device(bvh, nearest_silhouette(p, flip), scene<3>::silhouette_distance_calculator()) -> distance   query.cuh:325-423
  * r_max (NULL = unbounded, the reference behaviour): search radius per query; result is +inf when no silhouette point
- * lies within it — identical to filtering the unbounded answer.  flip: one byte per query, or NULL = false.
+ * lies within it — identical to filtering the unbounded answer, except that a radius whose square is zero finds
+ * nothing (r_max is the reference's max_radius: `min_radius_squared >= max_radius_squared -> false`, scene.cuh:791).  flip: one
+ * byte per query, or NULL = false.
  * Optional outputs (NULL = not wanted; asking for neither costs nothing) — what the reference computes and drops:
  *   out_edge      index in scene<3>::silhouettes of an edge attaining the distance ("TODO: identify nearest index",
  *                 query.cuh:386,411); 0xFFFFFFFF when the distance is +inf.  On exact ties any attaining edge.
@@ -199,8 +201,9 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
  *   "query.wide_max_n"  closest point: batches smaller than this — or with fewer than 2 queries per triangle — are walked one query
  *                       per warp (default 2097152; 0 = never)
  *   "query.wide_max_n_sil"  the same for silhouette batches (default 262144)
- *   "query.ray_kernel"  1 = reference-order ray walk with parked leaves for batches of 1M rays and more (default), 0 = leaves tested
- *                       where they are met, for every batch; 2 = parked leaves for every batch
+ *   "query.ray_kernel"  1 = reference-order ray walk with parked leaves (default; batches under 1M rays test a parked leaf at once),
+ *                       2 = the same with the large-batch setting for every batch, 0 = leaves tested where they are met (same hit
+ *                       flag and t; among triangles hit at the same t it keeps the first in its own order, not the reference's)
  *   "query.ray_flush" / "query.ray_refill"  parked / idle lanes of a warp that trigger the triangle tests / the next draw (8 / 8)
  *   "query.host_chunk"  host-pointer batches: queries per pipeline chunk (default 8388608; 0 = one chunk)
  *   "query.host_first"  host-pointer batches that are split: queries of the first chunk, whose H2D copy nothing overlaps

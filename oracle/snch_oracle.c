@@ -1299,14 +1299,30 @@ void orc_host_libm(int which, const float *x, long n, float *out)
  * after `defer` further nodes have been opened. */
 static long g_need_axis;
 long orc_need_axis_count(int reset) { const long v = g_need_axis; if (reset) g_need_axis = 0; return v; }
+static void nearfirst_walk(const orc_scene *s, const float *q, long n, int flip, const float *r_max, int defer, double *mean_internal,
+                           double *mean_leaves, float *dist_out);
 void orc_silhouette_nearfirst_visits(const orc_scene *s, const float *q, long n, int flip, const float *r_max, int defer, double *mean_internal,
                                      double *mean_leaves)
+{
+    nearfirst_walk(s, q, n, flip, r_max, defer, mean_internal, mean_leaves, NULL);
+}
+/* the distances such a walk returns (defer = 0): equal to the reference's whenever the answer does not depend on the order of
+ * the walk — i.e. unless the ROUNDED distance to an edge is smaller than the rounded distance to a box that holds it (far from
+ * the origin), see DESIGN.md "Far from the origin" */
+void orc_silhouette_nearfirst(const orc_scene *s, const float *q, long n, int flip, const float *r_max, float *dist)
+{
+    double a, b;
+    nearfirst_walk(s, q, n, flip, r_max, 0, &a, &b, dist);
+}
+static void nearfirst_walk(const orc_scene *s, const float *q, long n, int flip, const float *r_max, int defer, double *mean_internal,
+                           double *mean_leaves, float *dist_out)
 {
     long vi = 0, vl = 0;
     for (long i = 0; i < n && s->nT > 1; ++i)
     {
         const f3 p = mk3(q[3 * i], q[3 * i + 1], q[3 * i + 2]);
         float best = r_max ? r_max[i] : INFINITY;
+        int found_any = 0;
         float pend_d[64];
         long pend_at[64];
         int np = 0;
@@ -1349,6 +1365,7 @@ void orc_silhouette_nearfirst_visits(const orc_scene *s, const float *q, long n,
                     float d = INFINITY;
                     if (tri_closest_silhouette(s, (int)obj, p, best * best, &d, flip, 0.0f, NULL, NULL) && d <= best)
                     {
+                        found_any = 1;
                         if (defer <= 0 || np >= 64) best = d;
                         else { pend_d[np] = d; pend_at[np] = opened + defer; ++np; }
                     }
@@ -1364,6 +1381,7 @@ void orc_silhouette_nearfirst_visits(const orc_scene *s, const float *q, long n,
             if (next == LEAF_NONE) break;
             node = next;
         }
+        if (dist_out) dist_out[i] = found_any ? best : INFINITY;
     }
     *mean_internal = n ? (double)vi / (double)n : 0;
     *mean_leaves = n ? (double)vl / (double)n : 0;

@@ -527,7 +527,9 @@ SNCH_DI bool leaf_silhouette(const SceneView &sv, uint32_t first, uint32_t cnt, 
         const V3 pa = V3{e0.x, e0.y, e0.z}, pb = V3{e0.w, e1.x, e1.y};
         V3 cp;
         const float dist = point_segment_distance(pa, pb, p, &cp);
-        if (dist * dist > b2) continue;
+        // scene.cuh:791 `if (min_radius_squared >= max_radius_squared) return false` with min = 0: a bound whose square is zero (a
+        // star radius of 0: the query point lies on the surface) finds nothing, not even an edge at distance 0
+        if (0.0f >= b2 || dist * dist > b2) continue;
         bool is_sil = isnan(e1.z); // boundary edge
         if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
         if (is_sil && dist <= bound)
@@ -1520,10 +1522,10 @@ static void launch_intersect_kernel(const SceneView &v, const QueryTuning &t, co
                                     uint32_t n, snch_hit *hits, uint8_t *found, bool any_hit, unsigned long long *counter, cudaStream_t st,
                                     QueryCounters *qc)
 {
-    // A batch that does not fill the machine (one ray per lane: config C1, 64K rays) runs as long as its longest ray; there the
-    // plain per-lane walk with leaves tested where they are met has the shortest step (0.087 vs 0.104 ms on C1), so it keeps
-    // small batches.  ("query.ray_kernel" = 0 / 2 selects it / the parked walk for every batch: the A/B of the knob tests.)
-    if (t.ray_kernel == 0 || (t.ray_kernel == 1 && n < (1u << 20)))
+    // "query.ray_kernel" = 0: leaves tested where they are met (k_intersect), for every batch — the A/B of the knob tests.  Its
+    // hit flag and t equal the reference's, but among triangles hit at the SAME t (shared edges, duplicates, t = +0 / -0 for a
+    // ray that starts on the surface) it reports the first in ITS order, so the triangle — and the sign of a zero t — can differ.
+    if (t.ray_kernel == 0)
     {
         if (qc) qc->last_kernel = "k_intersect";
         if (any_hit) k_intersect<true><<<persistent_grid(k_intersect<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter);
@@ -1531,7 +1533,12 @@ static void launch_intersect_kernel(const SceneView &v, const QueryTuning &t, co
         return;
     }
     if (qc) qc->last_kernel = "k_intersect_parked";
-    const int fl = t.ray_flush < 1 ? 1 : t.ray_flush, rl = t.ray_refill < 1 ? 1 : t.ray_refill;
+    // The reference-order walk for every batch.  A batch that does not fill the machine (one ray per lane: config C1, 64K rays)
+    // runs as long as its longest ray, so there a lane tests its leaf at once (flush at 1 parked lane): 0.106 ms on C1 against
+    // 0.124 with the large-batch setting and 0.100 for k_intersect (tools/ray_small_exp.py); "query.ray_kernel" = 2 keeps the
+    // large-batch setting for every batch.
+    const bool small = t.ray_kernel == 1 && n < (1u << 20);
+    const int fl = small ? 1 : (t.ray_flush < 1 ? 1 : t.ray_flush), rl = t.ray_refill < 1 ? 1 : t.ray_refill;
     if (any_hit)
         k_intersect_parked<true><<<persistent_grid(k_intersect_parked<true>, t, n), kQueryThreads, 0, st>>>(v, o, d, tmax, perm, n, hits, found, counter, fl, rl);
     else

@@ -31,8 +31,9 @@ struct QueryTuning
     int wide_max_n_sil = 262144; // silhouette: the same for k_silhouette_wide (measured crossover 0.25-0.5M queries)
     int seed = 1;           // closest point: bit 0 = bound each query by the triangle that answered the lane's previous query;
                             // bit 1 = switch the per-triangle lower bound OFF (A/B)
-    int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked; batches under 1M rays keep k_intersect),
-                            // 0 = leaves tested where they are met (k_intersect) for every batch, 2 = parked leaves for every batch
+    int ray_kernel = 1;     // ray traversal: 1 = reference-order walk with parked leaves (k_intersect_parked; batches under 1M rays test a parked
+                            // leaf at once), 2 = the same with the large-batch flush for every batch, 0 = leaves tested where they are met
+                            // (k_intersect: same hit flag and t; among triangles hit at the same t its own order picks, not the reference's)
     int ray_flush = 8;      // k_intersect_parked: parked lanes of a warp that trigger the triangle tests
     int ray_refill = 8;
     int ray_prefetch = 1;   // k_intersect_parked: ask L2 for the record of a child when it is pushed     // k_intersect_parked: idle lanes of a warp that trigger the next draw of rays

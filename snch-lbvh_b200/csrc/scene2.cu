@@ -716,23 +716,23 @@ __global__ void __launch_bounds__(kQueryThreads)
             float t0, t1;
             const bool h0 = lbvh::intersects_d(ry, pr.b0, max_dist, &t0) && !(t0 > best_t);
             const bool h1 = lbvh::intersects_d(ry, pr.b1, max_dist, &t1) && !(t1 > best_t);
-            const bool swap = h1 && (!h0 || t1 < t0);
+            // The reference's order (query.cuh:128-160): the nearer hit child next (L on ties), the other — leaf or internal — on
+            // the stack with its entry distance; a leaf is tested when the walk REACHES it, not where it is met.  The first hit
+            // at a given t wins (t < best_t), so with segments meeting at a vertex, duplicated segments or a ray starting on the
+            // polyline (t = +0 / -0) the order decides which segment — and which sign of zero — is reported.
+            const bool swap = h0 && h1 && t1 < t0;
             uint32_t next = kNone;
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
+            if (h0 && h1) stk[sp++] = swap ? StackEntry{pr.r0, t0} : StackEntry{pr.r1, t1};
+            if (h0 || h1) next = (h0 && !swap) ? pr.r0 : pr.r1;
+            for (;;)
             {
-                const bool second = (ch == 1) != swap;
-                const bool h = second ? h1 : h0;
-                const float te = second ? t1 : t0;
-                const uint32_t r = second ? pr.r1 : pr.r0;
-                if (!h || te > best_t) continue;
-                if (r & kLeaf2) test_leaf(r & kRefIndex2);
-                else if (next == kNone) next = r;
-                else stk[sp++] = StackEntry{r, te};
-            }
-            if (kAnyHit && found) next = kNone, sp = 0;
-            while (next == kNone && sp > 0)
-            {
+                if (next != kNone && (next & kLeaf2))
+                {
+                    test_leaf(next & kRefIndex2);
+                    next = kNone;
+                    if (kAnyHit && found) sp = 0;
+                }
+                if (next != kNone || sp == 0) break;
                 const StackEntry se = stk[--sp];
                 if (!(se.key > best_t)) next = se.node;
             }

@@ -126,6 +126,17 @@ def check_silhouette_edges(q, dist, edge, point, orc, flip=False, r_max=None):
     return float(same.mean()) if fin.any() else 1.0
 
 
+def check_rays_exact(found, hits, q, d, tmax, orc):
+    """The reference-order kernels ("query.ray_kernel" 1, 2): hit flag, t, (u, v) AND the triangle are the oracle's bit for bit —
+    also where several triangles are hit at the same t (duplicates, shared edges, t = +0 / -0): the walk meets them in the
+    reference's order and keeps the first."""
+    f_o, t_o, uv_o, p_o = orc.ray(q, d, tmax, nthreads=8)
+    assert np.array_equal(found.astype(bool), f_o.astype(bool)), "ray hit flags differ"
+    assert np.array_equal(bits(hits["t"]), bits(t_o)), f"ray t differs on {np.count_nonzero(bits(hits['t']) != bits(t_o))} rays"
+    assert np.array_equal(hits["prim"].astype(np.uint32), p_o.astype(np.uint32)), f"ray triangle differs on {np.count_nonzero(hits['prim'].astype(np.uint32) != p_o.astype(np.uint32))} rays"
+    assert np.array_equal(bits(hits["u"]), bits(uv_o[:, 0])) and np.array_equal(bits(hits["v"]), bits(uv_o[:, 1])), "ray (u, v) differ"
+
+
 def check_rays(found, hits, q, d, tmax, orc, max_tie_frac=1e-3):
     """Hit flags and t BIT-IDENTICAL to the oracle's walk; the triangle and (u, v) too, except on exact ties (Q4: two
     triangles sharing an edge are hit at the same t — the kernel that tests leaves where it meets them reaches them in another

@@ -49,7 +49,7 @@ def test_silhouette_full_size(big, meshes):
     unb = sc.closest_silhouette(qd)
     torch.cuda.synchronize()
     inf = torch.full_like(unb, float("inf"))
-    assert torch.equal(bnd, torch.where(unb <= rmax, unb, inf)), "bounded search != filtered unbounded search"
+    assert torch.equal(bnd, torch.where((unb <= rmax) & (rmax * rmax > 0), unb, inf)), "bounded search != filtered unbounded search"
     assert torch.all((bnd <= rmax) | torch.isinf(bnd))
     assert torch.all(unb >= dcp * (1 - 1e-5) - 1e-6), "a silhouette point cannot be closer than the closest point"
     sel = np.random.default_rng(2).choice(NQ, 3000, replace=False)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import OracleScene
-from parity import bits, check_build_vs_oracle, check_closest, check_rays, check_silhouette, check_silhouette_edges, same_bits
+from parity import bits, check_build_vs_oracle, check_closest, check_rays_exact, check_silhouette, check_silhouette_edges, same_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -23,6 +23,24 @@ CASES = [
     (9, 100, 400, 0.0, 1.0, True),       # slivers: one coordinate squeezed by 1e-4
     (10, 2000, 20000, 0.0, 1.0, False),  # enough triangles for several sort tiles and refit CTAs
 ]
+
+
+def _extra_cases():
+    """SNCH_FUZZ_EXTRA=N adds N more soups with drawn parameters (seeds 101...): the long sweep of tools/gpu_fuzz_sweep.sh"""
+    import os
+    n = int(os.environ.get("SNCH_FUZZ_EXTRA", "0"))
+    out = []
+    for seed in range(101, 101 + n):
+        rng = np.random.default_rng(seed)
+        nv = int(rng.choice([5, 12, 40, 150, 600, 2500]))
+        nt = int(nv * rng.choice([0.7, 1.5, 2.0, 4.0, 20.0])) + 4
+        offset = float(rng.choice([0.0, 0.0, 3.0, 100.0, 1000.0, -5000.0]))
+        scale = float(rng.choice([1.0, 1.0, 1e-3, 50.0]))
+        out.append((seed, nv, nt, offset, scale, bool(rng.random() < 0.2)))
+    return out
+
+
+CASES += _extra_cases()
 
 
 def soup(seed, nv, nt, offset, scale, sliver):
@@ -75,7 +93,8 @@ def test_fuzz_silhouette(fuzz_scene, meshes, flip):
     dist_r, edge, pt = sc.closest_silhouette(q, flip=flip, r_max=rmax, with_edge=True)
     check_silhouette(dist_r, orc.silhouette(q, flip, r_max=rmax, nthreads=8))
     check_silhouette_edges(q, dist_r, edge, pt, orc, flip, r_max=rmax)
-    assert np.array_equal(bits(dist_r), bits(np.where(dist <= rmax, dist, np.inf).astype(np.float32)))
+    # bounded == filtered unbounded (Q5) — except that a radius whose square is zero finds nothing (scene.cuh:791: min_r2 >= max_r2)
+    assert np.array_equal(bits(dist_r), bits(np.where((dist <= rmax) & (rmax * rmax > 0), dist, np.inf).astype(np.float32)))
 
 
 @pytest.mark.parametrize("ray_kernel", [1, 2])
@@ -83,13 +102,11 @@ def test_fuzz_rays(fuzz_scene, ray_kernel):
     sc, orc, q, d, _ = fuzz_scene
     sc.set_option("query.ray_kernel", ray_kernel)
     found, hits = sc.intersect(q, d)
-    tm = np.full(len(q), 0.4, np.float32)
+    tm = np.full(len(q), 0.4 * float(np.ptp(orc.verts, axis=0).max()), np.float32)
     found_t, hits_t = sc.intersect(q, d, t_max=tm)
     sc.set_option("query.ray_kernel", 1)
-    # duplicated / coplanar overlapping triangles are hit at exactly the same t: which of them is reported is a tie (Q4) —
-    # every differing triangle is still verified in double precision to attain the bit-identical t
-    check_rays(found, hits, q, d, None, orc, max_tie_frac=1.0)
-    check_rays(found_t, hits_t, q, d, tm, orc, max_tie_frac=1.0)
+    check_rays_exact(found, hits, q, d, None, orc)
+    check_rays_exact(found_t, hits_t, q, d, tm, orc)
 
 
 def test_fuzz_sample(fuzz_scene, meshes):
@@ -159,6 +176,21 @@ CASES2 = [
 ]
 
 
+def _extra_cases2():
+    import os
+    n = int(os.environ.get("SNCH_FUZZ_EXTRA", "0"))
+    out = []
+    for seed in range(201, 201 + n):
+        rng = np.random.default_rng(seed)
+        nv = int(rng.choice([4, 10, 60, 400, 3000]))
+        ns = int(nv * rng.choice([0.8, 1.0, 2.0, 6.0])) + 3
+        out.append((seed, nv, ns, float(rng.choice([0.0, 0.0, 3.0, 1000.0, -5000.0])), float(rng.choice([1.0, 1.0, 1e-3, 50.0]))))
+    return out
+
+
+CASES2 += _extra_cases2()
+
+
 def soup2(seed, nv, ns, offset, scale):
     rng = np.random.default_rng(seed)
     v = (rng.random((nv, 2)) * scale + offset).astype(np.float32)
@@ -188,9 +220,9 @@ def test_fuzz_2d(pkg, meshes, case):
     _, odist = orc.closest(q)
     rmax = (odist * meshes.star_radius_scale(n)).astype(np.float32)
     osil = [orc.silhouette(q, False), orc.silhouette(q, True), orc.silhouette(q, False, rmax)]
-    of, ot, _, _ = orc.ray(q, d)
+    of, ot, _, op = orc.ray(q, d)
     tm = np.full(n, 0.4 * case[4], np.float32)
-    of_t, ot_t, _, _ = orc.ray(q, d, tm)
+    of_t, ot_t, _, op_t = orc.ray(q, d, tm)
     sph = np.concatenate([q, (odist * 1.5 + 0.05 * float(odist.max()))[:, None]], axis=1).astype(np.float32)
     u = meshes.uniforms(n, 2, seed=45)
     oi, opdf = orc.sample(sph, u[:, 0].copy())
@@ -208,7 +240,9 @@ def test_fuzz_2d(pkg, meshes, case):
         assert np.allclose(np.linalg.norm(pt[fin].astype(np.float64) - q[fin], axis=1), dv[fin], rtol=1e-5, atol=1e-6 * case[4] + 1e-7 * abs(case[3]))
         found, hits = sc.intersect(q, d)
         assert np.array_equal(found.astype(bool), of.astype(bool)) and np.array_equal(bits(hits["t"]), bits(ot)), f"rays (wide_max_n={wide})"
+        assert np.array_equal(hits["prim"], op.astype(np.uint32)), "ray segment (the walk follows the reference's order: ties included)"
         found_t, hits_t = sc.intersect(q, d, t_max=tm)
         assert np.array_equal(found_t.astype(bool), of_t.astype(bool)) and np.array_equal(bits(hits_t["t"]), bits(ot_t))
+        assert np.array_equal(hits_t["prim"], op_t.astype(np.uint32))
         si, pdf, _ = sc.sample_in_sphere(sph, u)
         assert np.array_equal(si, oi) and np.array_equal(bits(pdf), bits(opdf)), f"sample (wide_max_n={wide})"

@@ -6,7 +6,7 @@ import pytest
 
 from conftest import small_cases
 from oracle import OracleScene
-from parity import bits, check_closest, check_rays, check_silhouette, check_silhouette_edges, rel_close
+from parity import check_rays_exact, bits, check_closest, check_rays, check_silhouette, check_silhouette_edges, rel_close
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -69,13 +69,15 @@ def test_closest_silhouette_edge_and_point(scene, meshes, flip):
     check_silhouette_edges(q, dist, edge, pt, orc, flip, r_max=rmax)
 
 
-@pytest.mark.parametrize("ray_kernel", [1, 2])  # 1: a batch this small takes k_intersect; 2: k_intersect_parked for every batch
+@pytest.mark.parametrize("ray_kernel", [0, 1, 2])  # 0: k_intersect (leaves where they are met); 1, 2: the reference-order walk (flush at 1 / 8 parked lanes)
 def test_rays_closest_hit(scene, ray_kernel):
     _, sc, orc, q, d = scene
     sc.set_option("query.ray_kernel", ray_kernel)
     found, hits = sc.intersect(q, d)
     sc.set_option("query.ray_kernel", 1)
     both = check_rays(found, hits, q, d, None, orc)
+    if ray_kernel:
+        check_rays_exact(found, hits, q, d, None, orc)  # the triangle too, ties included
     # the reported primitive really is hit at the reported t (ties between triangles sharing an edge are legal, Q4)
     f_b, t_b, _, _ = orc.ray(q[both], d[both], brute=True)
     assert rel_close(hits["t"][both], t_b).all()
