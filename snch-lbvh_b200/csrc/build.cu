@@ -403,9 +403,11 @@ SNCH_DI uint32_t refit_leaf(const BuildCtx &c, uint32_t k, Box &box, Cone &cone)
         float4 *le = reinterpret_cast<float4 *>(c.ledge + owned[s]);
         const bool boundary = !(has0 && has1);
         le[0] = make_float4(ea.x, ea.y, ea.z, eb.x);
-        le[1] = make_float4(eb.y, eb.z, boundary ? __int_as_float(0x7FC00000) : u0.x, u0.y);
+        le[1] = make_float4(eb.y, eb.z, u0.x, u0.y);
         le[2] = make_float4(u0.z, u1.x, u1.y, u1.z);
-        le[3] = make_float4(__int_as_float(owned[s]), 0.0f, 0.0f, 0.0f); // the edge's id: what out_edge of a silhouette query reports
+        // the edge's id (what out_edge of a silhouette query reports) and the boundary flag — a flag of its own: a zero-area face has
+        // a NaN normal, which the reference feeds to its silhouette test (-> "not a silhouette"), not a missing face
+        le[3] = make_float4(__int_as_float(owned[s]), __int_as_float(boundary ? 1 : 0), 0.0f, 0.0f);
         ++cnt;
     }
     if (cnt == 0) cone.half_angle = -kPi;

@@ -14,7 +14,7 @@ namespace snch
 {
 
 constexpr uint64_t kArenaMagic = 0x534e43484c425648ull; // "SNCHLBVH"
-constexpr uint32_t kArenaVersion = 4;
+constexpr uint32_t kArenaVersion = 5; // 5: LEdge carries its boundary flag in id.y (was: NaN in n0.x)
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
@@ -76,9 +76,9 @@ struct __align__(32) LTri // 64 B (two sectors, two 256-bit loads), Morton (leaf
 struct __align__(32) LEdge // 64 B, grouped by owning leaf in Morton order
 {
     float4 a; // pa.xyz pb.x
-    float4 b; // pb.y pb.z n0.x n0.y       n0.x = NaN  <=> boundary edge (fewer than two faces: always a silhouette)
+    float4 b; // pb.y pb.z n0.x n0.y       (unit normals; NaN for a zero-area face, 0 for a missing one)
     float4 c; // n0.z n1.xyz
-    float4 id; // x = edge id bits (index into scene<3>::silhouettes), yzw = 0
+    float4 id; // x = edge id bits (index into scene<3>::silhouettes), y = 1 (bits) for a boundary edge (fewer than two faces: always a silhouette), zw = 0
 };
 static_assert(sizeof(BNode) == 64 && sizeof(SNode) == 96 && sizeof(LTri) == 64 && sizeof(LEdge) == 64, "record sizes");
 

@@ -530,7 +530,7 @@ SNCH_DI bool leaf_silhouette(const SceneView &sv, uint32_t first, uint32_t cnt, 
         // scene.cuh:791 `if (min_radius_squared >= max_radius_squared) return false` with min = 0: a bound whose square is zero (a
         // star radius of 0: the query point lies on the surface) finds nothing, not even an edge at distance 0
         if (0.0f >= b2 || dist * dist > b2) continue;
-        bool is_sil = isnan(e1.z); // boundary edge
+        bool is_sil = __float_as_uint(e3.y) != 0u; // boundary edge
         if (!is_sil) is_sil = is_silhouette_edge(pa, pb, V3{e1.z, e1.w, e2.x}, V3{e2.y, e2.z, e2.w}, p - cp, dist, flip);
         if (is_sil && dist <= bound)
         {

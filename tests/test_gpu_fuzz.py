@@ -26,11 +26,11 @@ CASES = [
 
 
 def _extra_cases():
-    """SNCH_FUZZ_EXTRA=N adds N more soups with drawn parameters (seeds 101...): the long sweep of tools/gpu_fuzz_sweep.sh"""
+    """SNCH_FUZZ_EXTRA=N adds N more soups with drawn parameters (seeds SNCH_FUZZ_FIRST = 101 ...): the long sweep of tools/gpu_fuzz_sweep.sh"""
     import os
-    n = int(os.environ.get("SNCH_FUZZ_EXTRA", "0"))
+    n, first = int(os.environ.get("SNCH_FUZZ_EXTRA", "0")), int(os.environ.get("SNCH_FUZZ_FIRST", "101"))
     out = []
-    for seed in range(101, 101 + n):
+    for seed in range(first, first + n):
         rng = np.random.default_rng(seed)
         nv = int(rng.choice([5, 12, 40, 150, 600, 2500]))
         nt = int(nv * rng.choice([0.7, 1.5, 2.0, 4.0, 20.0])) + 4
@@ -109,6 +109,30 @@ def test_fuzz_rays(fuzz_scene, ray_kernel):
     check_rays_exact(found_t, hits_t, q, d, tm, orc)
 
 
+@pytest.mark.parametrize("reverse", [False, True])
+def test_zero_area_face_is_not_a_missing_face(pkg, meshes, reverse):
+    """A ZERO-AREA triangle D (three collinear vertices) whose three edges are each shared with a proper triangle: no edge of D
+    is a boundary edge, but each has a face whose normal is normalize(0) = NaN.  The reference's silhouette test then answers
+    "no" (every comparison with NaN is false), whereas an edge with a MISSING face is always a silhouette.  `reverse` flips D, which
+    moves the NaN between the edge's first and second face."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [1, 2, 0], [2, 0, 0], [1.5, -1, 0.5], [0.5, -1, -0.5]], np.float32)
+    d = [0, 1, 3] if reverse else [0, 3, 1]
+    f = np.array([d, [3, 0, 2], [1, 3, 4], [0, 1, 5]], np.int32)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    orc = OracleScene(v, f)
+    e4, _, _ = orc.adjacency()
+    if not reverse:
+        assert sum(1 for e in e4 if e[0] != -1 and e[3] != -1) >= 3  # D's three edges have two faces each (reversed: same-direction half-edges overwrite a slot, Q18)
+    check_build_vs_oracle(sc, orc, pkg)
+    q = meshes.points_in_box(6000, np.array([-0.2, -0.3, -0.3], np.float32), np.array([2.2, 0.3, 0.3], np.float32), 1.0, seed=5)  # around the line
+    for flip in (False, True):
+        check_silhouette(sc.closest_silhouette(q, flip=flip), orc.silhouette(q, flip, nthreads=4))
+        sc.set_option("query.wide_max_n_sil", 0)
+        check_silhouette(sc.closest_silhouette(q, flip=flip), orc.silhouette(q, flip, nthreads=4))
+        sc.set_option("query.wide_max_n_sil", 262144)
+    check_closest(q, *sc.closest_point(q), orc)
+
+
 def test_fuzz_sample(fuzz_scene, meshes):
     sc, orc, q, _, _ = fuzz_scene
     _, dcp = orc.closest(q, nthreads=8)
@@ -178,9 +202,9 @@ CASES2 = [
 
 def _extra_cases2():
     import os
-    n = int(os.environ.get("SNCH_FUZZ_EXTRA", "0"))
+    n, first = int(os.environ.get("SNCH_FUZZ_EXTRA", "0")), int(os.environ.get("SNCH_FUZZ_FIRST", "101")) + 100
     out = []
-    for seed in range(201, 201 + n):
+    for seed in range(first, first + n):
         rng = np.random.default_rng(seed)
         nv = int(rng.choice([4, 10, 60, 400, 3000]))
         ns = int(nv * rng.choice([0.8, 1.0, 2.0, 6.0])) + 3
