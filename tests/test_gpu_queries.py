@@ -16,11 +16,15 @@ def _mesh(meshes, name):
     cases = small_cases(meshes)
     if name in cases:
         return cases[name]
+    def moved(vf, offset, scale=1.0):  # a structured mesh far from the origin: every coordinate-sized quantity rounds at the offset's ulp
+        return (vf[0] * np.float32(scale) + np.asarray(offset, np.float32)).astype(np.float32), vf[1]
     return {"ico5": lambda: meshes.icosphere(5), "grid40": lambda: meshes.open_grid(40),
-            "torus200": lambda: meshes.bumpy_torus(200, 200)}[name]()
+            "torus200": lambda: meshes.bumpy_torus(200, 200),
+            "torus128_far": lambda: moved(meshes.bumpy_torus(128, 128), (1000.0, -2000.0, 500.0)),
+            "ico5_far_small": lambda: moved(meshes.icosphere(5), (100.0, 100.0, -100.0), 0.01)}[name]()
 
 
-@pytest.fixture(scope="module", params=["tet", "ico2", "grid6", "torus24x16", "ico5", "grid40", "torus200"])
+@pytest.fixture(scope="module", params=["tet", "ico2", "grid6", "torus24x16", "ico5", "grid40", "torus200", "torus128_far", "ico5_far_small"])
 def scene(request, pkg, meshes):
     v, f = _mesh(meshes, request.param)
     sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
@@ -53,7 +57,7 @@ def test_closest_silhouette_star_radius(scene, meshes):
     dist = sc.closest_silhouette(q, r_max=rmax)
     check_silhouette(dist, orc.silhouette(q, False, r_max=rmax, nthreads=8))
     unb = sc.closest_silhouette(q)
-    assert np.array_equal(bits(dist), bits(np.where(unb <= rmax, unb, np.inf).astype(np.float32)))
+    assert np.array_equal(bits(dist), bits(np.where((unb <= rmax) & (rmax * rmax > 0), unb, np.inf).astype(np.float32)))
 
 
 @pytest.mark.parametrize("flip", [False, True])
