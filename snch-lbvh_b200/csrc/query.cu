@@ -1556,7 +1556,11 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
     }
     unsigned long long *counter;
     const uint32_t *perm;
-    const int rc = prepare_batch(t, t.sort_rays != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3, 0, t.sort_rays >= 2 ? d : nullptr);
+    // "query.sort_rays" = -1 (default): rays are visited in Morton order of their origins when the traversal records (128 B per
+    // triangle) do not fit the 126 MB L2 — 16.7M rays: 7.38 -> 6.80 ms at 4M triangles, 13.5 -> 8.5 ms at 10M, but 5.12 -> 5.90 ms
+    // at 1M, where the ordering costs more than it returns (tools/c4_ray_exp.py, profiles/r2x_c4_ray_order.json)
+    const int sr = t.sort_rays >= 0 ? t.sort_rays : (v.n_tris >= (1u << 21) ? 1 : 0);
+    const int rc = prepare_batch(t, sr != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3, 0, sr >= 2 ? d : nullptr);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);
     launch_intersect_kernel(v, t, o, d, tmax, perm, (uint32_t)n, hits, found, any_hit != 0, counter, st, qc);
@@ -1641,6 +1645,7 @@ int launch_wost_step(const SceneView &v, const QueryTuning &t, const WostBuffers
     {
         SNCH_CUDA(cudaMemsetAsync(counter, 0, 8, st));
         TraversalTimer tt(qc, st);
+        // the walkers' Morton order is already there: the rays use it unless ordering is switched off ("query.sort_rays" = 0)
         launch_intersect_kernel(v, t, io.points, io.dirs, radius, t.sort_rays ? perm : nullptr, m, io.hits, io.found, false, counter, st, qc);
     }
     if (io.rnd && io.sample_index && io.sample_pdf)

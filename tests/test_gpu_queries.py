@@ -248,7 +248,7 @@ def test_results_do_not_depend_on_scheduling_knobs(pkg, meshes):
                 {"query.wide_max_n_sil": 1 << 30, "query.sort_min_n": 0},
                 {"query.sil_flush": 1}, {"query.sil_flush": 32}, {"query.sil_chunk": 8}, {"query.sil_chunk": 64}, {"query.sil_chunk": 32, "query.sil_tail": 0}, {"query.sil_flush": 12, "query.cone_filter": 0}, {"query.sil_tail": 0}, {"query.sil_tail": 31}, {"query.sil_tail": 31, "query.sort_min_n": 0}, {"query.sil_tail": 31, "query.cone_filter": 0},
                 {"query.sil_tail": 16, "query.blocks_per_sm": 1}, {"query.sort_radius": 1}, {"query.sort_radius": 2}, {"query.sort_radius": 3},
-                {"query.sort_rays": 1}, {"query.sort_rays": 2}, {"query.ray_kernel": 0}, {"query.ray_kernel": 1}, {"query.ray_kernel": 0, "query.sort_rays": 1},
+                {"query.sort_rays": 1}, {"query.sort_rays": 2}, {"query.sort_rays": -1}, {"query.ray_kernel": 0}, {"query.ray_kernel": 1}, {"query.ray_kernel": 0, "query.sort_rays": 1},
                 {"query.ray_flush": 1, "query.ray_refill": 1}, {"query.ray_flush": 32, "query.ray_refill": 32}, {"query.ray_flush": 16, "query.sort_rays": 1},
                 {"query.sort_bits": 12}, {"query.blocks_per_sm": 1},
                 {"query.host_chunk": 7001}, {"query.host_chunk": 0}, {"query.host_chunk": 500, "query.sort_min_n": 0},  # host-pointer pipeline
