@@ -9,4 +9,4 @@
 Only tests/, bench.py's baseline legs and __graft_entry__.smoke() may import this package.  The product
 (``snch-lbvh_b200``) never does and has no CPU fallback.
 """
-from .loader import RefScene, RefScene2, OracleScene, OracleScene2, FcpwScene, ref_available, oracle_lib, build_oracle, host_libm  # noqa: F401
+from .loader import RefScene, RefScene2, OracleScene, OracleScene2, FcpwScene, ref_available, oracle_lib, build_oracle, host_libm, restated_libm  # noqa: F401

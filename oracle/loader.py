@@ -26,7 +26,7 @@ def _i32(a):
 
 def build_oracle(with_ref: bool = True) -> None:
     """Compile liboracle.so (always) and, when /root/reference is present, oracle/_ref/*.so."""
-    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so"])
+    subprocess.check_call(["make", "-s", "-C", HERE, "liboracle.so", "libhostlibm.so"])
     if with_ref:
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
@@ -325,6 +325,19 @@ def host_libm(which: int, x) -> np.ndarray:
     x = _f32(x)
     out = np.empty_like(x)
     oracle_lib().orc_host_libm(which, x, x.size, out)
+    return out
+
+
+def restated_libm(which: int, x) -> np.ndarray:
+    """the HOST build of the product's restatement (include/snch_lbvh/core/host_libm.cuh `*_glibc`), element-wise"""
+    path = os.path.join(HERE, "libhostlibm.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", HERE, "libhostlibm.so"])
+    L = C.CDLL(path)
+    L.orc_restated_libm.argtypes = [C.c_int, _f32p, C.c_long, _f32p]
+    x = _f32(x)
+    out = np.empty_like(x)
+    L.orc_restated_libm(which, x, x.size, out)
     return out
 
 
