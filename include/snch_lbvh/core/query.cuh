@@ -176,7 +176,7 @@ SNCH_LBVH_DEVICE thrust::pair<unsigned int, Real> query_device(const detail::bas
     {
         Real d = calc_dist(q.target, bvh.objects[obj]);
         d *= d;
-        if (d < best2 || best_obj == detail::kNoObject)
+        if (d < best2 || (best_obj == detail::kNoObject && d <= best2)) // the first object at any distance up to +inf, never a NaN
         {
             best2 = d;
             best_obj = obj;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kQueryThreads)
         ld256(v.l2 + k, a, b);
         float d = dist_point_segment(make_float2(a.x, a.y), make_float2(a.z, a.w), p);
         d *= d;
-        if (d < best2 || best_obj == kNone)
+        if (d < best2 || (best_obj == kNone && d <= best2)) // the first object at any distance up to +inf (the reference's `<=`), never a NaN
         {
             best2 = d;
             best_obj = __float_as_uint(b.x);
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kQueryThreads)
                             ld256(v.l2 + (r & kRefIndex2), a, b);
                             float d = dist_point_segment(make_float2(a.x, a.y), make_float2(a.z, a.w), p);
                             d *= d;
-                            if ((d < b2 || bi == kNone) && __float_as_uint(d) < cand)
+                            if ((d < b2 || (bi == kNone && d <= b2)) && __float_as_uint(d) < cand)
                             {
                                 cand = __float_as_uint(d);
                                 cand_i = __float_as_uint(b.x);

@@ -183,6 +183,61 @@ def test_edge_cases(pkg, meshes):
     assert np.array_equal(found.astype(bool), f_o.astype(bool)) and rel_close(hits["t"], t_o).all()
 
 
+def test_nan_inf_and_huge_inputs(pkg, meshes):
+    """Query points, radii, directions and spheres that are NaN, infinite, huge, denormal or zero, mixed into an ordinary batch:
+    every kernel terminates and answers what the reference's comparisons answer (a NaN compares false everywhere), in the
+    one-query-per-warp kernels and in the large-batch ones (packets, leaf queue, parked rays), with and without batch ordering."""
+    from parity import same_bits
+    v, f = meshes.icosphere(3)
+    sc = pkg.Scene3(v, f).compute_silhouettes().build_bvh()
+    orc = OracleScene(v, f)
+    nan, inf = np.nan, np.inf
+    qs = np.array([[nan, 0, 0], [0, nan, 0], [nan, nan, nan], [inf, 0, 0], [-inf, 0, 0], [inf, inf, inf], [1e30, 0, 0], [3e38, 3e38, 3e38],
+                   [0, 0, 0], [1e-30, 0, 0], [1, 0, 0], [1e-45, -1e-45, 0]], np.float32)
+    ds = np.array([[0, 0, 0], [nan, 0, 1], [inf, 0, 0], [1, 0, 0], [0, 0, 1], [0, 1, 0], [-1, 0, 0], [1, 1, 1], [0, 0, inf], [nan, nan, nan], [-1, 0, 0],
+                   [1e-45, 0, 1]], np.float32)
+    rs = np.array([inf, nan, 1, 0, inf, 1, inf, inf, nan, 1, -1, 1e-30], np.float32)
+    n, k = 4096, len(qs)
+    q = meshes.points_in_box(n, *meshes.mesh_bounds(v), 1.5, seed=61)
+    d = meshes.unit_directions(n, seed=62)
+    rmax = (orc.closest(q, nthreads=8)[1] * meshes.star_radius_scale(n)).astype(np.float32)
+    at = np.arange(k) * 331 % n  # scattered through the batch
+    q[at], rmax[at] = qs, rs
+    d[at] = ds
+    q[at[3:6] + 1] = 0.3  # ordinary points with special directions / radii next to them
+    d[at[3:6] + 1], rmax[at[3:6] + 1] = ds[:3], rs[:3]
+    sph = np.concatenate([q, np.abs(rmax)[:, None] + 0.05], axis=1).astype(np.float32)
+    sph[at, 3] = np.array([1, 1, 1, 1, inf, 1, 1e30, inf, nan, 0, -1, 1e-30], np.float32)
+    rnd = meshes.uniforms(n, 3, seed=63)
+    o_dist = orc.closest(q, nthreads=8)[1]
+    o_sil = [orc.silhouette(q, False, nthreads=8), orc.silhouette(q, True, nthreads=8), orc.silhouette(q, False, r_max=rmax, nthreads=8)]
+    o_f, o_t, _, o_p = orc.ray(q, d, nthreads=8)
+    o_ft, o_tt, _, _ = orc.ray(q, d, rmax, nthreads=8)
+    o_si, o_pdf = orc.sample(sph, rnd[:, 0].copy())
+    try:
+        for knobs in ({}, {"query.wide_max_n": 0, "query.wide_max_n_sil": 0, "query.sort_min_n": 1, "query.ray_kernel": 2},
+                      {"query.wide_max_n": 0, "query.wide_max_n_sil": 0, "query.sort_min_n": 0, "query.ray_kernel": 0}):
+            for kk, val in {"query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144, "query.sort_min_n": 16384, "query.ray_kernel": 1, **knobs}.items():
+                sc.set_option(kk, val)
+            _, dist = sc.closest_point(q)
+            assert same_bits(dist, o_dist).all(), knobs
+            for got, want in zip([sc.closest_silhouette(q), sc.closest_silhouette(q, flip=True), sc.closest_silhouette(q, r_max=rmax)], o_sil):
+                assert same_bits(got, want).all(), knobs
+            found, hits = sc.intersect(q, d)
+            assert np.array_equal(found.astype(bool), o_f.astype(bool)) and same_bits(hits["t"], o_t).all(), knobs
+            if knobs.get("query.ray_kernel", 1):
+                assert np.array_equal(hits["prim"], o_p.astype(np.uint32)), knobs
+            found, hits = sc.intersect(q, d, t_max=rmax)
+            assert np.array_equal(found.astype(bool), o_ft.astype(bool)) and same_bits(hits["t"], o_tt).all(), knobs
+            si, pdf, _ = sc.sample_in_sphere(sph, rnd)
+            assert np.array_equal(si, o_si) and same_bits(pdf, o_pdf).all(), knobs
+            r = sc.wost_step(q, d, rnd)  # the fused step on the same inputs: terminates, and its closest distances are the same
+            assert same_bits(r["closest_distance"], o_dist).all(), knobs
+    finally:
+        for kk, val in {"query.wide_max_n": 2097152, "query.wide_max_n_sil": 262144, "query.sort_min_n": 16384, "query.ray_kernel": 1}.items():
+            sc.set_option(kk, val)
+
+
 def test_host_and_device_pointer_paths_agree(pkg, meshes):
     import torch
     v, f = meshes.bumpy_torus(64, 48)
