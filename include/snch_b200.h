@@ -187,7 +187,7 @@ int snch_wost_step_batch(const snch_scene *s, const snch_wost_io *io, uint64_t n
 /* Scheduling knobs of the batched kernels; results never depend on them (tests/test_gpu_queries.py sweeps them).
  *   "query.sort_min_n"  batches at least this large are visited in Morton order of the query points (default 16384; 0 = never)
  *   "query.sort_bits"   key bits of that ordering (8..30, default 24)
- *   "query.sort_rays"   ray batches: -1 = by tree size (default: Morton order of the origins from 2M triangles up, caller's order below),
+ *   "query.sort_rays"   ray batches: -1 = by size (default: Morton order of the origins for 4M rays or more on 2M triangles or more, caller's order otherwise),
  *                       0 = caller's order, 1 = Morton order of the origins, 2 = direction octant, then origin
  *   "query.cone_filter" silhouette normal-cone test: 0 = cone.cuh:168-212 verbatim; 1 = guard-banded sine-space evaluation on MUFU
  *                       approximations, the verbatim chain out of line for everything inside the band (default)

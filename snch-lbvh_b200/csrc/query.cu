@@ -1559,7 +1559,9 @@ int launch_intersect(const SceneView &v, const QueryTuning &t, const float *o, c
     // "query.sort_rays" = -1 (default): rays are visited in Morton order of their origins when the traversal records (128 B per
     // triangle) do not fit the 126 MB L2 — 16.7M rays: 7.38 -> 6.80 ms at 4M triangles, 13.5 -> 8.5 ms at 10M, but 5.12 -> 5.90 ms
     // at 1M, where the ordering costs more than it returns (tools/c4_ray_exp.py, profiles/r2x_c4_ray_order.json)
-    const int sr = t.sort_rays >= 0 ? t.sort_rays : (v.n_tris >= (1u << 21) ? 1 : 0);
+    // ... and the batch has 4M rays or more: a 2M-ray shard is latency-bound and the ordering's own launches cost what the better
+    // locality returns (1.47 ms in the caller's order, 1.53 ordered, per rank of the 8-GPU C4 run; a wash at 4.2M rays)
+    const int sr = t.sort_rays >= 0 ? t.sort_rays : ((v.n_tris >= (1u << 21) && n >= (1ull << 22)) ? 1 : 0);
     const int rc = prepare_batch(t, sr != 0, o, 3, nullptr, (uint32_t)n, scratch, st, &counter, &perm, qc, 3, 0, sr >= 2 ? d : nullptr);
     if (rc != SNCH_OK) return rc;
     TraversalTimer tt(qc, st);

@@ -18,8 +18,8 @@ struct QueryTuning
     int sort_radius = 2;    // bounded silhouette batches: 1 = order by search-radius octave first, then Morton code;
                             // 2 = the same with the largest radii first (longest walks start first, the tail is made of cheap queries);
                             // 3, 4 = largest first with 2 / 4 classes per octave
-    int sort_rays = -1;     // ray batches: -1 = Morton order of the origins when the tree has 2M triangles or more (its records exceed L2),
-                            // caller's order below (at 1M triangles ordering costs more than it returns); 0 = caller's order,
+    int sort_rays = -1;     // ray batches: -1 = Morton order of the origins when the tree has 2M triangles or more (its records exceed L2) and the
+                            // batch 4M rays or more, caller's order otherwise (at 1M triangles ordering costs more than it returns); 0 = caller's order,
                             // 1 = Morton order of the origins, 2 = direction octant, then origin
     int cone_filter = 1;    // silhouette normal-cone test: 0 = the reference's libm chain verbatim, 1 = guard-banded sine-space filter on
                             // MUFU approximations with the exact chain out of line (decisions identical; 52.3 vs 69 ms on C3)
